@@ -1,0 +1,139 @@
+/*
+ * tr_b200.h — C ABI of libtrb200.so: the CP (Kruskal) tensor-regression fit iteration
+ * (forward contraction, residual-weighted MTTKRP gradients, penalty + Adam update) as
+ * hand-written sm_100a CUDA kernels.
+ *
+ * The reference (kimerein/tensor_regression) has no FFI: its boundary for this path is the
+ * Python surface of standard_tensor_regression.py / multinomial_tensor_regression.py.  Each
+ * entry point below names the reference lines whose work it replaces; the Python modules in
+ * tensor_regression_b200/ keep the reference's signatures and call these through ctypes
+ * (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked host;
+ *   - the caller owns every buffer; the library owns only the opaque handle + its workspace;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises
+ *     the device except tr_create / tr_reserve / tr_destroy (allocation);
+ *   - every function returns 0 on success, non-zero on error (TR_ERR_*); the message is
+ *     available from tr_last_error(); no exceptions cross the boundary;
+ *   - there is no CPU fallback: without a CUDA device tr_create fails.
+ *   - dtype: TR_F32 / TR_F64 is the type of X, theta, w, y (std), the predictions and `grad`.
+ *     `gradsum` and `loss` are always double.
+ *
+ * Parameter vector layout (theta, grad, Adam state), row-major (I_m, R) blocks:
+ *     theta = [ F_0 | F_1 | ... | F_{k-1} | F_C (multinomial only, (C,R)) | bias (standard only) ]
+ * which is the reference's Kruskal list `Bcp` (README.md:12-13,21-22; mn:280) laid end to end.
+ * Pf = R * (sum_m I_m + C) is the number of factor entries; P = Pf + (C == 0 ? 1 : 0).
+ *
+ * gradsum layout (unnormalised LOCAL sums over the N samples of this call — the vector one
+ * NCCL all-reduce sums across GPUs when the sample axis is sharded):
+ *     standard   : [ dFt (Pf) | sum_n res_n | sum_n res_n^2 ]                 (Pf + 2 doubles)
+ *     multinomial: [ dFt (Pf, class factor last) | sum_n -omega[y_n] log Q[n,y_n] ]   (Pf + 1)
+ * where dFt is the derivative with respect to the softplus-ed factors before the 2/N (or
+ * 1/W) normalisation, res_n = yhat_n - y_n.
+ */
+#ifndef TR_B200_H
+#define TR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TR_B200_VERSION 100
+
+enum { TR_F32 = 0, TR_F64 = 1 };
+enum { TR_OK = 0, TR_ERR_INVALID = 1, TR_ERR_CUDA = 2, TR_ERR_UNSUPPORTED = 3, TR_ERR_NOMEM = 4 };
+
+#define TR_MAX_MODES 8      /* feature modes of X (k) */
+#define TR_MAX_CLASSES 128  /* multinomial classes */
+
+typedef struct tr_handle tr_handle;
+
+int tr_version(void);
+
+/* Plan for one model geometry.  dims = host array of the k feature-mode sizes (X.shape[1:]),
+ * R = CP rank, C = 0 for the standard model, n_classes for the multinomial model.
+ * Replaces the geometry bookkeeping of CP_linear_regression.__init__ (std:204-303) and
+ * CP_logistic_regression.__init__ (mn:212-286). */
+int tr_create(tr_handle** out, int dtype, int k, const int64_t* dims, int R, int C, int device);
+int tr_destroy(tr_handle* h);
+
+/* Last error message of this handle (h may be NULL: message of the last failed tr_create). */
+const char* tr_last_error(tr_handle* h);
+
+/* P (all trainable scalars, incl. bias for the standard model) and Pf (factor entries). */
+int tr_param_count(tr_handle* h, int64_t* P, int64_t* Pf);
+
+/* Number of doubles in gradsum (Pf + 2 standard, Pf + 1 multinomial). */
+int tr_gradsum_count(tr_handle* h, int64_t* count);
+
+/* Pre-allocate the workspace for calls with up to N samples (otherwise grown on demand by the
+ * first call that needs it, which then synchronises once). */
+int tr_reserve(tr_handle* h, int64_t N);
+
+/* Forward only — lin_model (std:87-130): yhat[n] = <X_n, cp_to_tensor(w, softplus?(F))> + bias.
+ * X: (N, I_1..I_k) row-major contiguous; yhat: (N).  nn_mask bit m = softplus on factor m
+ * (non_neg_fn, std:53-85) with torch.nn.functional.softplus(beta, threshold) semantics. */
+int tr_forward_std(tr_handle* h, const void* X, int64_t N, const void* theta, const void* w,
+                   uint32_t nn_mask, double sp_beta, double sp_thr, void* yhat, void* stream);
+
+/* Forward only — model (mn:148-187): P[n,:] = softmax(<X_n, cp_to_tensor(w, F incl. class factor)>).
+ * P: (N, C).  pred (int64, N) may be NULL; otherwise argmax_c P[n,c] (predict, mn:526-527). */
+int tr_forward_mn(tr_handle* h, const void* X, int64_t N, const void* theta, const void* w,
+                  uint32_t nn_mask, double sp_beta, double sp_thr, void* P, int64_t* pred, void* stream);
+
+/* One closure evaluation without the penalty and normalisation (std:368-373 / 459-462):
+ * forward, residual, and all per-mode residual-weighted MTTKRP gradients in two streaming
+ * passes over X.  y: (N) same dtype as X.  yhat may be NULL. */
+int tr_fwd_grad_std(tr_handle* h, const void* X, const void* y, int64_t N, const void* theta,
+                    const void* w, uint32_t nn_mask, double sp_beta, double sp_thr,
+                    double* gradsum, void* yhat, void* stream);
+
+/* Same for the multinomial model (mn:357-362 / 454-457): softmax, the reference's SECOND
+ * softmax inside CrossEntropyLoss (mn:364-366), class-weighted CE, dZ, and all factor
+ * gradients incl. the class factor.  y: int64 (N) in [0,C); class_w: (C) of dtype.  P may be NULL. */
+int tr_fwd_grad_mn(tr_handle* h, const void* X, const int64_t* y, const void* class_w, int64_t N,
+                   const void* theta, const void* w, uint32_t nn_mask, double sp_beta, double sp_thr,
+                   double* gradsum, void* P, void* stream);
+
+/* Vector-Jacobian product of lin_model for an arbitrary upstream gradient dyhat (N) — what
+ * autograd's MmBackward0 + the cp_to_tensor backward compute (std:372,462).  Writes
+ * gradsum = [ dFt | sum_n dyhat_n | 0 ]. */
+int tr_backward_std(tr_handle* h, const void* X, const void* dyhat, int64_t N, const void* theta,
+                    const void* w, uint32_t nn_mask, double sp_beta, double sp_thr,
+                    double* gradsum, void* stream);
+
+/* gradsum (after the cross-GPU sum, if any) -> gradient wrt the RAW parameters and the losses:
+ *   grad[F_m] = grad_scale * dFt_m * softplus'(F_m) + lambda_L2 * F_m / ||F_m||_F   (L2_penalty, std:180-196)
+ *   grad[bias] = grad_scale * gradsum[Pf]            (standard only)
+ *   loss[0] = loss_scale * gradsum[last]  (MSE or CE),  loss[1] = loss[0] + lambda_L2 * sum_m ||F_m||_F
+ * grad_scale = 2/N_total, loss_scale = 1/N_total (standard); both 1/sum_n omega[y_n] (multinomial). */
+int tr_finish_grad(tr_handle* h, const double* gradsum, double grad_scale, double loss_scale,
+                   const void* theta, double lambda_L2, uint32_t nn_mask, double sp_beta, double sp_thr,
+                   void* grad, double* loss, void* stream);
+
+/* torch.optim.Adam step (std:453,463 / mn:447,458; torch/optim/adam.py single-tensor path) on
+ * the flat parameter vector.  step is 1-based.  vmax may be NULL (amsgrad off). */
+int tr_adam_step(tr_handle* h, void* theta, const void* grad, void* m, void* v, void* vmax,
+                 int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
+                 void* stream);
+
+/* Optional timing of the two streaming kernels with CUDA events recorded on the launching stream
+ * (what bench.py's roofline uses).  tr_profile_enable(h, 1) resets the sums; tr_profile_read waits
+ * for the last recorded launch and returns out4 = { forward-pass ms total, forward launches,
+ * gradient-pass ms total, gradient launches } (host doubles). */
+int tr_profile_enable(tr_handle* h, int enable);
+int tr_profile_read(tr_handle* h, double* out4);
+
+/* How the last tr_fwd_grad_* / tr_forward_* call was executed (host ints):
+ * info[0]=kernel launches, [1]=forward grid, [2]=gradient grid, [3]=tiles per sample,
+ * [4]=sample groups (forward), [5]=sample groups (gradient), [6]=channels RK, [7]=vector width. */
+int tr_last_launch_info(tr_handle* h, int64_t* info8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TR_B200_H */

@@ -1,0 +1,56 @@
+"""ctypes binding of libtrb200.so (include/tr_b200.h).  No torch types cross this boundary:
+raw device pointers, sizes and a cudaStream_t."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtrb200.so')
+
+TR_F32, TR_F64 = 0, 1
+
+SYMBOLS = [
+    'tr_version', 'tr_create', 'tr_destroy', 'tr_last_error', 'tr_param_count', 'tr_gradsum_count',
+    'tr_reserve', 'tr_forward_std', 'tr_forward_mn', 'tr_fwd_grad_std', 'tr_fwd_grad_mn',
+    'tr_backward_std', 'tr_finish_grad', 'tr_adam_step', 'tr_last_launch_info', 'tr_profile_enable',
+    'tr_profile_read',
+]
+
+
+class TRError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise TRError(
+            f'{LIB_PATH} not found: the CUDA extension is not built. Run '
+            f'`python -c "import __graft_entry__ as g; g.build()"` or '
+            f'`tensor_regression_b200/csrc/build.sh`. There is no CPU fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32, u32, dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_uint32, ctypes.c_double
+    lib.tr_version.restype = i32
+    lib.tr_create.argtypes = [ctypes.POINTER(vp), i32, i32, ctypes.POINTER(i64), i32, i32, i32]
+    lib.tr_destroy.argtypes = [vp]
+    lib.tr_last_error.argtypes = [vp]
+    lib.tr_last_error.restype = ctypes.c_char_p
+    lib.tr_param_count.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.tr_gradsum_count.argtypes = [vp, ctypes.POINTER(i64)]
+    lib.tr_reserve.argtypes = [vp, i64]
+    lib.tr_forward_std.argtypes = [vp, vp, i64, vp, vp, u32, dbl, dbl, vp, vp]
+    lib.tr_forward_mn.argtypes = [vp, vp, i64, vp, vp, u32, dbl, dbl, vp, vp, vp]
+    lib.tr_fwd_grad_std.argtypes = [vp, vp, vp, i64, vp, vp, u32, dbl, dbl, vp, vp, vp]
+    lib.tr_fwd_grad_mn.argtypes = [vp, vp, vp, vp, i64, vp, vp, u32, dbl, dbl, vp, vp, vp]
+    lib.tr_backward_std.argtypes = [vp, vp, vp, i64, vp, vp, u32, dbl, dbl, vp, vp]
+    lib.tr_finish_grad.argtypes = [vp, vp, dbl, dbl, vp, dbl, u32, dbl, dbl, vp, vp, vp]
+    lib.tr_adam_step.argtypes = [vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, dbl, dbl, vp]
+    lib.tr_last_launch_info.argtypes = [vp, ctypes.POINTER(i64)]
+    lib.tr_profile_enable.argtypes = [vp, i32]
+    lib.tr_profile_read.argtypes = [vp, ctypes.POINTER(dbl)]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if name not in ('tr_last_error',):
+            fn.restype = i32
+    return lib
+
+
+lib = _load()

@@ -1,0 +1,629 @@
+// tr_api.cu — C ABI (include/tr_b200.h) over the kernels in tr_kernels.cuh.
+// Host-side planning only: tile / sample-group geometry, workspace, kernel dispatch, launches.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "tr_kernels.cuh"
+#include "tr_dispatch.h"
+#include "tr_small.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+// streaming-kernel tables are compiled in separate translation units (tr_stream.cu, one per
+// TR_PART) so the build parallelises; merged here on first use.
+template <typename T> std::vector<KEntry<T>>& merged();
+template <> std::vector<KEntry<float>>& merged<float>() {
+    static std::vector<KEntry<float>> v = [] {
+        std::vector<KEntry<float>> t;
+        int n; const KEntry<float>* p;
+        p = tr_entries_f32_0(&n); t.insert(t.end(), p, p + n);
+        p = tr_entries_f32_1(&n); t.insert(t.end(), p, p + n);
+        p = tr_entries_f32_2(&n); t.insert(t.end(), p, p + n);
+        p = tr_entries_f32_3(&n); t.insert(t.end(), p, p + n);
+        std::sort(t.begin(), t.end(), [](const KEntry<float>& a, const KEntry<float>& b) { return a.RK < b.RK; });
+        return t;
+    }();
+    return v;
+}
+template <> std::vector<KEntry<double>>& merged<double>() {
+    static std::vector<KEntry<double>> v = [] {
+        std::vector<KEntry<double>> t;
+        int n; const KEntry<double>* p;
+        p = tr_entries_f64_0(&n); t.insert(t.end(), p, p + n);
+        p = tr_entries_f64_1(&n); t.insert(t.end(), p, p + n);
+        p = tr_entries_f64_2(&n); t.insert(t.end(), p, p + n);
+        p = tr_entries_f64_3(&n); t.insert(t.end(), p, p + n);
+        std::sort(t.begin(), t.end(), [](const KEntry<double>& a, const KEntry<double>& b) { return a.RK < b.RK; });
+        return t;
+    }();
+    return v;
+}
+
+template <typename T>
+const KEntry<T>* pick_entry(int rk) {
+    for (const KEntry<T>& e : merged<T>())
+        if (e.RK >= rk) return &e;
+    return nullptr;
+}
+
+struct Plan {
+    int RKs;            // instantiated channel count (>= needed)
+    int tile;           // elements per warp tile
+    int WT;             // warp tiles per sample
+    long long Dpad;
+    int Gn_f, grid_f;
+    int Gn_g, grid_g;
+    int nchunk;
+    long long spc;
+    int vec;            // 1 = 16-byte loads, 0 = element loads
+    size_t smem_f;
+};
+
+}  // namespace
+
+struct tr_handle {
+    int dtype = 0, device = 0, sms = 0;
+    size_t elt = 4;
+    Geo geo;
+    std::string err;
+    std::map<const void*, int> occ;     // kernel -> resident blocks per SM
+    Buf FtT, Ft64, partial, V, u_ws, dZ_ws, Gpart, Gred, epi_part, dfc_part;
+    long long info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int launches = 0;
+    // optional in-stream timing of the two streaming kernels (tr_profile_*)
+    bool prof = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fwd begin/end, grad begin/end
+    bool ev_set[2] = {false, false};
+    double prof_ms[2] = {0.0, 0.0};
+    long long prof_n[2] = {0, 0};
+};
+
+namespace {
+
+int fail(tr_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define TR_CUDA(h, call)                                                                          \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(h, TR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+
+int ensure(tr_handle* h, Buf& b, size_t bytes) {
+    if (bytes <= b.cap) return TR_OK;
+    if (b.p) { TR_CUDA(h, cudaDeviceSynchronize()); TR_CUDA(h, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    const size_t want = bytes + bytes / 16 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(h, TR_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e)); }
+    b.cap = want;
+    return TR_OK;
+}
+
+template <typename K>
+int occupancy(tr_handle* h, K kern, size_t smem, int* out) {
+    const void* key = (const void*)kern;
+    auto it = h->occ.find(key);
+    if (it != h->occ.end()) { *out = it->second; return TR_OK; }
+    if (smem > 48 * 1024) TR_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    TR_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, TR_TPB, smem));
+    if (nb < 1) return fail(h, TR_ERR_UNSUPPORTED, "kernel does not fit on an SM (dynamic smem %zu bytes)", smem);
+    h->occ[key] = nb;
+    *out = nb;
+    return TR_OK;
+}
+
+template <typename T>
+int make_plan(tr_handle* h, long long N, int rk_needed, bool vec, Plan* pl, const KEntry<T>** ent) {
+    const KEntry<T>* e = pick_entry<T>(rk_needed);
+    if (!e) return fail(h, TR_ERR_UNSUPPORTED, "rank %d exceeds the %d channels the streaming kernels are built for", rk_needed, TR_MAX_RANK_MN);
+    *ent = e;
+    pl->RKs = e->RK;
+    pl->vec = vec ? 1 : 0;
+    pl->tile = 32 * e->E * VN<T>::v;
+    const long long D = h->geo.D;
+    pl->WT = (int)((D + pl->tile - 1) / pl->tile);
+    pl->Dpad = (long long)pl->WT * pl->tile;
+    pl->smem_f = (size_t)(h->geo.pfeat + h->geo.R) * sizeof(T);
+    if (pl->smem_f > 200 * 1024)
+        return fail(h, TR_ERR_UNSUPPORTED, "factor rows (%zu bytes) do not fit in shared memory", pl->smem_f);
+    int occ_f = 0, occ_g = 0, rc;
+    if ((rc = occupancy(h, vec ? e->fwd_vec : e->fwd_sc, pl->smem_f, &occ_f))) return rc;
+    if ((rc = occupancy(h, vec ? e->grad_vec : e->grad_sc, 0, &occ_g))) return rc;
+    auto groups = [&](int occ, int* Gn, int* grid) {
+        const long long wtot = (long long)h->sms * occ * TR_WPB;
+        if (pl->WT <= wtot) {
+            long long g = wtot / pl->WT;
+            if (g > N) g = N;
+            if (g < 1) g = 1;
+            *Gn = (int)g;
+            *grid = (int)(((long long)pl->WT * g + TR_WPB - 1) / TR_WPB);
+        } else {
+            *Gn = 1;
+            *grid = h->sms * occ;
+        }
+    };
+    groups(occ_f, &pl->Gn_f, &pl->grid_f);
+    groups(occ_g, &pl->Gn_g, &pl->grid_g);
+    // bound the length of each fp32 running sum in the gradient pass
+    const long long Sg = (N + pl->Gn_g - 1) / pl->Gn_g;
+    const long long target = sizeof(T) == 4 ? 2048 : (1LL << 40);
+    long long nchunk = std::max<long long>(1, (Sg + target - 1) / target);
+    const size_t slot_bytes = (size_t)pl->RKs * (size_t)pl->Dpad * sizeof(T);
+    const size_t cap_bytes = (size_t)1 << 30;
+    while (nchunk > 1 && (size_t)nchunk * pl->Gn_g * slot_bytes > cap_bytes) --nchunk;
+    pl->nchunk = (int)nchunk;
+    pl->spc = std::max<long long>(1, (Sg + nchunk - 1) / nchunk);
+    return TR_OK;
+}
+
+template <typename T>
+int reserve_for(tr_handle* h, long long N, const Plan& pl) {
+    int rc;
+    const Geo& g = h->geo;
+    if ((rc = ensure(h, h->FtT, (size_t)g.pf * sizeof(T)))) return rc;
+    if ((rc = ensure(h, h->Ft64, (size_t)g.pf * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->partial, (size_t)N * pl.WT * pl.RKs * sizeof(T)))) return rc;
+    if ((rc = ensure(h, h->V, (size_t)N * pl.RKs * sizeof(T)))) return rc;
+    if (g.C > 0) {
+        if ((rc = ensure(h, h->u_ws, (size_t)N * g.R * sizeof(T)))) return rc;
+        if ((rc = ensure(h, h->dZ_ws, (size_t)N * g.C * sizeof(T)))) return rc;
+        if ((rc = ensure(h, h->dfc_part, (size_t)h->sms * 2 * g.C * g.R * sizeof(double)))) return rc;
+    }
+    if ((rc = ensure(h, h->Gpart, (size_t)pl.nchunk * pl.Gn_g * pl.RKs * pl.Dpad * sizeof(T)))) return rc;
+    if ((rc = ensure(h, h->Gred, (size_t)pl.RKs * g.D * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->epi_part, (size_t)h->sms * 8 * 2 * sizeof(double)))) return rc;
+    return TR_OK;
+}
+
+inline bool vec_ok(const void* X, long long D, size_t elt) {
+    return ((uintptr_t)X % 16 == 0) && ((D * (long long)elt) % 16 == 0);
+}
+
+#define TR_LAUNCH_CHECK(h)                                                                        \
+    do {                                                                                          \
+        cudaError_t e_ = cudaPeekAtLastError();                                                   \
+        if (e_ != cudaSuccess) { cudaGetLastError(); return fail(h, TR_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); } \
+        ++(h)->launches;                                                                          \
+    } while (0)
+
+// Adds the elapsed time of the previous (already finished) recorded launches to the running sums.
+int prof_fold(tr_handle* h, bool wait) {
+    for (int i = 0; i < 2; ++i) {
+        if (!h->ev_set[i]) continue;
+        if (wait) TR_CUDA(h, cudaEventSynchronize(h->ev[2 * i + 1]));
+        else if (cudaEventQuery(h->ev[2 * i + 1]) != cudaSuccess) { cudaGetLastError(); TR_CUDA(h, cudaEventSynchronize(h->ev[2 * i + 1])); }
+        float ms = 0.f;
+        TR_CUDA(h, cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]));
+        h->prof_ms[i] += ms;
+        h->prof_n[i] += 1;
+        h->ev_set[i] = false;
+    }
+    return TR_OK;
+}
+
+// prep + pass 1 (+ nothing else): fills h->partial
+template <typename T>
+int run_forward(tr_handle* h, const T* X, long long N, const T* theta, const T* w, uint32_t nn_mask,
+                double beta, double thr, const Plan& pl, const KEntry<T>* e, cudaStream_t st) {
+    const Geo& g = h->geo;
+    k_prep<T><<<std::max(1, std::min(64, (g.pf + 255) / 256)), 256, 0, st>>>(theta, g, nn_mask, beta, thr,
+                                                                           (T*)h->FtT.p, (double*)h->Ft64.p);
+    TR_LAUNCH_CHECK(h);
+    FwdArgs<T> fa;
+    fa.X = X; fa.N = N; fa.FtT = (const T*)h->FtT.p; fa.w = w; fa.geo = g;
+    fa.partial = (T*)h->partial.p; fa.WT = pl.WT; fa.Gn = pl.Gn_f; fa.mode = g.C > 0 ? 1 : 0;
+    auto kern = pl.vec ? e->fwd_vec : e->fwd_sc;
+    if (h->prof) { int rc = prof_fold(h, false); if (rc) return rc; TR_CUDA(h, cudaEventRecord(h->ev[0], st)); }
+    kern<<<pl.grid_f, TR_TPB, pl.smem_f, st>>>(fa);
+    TR_LAUNCH_CHECK(h);
+    if (h->prof) { TR_CUDA(h, cudaEventRecord(h->ev[1], st)); h->ev_set[0] = true; }
+    return TR_OK;
+}
+
+// pass 2 + reduction + all-mode MTTKRP: consumes V (N, RKs), fills gradsum[0 .. pfeat)
+template <typename T>
+int run_gradient(tr_handle* h, const T* X, long long N, const T* V, const T* w, const Plan& pl,
+                 const KEntry<T>* e, double* gradsum, cudaStream_t st) {
+    const Geo& g = h->geo;
+    GradArgs<T> ga;
+    ga.X = X; ga.N = N; ga.D = g.D; ga.V = V; ga.Gpart = (T*)h->Gpart.p; ga.Dpad = pl.Dpad;
+    ga.WT = pl.WT; ga.Gn = pl.Gn_g; ga.nchunk = pl.nchunk; ga.spc = pl.spc;
+    auto kern = pl.vec ? e->grad_vec : e->grad_sc;
+    if (h->prof) TR_CUDA(h, cudaEventRecord(h->ev[2], st));
+    kern<<<pl.grid_g, TR_TPB, 0, st>>>(ga);
+    TR_LAUNCH_CHECK(h);
+    if (h->prof) { TR_CUDA(h, cudaEventRecord(h->ev[3], st)); h->ev_set[1] = true; }
+    const long long tot = (long long)pl.RKs * g.D;
+    const int rgrid = (int)std::min<long long>((tot + 255) / 256, (long long)h->sms * 8);
+    k_reduce_G<T><<<rgrid, 256, 0, st>>>((const T*)h->Gpart.p, pl.nchunk * pl.Gn_g, pl.RKs, g.D, pl.Dpad,
+                                         (double*)h->Gred.p);
+    TR_LAUNCH_CHECK(h);
+    MtArgs ma;
+    ma.G = (const double*)h->Gred.p; ma.Ft64 = (const double*)h->Ft64.p; ma.w = w;
+    ma.w_is_f64 = sizeof(T) == 8; ma.per_rank = g.C > 0 ? 1 : 0; ma.geo = g; ma.gradsum = gradsum;
+    int rows = 0;
+    for (int m = 0; m < g.k; ++m) rows += g.dims[m];
+    k_mttkrp<<<rows, TR_TPB, 0, st>>>(ma);
+    TR_LAUNCH_CHECK(h);
+    return TR_OK;
+}
+
+void set_info(tr_handle* h, const Plan& pl) {
+    h->info[0] = h->launches; h->info[1] = pl.grid_f; h->info[2] = pl.grid_g; h->info[3] = pl.WT;
+    h->info[4] = pl.Gn_f; h->info[5] = pl.Gn_g; h->info[6] = pl.RKs; h->info[7] = pl.vec ? (int)(16 / h->elt) : 1;
+}
+
+template <typename T>
+int forward_std_t(tr_handle* h, const void* X, long long N, const void* theta, const void* w, uint32_t nn_mask,
+                  double beta, double thr, void* yhat, cudaStream_t st) {
+    Plan pl; const KEntry<T>* e; int rc;
+    if ((rc = make_plan<T>(h, N, 1, vec_ok(X, h->geo.D, sizeof(T)), &pl, &e))) return rc;
+    if ((rc = reserve_for<T>(h, N, pl))) return rc;
+    h->launches = 0;
+    if ((rc = run_forward<T>(h, (const T*)X, N, (const T*)theta, (const T*)w, nn_mask, beta, thr, pl, e, st))) return rc;
+    EpiStdArgs<T> ea;
+    ea.partial = (const T*)h->partial.p; ea.WT = pl.WT; ea.N = N; ea.theta = (const T*)theta;
+    ea.bias_off = h->geo.pf; ea.y = nullptr; ea.yhat = (T*)yhat; ea.V = nullptr; ea.part = nullptr;
+    const int egrid = (int)std::min<long long>((N + TR_WPB - 1) / TR_WPB, (long long)h->sms * 8);
+    k_epi_std<T><<<egrid, TR_TPB, 0, st>>>(ea);
+    TR_LAUNCH_CHECK(h);
+    set_info(h, pl);
+    return TR_OK;
+}
+
+template <typename T>
+int fwd_grad_std_t(tr_handle* h, const void* X, const void* y, long long N, const void* theta, const void* w,
+                   uint32_t nn_mask, double beta, double thr, double* gradsum, void* yhat, cudaStream_t st,
+                   bool backward_only) {
+    Plan pl; const KEntry<T>* e; int rc;
+    const Geo& g = h->geo;
+    if ((rc = make_plan<T>(h, N, 1, vec_ok(X, g.D, sizeof(T)), &pl, &e))) return rc;
+    if ((rc = reserve_for<T>(h, N, pl))) return rc;
+    h->launches = 0;
+    const int egrid = (int)std::min<long long>((N + TR_WPB - 1) / TR_WPB, (long long)h->sms * 8);
+    const T* V;
+    if (!backward_only) {
+        if ((rc = run_forward<T>(h, (const T*)X, N, (const T*)theta, (const T*)w, nn_mask, beta, thr, pl, e, st))) return rc;
+        EpiStdArgs<T> ea;
+        ea.partial = (const T*)h->partial.p; ea.WT = pl.WT; ea.N = N; ea.theta = (const T*)theta;
+        ea.bias_off = g.pf; ea.y = (const T*)y; ea.yhat = (T*)yhat; ea.V = (T*)h->V.p; ea.part = (double*)h->epi_part.p;
+        k_epi_std<T><<<egrid, TR_TPB, 0, st>>>(ea);
+        TR_LAUNCH_CHECK(h);
+        // gradsum[pf] = sum res, gradsum[pf+1] = sum res^2
+        k_colsum<<<1, 32, 0, st>>>((const double*)h->epi_part.p, egrid, 2, gradsum + g.pf);
+        TR_LAUNCH_CHECK(h);
+        V = (const T*)h->V.p;
+    } else {
+        // y carries the upstream gradient dyhat; prep is still needed for the MTTKRP factors
+        k_prep<T><<<std::max(1, std::min(64, (g.pf + 255) / 256)), 256, 0, st>>>((const T*)theta, g, nn_mask, beta, thr,
+                                                                               (T*)h->FtT.p, (double*)h->Ft64.p);
+        TR_LAUNCH_CHECK(h);
+        V = (const T*)y;
+        k_vecsum<T><<<1, 1024, 0, st>>>(V, N, gradsum + g.pf);
+        TR_LAUNCH_CHECK(h);
+        TR_CUDA(h, cudaMemsetAsync(gradsum + g.pf + 1, 0, sizeof(double), st));
+    }
+    if ((rc = run_gradient<T>(h, (const T*)X, N, V, (const T*)w, pl, e, gradsum, st))) return rc;
+    set_info(h, pl);
+    return TR_OK;
+}
+
+template <typename T>
+int mn_t(tr_handle* h, const void* X, const long long* y, const void* class_w, long long N, const void* theta,
+         const void* w, uint32_t nn_mask, double beta, double thr, double* gradsum, void* P, long long* pred,
+         cudaStream_t st) {
+    Plan pl; const KEntry<T>* e; int rc;
+    const Geo& g = h->geo;
+    if ((rc = make_plan<T>(h, N, g.R, vec_ok(X, g.D, sizeof(T)), &pl, &e))) return rc;
+    if ((rc = reserve_for<T>(h, N, pl))) return rc;
+    h->launches = 0;
+    if ((rc = run_forward<T>(h, (const T*)X, N, (const T*)theta, (const T*)w, nn_mask, beta, thr, pl, e, st))) return rc;
+    const bool train = (y != nullptr);
+    EpiMnArgs<T> ea;
+    ea.partial = (const T*)h->partial.p; ea.WT = pl.WT; ea.RKs = pl.RKs; ea.N = N; ea.R = g.R; ea.C = g.C;
+    ea.FC = (const double*)h->Ft64.p + g.pfeat; ea.w = (const T*)w; ea.y = y; ea.class_w = (const T*)class_w;
+    ea.P = (T*)P; ea.pred = pred;
+    ea.V = train ? (T*)h->V.p : nullptr; ea.u_ws = train ? (T*)h->u_ws.p : nullptr;
+    ea.dZ_ws = train ? (T*)h->dZ_ws.p : nullptr; ea.part = train ? (double*)h->epi_part.p : nullptr;
+    const int egrid = (int)std::min<long long>((N + TR_WPB - 1) / TR_WPB, (long long)h->sms * 8);
+    const size_t esmem = (size_t)(g.C * g.R + g.R) * sizeof(double);
+    k_epi_mn<T><<<egrid, TR_TPB, esmem, st>>>(ea);
+    TR_LAUNCH_CHECK(h);
+    if (train) {
+        k_colsum<<<1, 32, 0, st>>>((const double*)h->epi_part.p, egrid, 1, gradsum + g.pf);
+        TR_LAUNCH_CHECK(h);
+        const int dgrid = (int)std::min<long long>((N + 63) / 64, (long long)h->sms * 2);
+        k_dfc<T><<<dgrid, TR_TPB, 0, st>>>((const T*)h->dZ_ws.p, (const T*)h->u_ws.p, (const T*)w, N, g.C, g.R,
+                                           (double*)h->dfc_part.p);
+        TR_LAUNCH_CHECK(h);
+        k_colsum<<<(g.C * g.R + 127) / 128, 128, 0, st>>>((const double*)h->dfc_part.p, dgrid, g.C * g.R,
+                                                          gradsum + g.pfeat);
+        TR_LAUNCH_CHECK(h);
+        if ((rc = run_gradient<T>(h, (const T*)X, N, (const T*)h->V.p, (const T*)w, pl, e, gradsum, st))) return rc;
+    }
+    set_info(h, pl);
+    return TR_OK;
+}
+
+int check_common(tr_handle* h, const void* X, long long N, const void* theta, const void* w) {
+    if (!h) return TR_ERR_INVALID;
+    if (N < 0) return fail(h, TR_ERR_INVALID, "N must be >= 0 (got %lld)", N);
+    if ((N > 0 && !X) || !theta || !w) return fail(h, TR_ERR_INVALID, "null X / theta / w pointer");
+    if ((uintptr_t)X % h->elt != 0) return fail(h, TR_ERR_INVALID, "X is not aligned to its element size");
+    return TR_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int tr_version(void) { return TR_B200_VERSION; }
+
+int tr_create(tr_handle** out, int dtype, int k, const int64_t* dims, int R, int C, int device) {
+    if (!out) return fail(nullptr, TR_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (dtype != TR_F32 && dtype != TR_F64) return fail(nullptr, TR_ERR_INVALID, "dtype must be TR_F32 or TR_F64");
+    if (k < 1 || k > TR_MAX_MODES) return fail(nullptr, TR_ERR_UNSUPPORTED, "k=%d feature modes (supported: 1..%d)", k, TR_MAX_MODES);
+    if (R < 1) return fail(nullptr, TR_ERR_INVALID, "rank must be >= 1");
+    if (C < 0 || C > TR_MAX_CLASSES) return fail(nullptr, TR_ERR_UNSUPPORTED, "n_classes=%d (supported: up to %d)", C, TR_MAX_CLASSES);
+    if (C > 0 && R > TR_MAX_RANK_MN) return fail(nullptr, TR_ERR_UNSUPPORTED, "multinomial rank %d (supported: up to %d)", R, TR_MAX_RANK_MN);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, TR_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, TR_ERR_INVALID, "device %d out of range (have %d)", device, ndev);
+    tr_handle* h = new tr_handle();
+    h->dtype = dtype; h->device = device; h->elt = dtype == TR_F32 ? 4 : 8;
+    Geo& g = h->geo;
+    memset(&g, 0, sizeof(g));
+    g.k = k; g.R = R; g.C = C; g.D = 1;
+    long long sumI = 0;
+    for (int m = 0; m < k; ++m) {
+        if (dims[m] < 1 || dims[m] > (1LL << 30)) { delete h; return fail(nullptr, TR_ERR_INVALID, "dims[%d]=%lld invalid", m, (long long)dims[m]); }
+        g.dims[m] = (int)dims[m];
+        g.foff[m] = (int)(sumI * R);
+        sumI += dims[m];
+        g.D *= dims[m];
+        if (g.D > (1LL << 31) - 4096) { delete h; return fail(nullptr, TR_ERR_UNSUPPORTED, "one sample has more than 2^31 elements"); }
+    }
+    if ((sumI + C) * R > (1LL << 30)) { delete h; return fail(nullptr, TR_ERR_UNSUPPORTED, "too many parameters"); }
+    g.pfeat = (int)(sumI * R);
+    g.foff[k] = g.pfeat;
+    g.pf = g.pfeat + C * R;
+    g.foff[k + 1] = g.pf;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete h; return fail(nullptr, TR_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    if (prop.major < 10) { delete h; return fail(nullptr, TR_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); }
+    h->sms = prop.multiProcessorCount;
+    *out = h;
+    return TR_OK;
+}
+
+int tr_destroy(tr_handle* h) {
+    if (!h) return TR_OK;
+    DeviceGuard dg(h->device);
+    cudaDeviceSynchronize();
+    Buf* bufs[] = {&h->FtT, &h->Ft64, &h->partial, &h->V, &h->u_ws, &h->dZ_ws, &h->Gpart, &h->Gred, &h->epi_part, &h->dfc_part};
+    for (Buf* b : bufs) if (b->p) cudaFree(b->p);
+    for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    delete h;
+    return TR_OK;
+}
+
+const char* tr_last_error(tr_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int tr_param_count(tr_handle* h, int64_t* P, int64_t* Pf) {
+    if (!h) return TR_ERR_INVALID;
+    if (P) *P = h->geo.pf + (h->geo.C == 0 ? 1 : 0);
+    if (Pf) *Pf = h->geo.pf;
+    return TR_OK;
+}
+
+int tr_gradsum_count(tr_handle* h, int64_t* count) {
+    if (!h || !count) return TR_ERR_INVALID;
+    *count = h->geo.pf + (h->geo.C == 0 ? 2 : 1);
+    return TR_OK;
+}
+
+int tr_reserve(tr_handle* h, int64_t N) {
+    if (!h) return TR_ERR_INVALID;
+    if (N < 1) return TR_OK;
+    DeviceGuard dg(h->device);
+    const int rk = h->geo.C > 0 ? h->geo.R : 1;
+    int rc;
+    for (int vec = 0; vec < 2; ++vec) {
+        Plan pl;
+        if (h->dtype == TR_F32) {
+            const KEntry<float>* e;
+            if ((rc = make_plan<float>(h, N, rk, vec != 0, &pl, &e))) return rc;
+            if ((rc = reserve_for<float>(h, N, pl))) return rc;
+        } else {
+            const KEntry<double>* e;
+            if ((rc = make_plan<double>(h, N, rk, vec != 0, &pl, &e))) return rc;
+            if ((rc = reserve_for<double>(h, N, pl))) return rc;
+        }
+    }
+    return TR_OK;
+}
+
+int tr_forward_std(tr_handle* h, const void* X, int64_t N, const void* theta, const void* w, uint32_t nn_mask,
+                   double sp_beta, double sp_thr, void* yhat, void* stream) {
+    int rc = check_common(h, X, N, theta, w);
+    if (rc) return rc;
+    if (h->geo.C != 0) return fail(h, TR_ERR_INVALID, "tr_forward_std on a multinomial handle");
+    if (N == 0) return TR_OK;
+    if (!yhat) return fail(h, TR_ERR_INVALID, "yhat is null");
+    DeviceGuard dg(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    return h->dtype == TR_F32 ? forward_std_t<float>(h, X, N, theta, w, nn_mask, sp_beta, sp_thr, yhat, st)
+                              : forward_std_t<double>(h, X, N, theta, w, nn_mask, sp_beta, sp_thr, yhat, st);
+}
+
+int tr_forward_mn(tr_handle* h, const void* X, int64_t N, const void* theta, const void* w, uint32_t nn_mask,
+                  double sp_beta, double sp_thr, void* P, int64_t* pred, void* stream) {
+    int rc = check_common(h, X, N, theta, w);
+    if (rc) return rc;
+    if (h->geo.C == 0) return fail(h, TR_ERR_INVALID, "tr_forward_mn on a standard handle");
+    if (N == 0) return TR_OK;
+    if (!P && !pred) return fail(h, TR_ERR_INVALID, "P and pred are both null");
+    DeviceGuard dg(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    return h->dtype == TR_F32
+               ? mn_t<float>(h, X, nullptr, nullptr, N, theta, w, nn_mask, sp_beta, sp_thr, nullptr, P, (long long*)pred, st)
+               : mn_t<double>(h, X, nullptr, nullptr, N, theta, w, nn_mask, sp_beta, sp_thr, nullptr, P, (long long*)pred, st);
+}
+
+static int zero_gradsum(tr_handle* h, double* gradsum, cudaStream_t st) {
+    const size_t n = (size_t)h->geo.pf + (h->geo.C == 0 ? 2 : 1);
+    TR_CUDA(h, cudaMemsetAsync(gradsum, 0, n * sizeof(double), st));
+    return TR_OK;
+}
+
+int tr_fwd_grad_std(tr_handle* h, const void* X, const void* y, int64_t N, const void* theta, const void* w,
+                    uint32_t nn_mask, double sp_beta, double sp_thr, double* gradsum, void* yhat, void* stream) {
+    int rc = check_common(h, X, N, theta, w);
+    if (rc) return rc;
+    if (h->geo.C != 0) return fail(h, TR_ERR_INVALID, "tr_fwd_grad_std on a multinomial handle");
+    if (!gradsum || (N > 0 && !y)) return fail(h, TR_ERR_INVALID, "null y / gradsum pointer");
+    DeviceGuard dg(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) return zero_gradsum(h, gradsum, st);
+    return h->dtype == TR_F32
+               ? fwd_grad_std_t<float>(h, X, y, N, theta, w, nn_mask, sp_beta, sp_thr, gradsum, yhat, st, false)
+               : fwd_grad_std_t<double>(h, X, y, N, theta, w, nn_mask, sp_beta, sp_thr, gradsum, yhat, st, false);
+}
+
+int tr_backward_std(tr_handle* h, const void* X, const void* dyhat, int64_t N, const void* theta, const void* w,
+                    uint32_t nn_mask, double sp_beta, double sp_thr, double* gradsum, void* stream) {
+    int rc = check_common(h, X, N, theta, w);
+    if (rc) return rc;
+    if (h->geo.C != 0) return fail(h, TR_ERR_INVALID, "tr_backward_std on a multinomial handle");
+    if (!gradsum || (N > 0 && !dyhat)) return fail(h, TR_ERR_INVALID, "null dyhat / gradsum pointer");
+    DeviceGuard dg(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) return zero_gradsum(h, gradsum, st);
+    return h->dtype == TR_F32
+               ? fwd_grad_std_t<float>(h, X, dyhat, N, theta, w, nn_mask, sp_beta, sp_thr, gradsum, nullptr, st, true)
+               : fwd_grad_std_t<double>(h, X, dyhat, N, theta, w, nn_mask, sp_beta, sp_thr, gradsum, nullptr, st, true);
+}
+
+int tr_fwd_grad_mn(tr_handle* h, const void* X, const int64_t* y, const void* class_w, int64_t N, const void* theta,
+                   const void* w, uint32_t nn_mask, double sp_beta, double sp_thr, double* gradsum, void* P,
+                   void* stream) {
+    int rc = check_common(h, X, N, theta, w);
+    if (rc) return rc;
+    if (h->geo.C == 0) return fail(h, TR_ERR_INVALID, "tr_fwd_grad_mn on a standard handle");
+    if (!gradsum || (N > 0 && (!y || !class_w))) return fail(h, TR_ERR_INVALID, "null y / class_w / gradsum pointer");
+    DeviceGuard dg(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) return zero_gradsum(h, gradsum, st);
+    return h->dtype == TR_F32
+               ? mn_t<float>(h, X, (const long long*)y, class_w, N, theta, w, nn_mask, sp_beta, sp_thr, gradsum, P, nullptr, st)
+               : mn_t<double>(h, X, (const long long*)y, class_w, N, theta, w, nn_mask, sp_beta, sp_thr, gradsum, P, nullptr, st);
+}
+
+int tr_finish_grad(tr_handle* h, const double* gradsum, double grad_scale, double loss_scale, const void* theta,
+                   double lambda_L2, uint32_t nn_mask, double sp_beta, double sp_thr, void* grad, double* loss,
+                   void* stream) {
+    if (!h) return TR_ERR_INVALID;
+    if (!gradsum || !theta || !grad || !loss) return fail(h, TR_ERR_INVALID, "null pointer argument");
+    DeviceGuard dg(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_gs = h->geo.pf + (h->geo.C == 0 ? 2 : 1);
+    if (h->dtype == TR_F32)
+        k_finish<float><<<1, 1024, 0, st>>>(gradsum, n_gs, grad_scale, loss_scale, (const float*)theta, h->geo,
+                                            lambda_L2, nn_mask, sp_beta, sp_thr, (float*)grad, loss);
+    else
+        k_finish<double><<<1, 1024, 0, st>>>(gradsum, n_gs, grad_scale, loss_scale, (const double*)theta, h->geo,
+                                             lambda_L2, nn_mask, sp_beta, sp_thr, (double*)grad, loss);
+    TR_LAUNCH_CHECK(h);
+    return TR_OK;
+}
+
+int tr_adam_step(tr_handle* h, void* theta, const void* grad, void* m, void* v, void* vmax, int64_t step,
+                 double lr, double beta1, double beta2, double eps, double weight_decay, void* stream) {
+    if (!h) return TR_ERR_INVALID;
+    if (!theta || !grad || !m || !v) return fail(h, TR_ERR_INVALID, "null pointer argument");
+    if (step < 1) return fail(h, TR_ERR_INVALID, "step is 1-based (got %lld)", (long long)step);
+    DeviceGuard dg(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long P = h->geo.pf + (h->geo.C == 0 ? 1 : 0);
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    const double step_size = lr / bc1;
+    const double bc2_sqrt = sqrt(bc2);
+    const int grid = (int)std::min<long long>((P + 255) / 256, 1024);
+    if (h->dtype == TR_F32)
+        k_adam<float><<<grid, 256, 0, st>>>((float*)theta, (const float*)grad, (float*)m, (float*)v, (float*)vmax, P,
+                                            beta1, beta2, eps, weight_decay, step_size, bc2_sqrt);
+    else
+        k_adam<double><<<grid, 256, 0, st>>>((double*)theta, (const double*)grad, (double*)m, (double*)v, (double*)vmax,
+                                             P, beta1, beta2, eps, weight_decay, step_size, bc2_sqrt);
+    TR_LAUNCH_CHECK(h);
+    return TR_OK;
+}
+
+int tr_profile_enable(tr_handle* h, int enable) {
+    if (!h) return TR_ERR_INVALID;
+    DeviceGuard dg(h->device);
+    if (enable && !h->ev[0])
+        for (int i = 0; i < 4; ++i) TR_CUDA(h, cudaEventCreate(&h->ev[i]));
+    if (h->prof && !enable) { int rc = prof_fold(h, true); if (rc) return rc; }
+    h->prof = enable != 0;
+    if (enable) { h->prof_ms[0] = h->prof_ms[1] = 0.0; h->prof_n[0] = h->prof_n[1] = 0; h->ev_set[0] = h->ev_set[1] = false; }
+    return TR_OK;
+}
+
+int tr_profile_read(tr_handle* h, double* out4) {
+    if (!h || !out4) return TR_ERR_INVALID;
+    DeviceGuard dg(h->device);
+    int rc = prof_fold(h, true);
+    if (rc) return rc;
+    out4[0] = h->prof_ms[0]; out4[1] = (double)h->prof_n[0];
+    out4[2] = h->prof_ms[1]; out4[3] = (double)h->prof_n[1];
+    return TR_OK;
+}
+
+int tr_last_launch_info(tr_handle* h, int64_t* info8) {
+    if (!h || !info8) return TR_ERR_INVALID;
+    for (int i = 0; i < 8; ++i) info8[i] = h->info[i];
+    return TR_OK;
+}
+
+}  // extern "C"

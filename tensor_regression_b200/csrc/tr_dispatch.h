@@ -1,0 +1,29 @@
+// tr_dispatch.h — table of streaming-kernel instantiations shared by tr_api.cu and tr_stream.cu.
+#pragma once
+#include "tr_kernels.cuh"
+
+template <typename T> struct VN;
+template <> struct VN<float> { static constexpr int v = 4; };
+template <> struct VN<double> { static constexpr int v = 2; };
+
+template <typename T>
+struct KEntry {
+    int RK, E, U;                         // E in native 16-byte chunks per lane
+    void (*fwd_vec)(FwdArgs<T>);
+    void (*fwd_sc)(FwdArgs<T>);
+    void (*grad_vec)(GradArgs<T>);
+    void (*grad_sc)(GradArgs<T>);
+};
+
+#define TR_ENTRY(T, RK, E, U)                                                                       \
+    { RK, E, U, k_fwd<T, RK, E, U, VN<T>::v>, k_fwd<T, RK, E * VN<T>::v, U, 1>,                     \
+      k_grad<T, RK, E, U, VN<T>::v>, k_grad<T, RK, E * VN<T>::v, U, 1> }
+
+const KEntry<float>* tr_entries_f32_0(int* n);
+const KEntry<float>* tr_entries_f32_1(int* n);
+const KEntry<float>* tr_entries_f32_2(int* n);
+const KEntry<float>* tr_entries_f32_3(int* n);
+const KEntry<double>* tr_entries_f64_0(int* n);
+const KEntry<double>* tr_entries_f64_1(int* n);
+const KEntry<double>* tr_entries_f64_2(int* n);
+const KEntry<double>* tr_entries_f64_3(int* n);

@@ -1,0 +1,409 @@
+// tr_small.cuh — the small kernels around the two streaming passes: factor preparation,
+// per-sample epilogues, split-N reduction, all-mode MTTKRP, finish (normalise + penalty) and Adam.
+// Included by tr_api.cu only.
+#pragma once
+#include "tr_kernels.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// k_prep: Ft = softplus?(theta) for the Pf factor entries, in T (for the streaming kernels) and
+// in double (for the small finishing kernels).  non_neg_fn, std:53-85 / mn:116-146.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_prep(const T* __restrict__ theta, Geo g, uint32_t nn_mask, double beta, double thr,
+                       T* __restrict__ FtT, double* __restrict__ Ft64) {
+    const int nfac = g.k + (g.C > 0 ? 1 : 0);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g.pf; p += gridDim.x * blockDim.x) {
+        int m = 0;
+        while (m + 1 < nfac && p >= g.foff[m + 1]) ++m;
+        T x = theta[p];
+        if ((nn_mask >> m) & 1u) x = tr_softplus<T>(x, (T)beta, (T)thr);
+        FtT[p] = x;
+        Ft64[p] = (double)x;
+    }
+}
+
+// Gred[c, i] = sum_slots Gpart[slot, c, i]  (double accumulation; Gpart is L2-resident)
+template <typename T>
+__global__ void k_reduce_G(const T* __restrict__ Gpart, int slots, int RK, long long D, long long Dpad,
+                           double* __restrict__ Gred) {
+    const long long total = (long long)RK * D;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e / D);
+        const long long i = e % D;
+        double s = 0.0;
+        for (int sl = 0; sl < slots; ++sl) s += (double)Gpart[((long long)sl * RK + c) * Dpad + i];
+        Gred[e] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-sample epilogues (one warp per sample)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct EpiStdArgs {
+    const T* partial; int WT; long long N;
+    const T* theta; int bias_off;
+    const T* y;        // may be null (forward only)
+    T* yhat;           // may be null
+    T* V;              // residual out (N) or null
+    double* part;      // (gridDim.x, 2): sum res, sum res^2
+};
+
+template <typename T>
+__global__ void __launch_bounds__(TR_TPB) k_epi_std(const EpiStdArgs<T> a) {
+    __shared__ double sbuf[32];
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = (long long)blockIdx.x * TR_WPB + (threadIdx.x >> 5);
+    const long long wtot = (long long)gridDim.x * TR_WPB;
+    const double bias = (double)a.theta[a.bias_off];
+    double l2 = 0.0, l1 = 0.0;
+    for (long long n = warp_global; n < a.N; n += wtot) {
+        const T* p = a.partial + n * a.WT;
+        double s = 0.0;
+        for (int t = lane; t < a.WT; t += 32) s += (double)p[t];
+        s = warp_sum(s);
+        if (lane == 0) {
+            const T yh = (T)(s + bias);                // yhat in the model dtype, as the reference returns it
+            if (a.yhat) a.yhat[n] = yh;
+            if (a.y) {
+                const double res = (double)yh - (double)a.y[n];
+                if (a.V) a.V[n] = (T)res;
+                l2 += res * res;
+                l1 += res;
+            }
+        }
+    }
+    const double t2 = block_sum(l2, sbuf);
+    const double t1 = block_sum(l1, sbuf);
+    if (threadIdx.x == 0 && a.part) { a.part[blockIdx.x * 2 + 0] = t1; a.part[blockIdx.x * 2 + 1] = t2; }
+}
+
+template <typename T>
+struct EpiMnArgs {
+    const T* partial; int WT; int RKs; long long N;
+    int R, C;
+    const double* FC;   // class factor (C,R), softplus-ed, double
+    const T* w;         // rank weights
+    const long long* y; // may be null (forward only)
+    const T* class_w;   // (C) or null
+    T* P;               // (N,C) or null
+    long long* pred;    // (N) or null
+    T* V;               // (N,RKs) or null
+    T* u_ws;            // (N,R) or null
+    T* dZ_ws;           // (N,C) or null
+    double* part;       // (gridDim.x): sum -omega log Q
+};
+
+#define TR_JC (TR_MAX_CLASSES / 32)
+#define TR_MAX_RANK_MN 16
+
+template <typename T>
+__global__ void __launch_bounds__(TR_TPB) k_epi_mn(const EpiMnArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char tr_smem[];
+    double* sFC = reinterpret_cast<double*>(tr_smem);      // C*R
+    double* sW = sFC + a.C * a.R;                            // R
+    __shared__ double sbuf[32];
+    for (int i = threadIdx.x; i < a.C * a.R + a.R; i += TR_TPB)
+        sFC[i] = i < a.C * a.R ? a.FC[i] : (double)a.w[i - a.C * a.R];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = (long long)blockIdx.x * TR_WPB + (threadIdx.x >> 5);
+    const long long wtot = (long long)gridDim.x * TR_WPB;
+    const int R = a.R, C = a.C;
+    double loss = 0.0;
+    for (long long n = warp_global; n < a.N; n += wtot) {
+        // u[r] = sum over warp tiles
+        double u[TR_MAX_RANK_MN];
+        const T* p = a.partial + n * a.WT * a.RKs;
+#pragma unroll
+        for (int r = 0; r < TR_MAX_RANK_MN; ++r) {
+            u[r] = 0.0;
+            if (r < R) {
+                double s = 0.0;
+                for (int t = lane; t < a.WT; t += 32) s += (double)p[t * a.RKs + r];
+                u[r] = warp_sum(s);
+            }
+        }
+        // logits of this lane's classes, softmax
+        double z[TR_JC], P[TR_JC];
+        double zmax = -INFINITY;
+#pragma unroll
+        for (int jc = 0; jc < TR_JC; ++jc) {
+            const int c = lane + 32 * jc;
+            z[jc] = -INFINITY;
+            if (c < C) {
+                double s = 0.0;
+#pragma unroll
+                for (int r = 0; r < TR_MAX_RANK_MN; ++r)
+                    if (r < R) s += sW[r] * u[r] * sFC[c * R + r];
+                z[jc] = s;
+                zmax = fmax(zmax, s);
+            }
+        }
+        zmax = warp_max(zmax);
+        double zs = 0.0;
+#pragma unroll
+        for (int jc = 0; jc < TR_JC; ++jc) {
+            const int c = lane + 32 * jc;
+            P[jc] = c < C ? exp(z[jc] - zmax) : 0.0;
+            zs += P[jc];
+        }
+        zs = warp_sum(zs);
+        double pmax = -INFINITY;
+#pragma unroll
+        for (int jc = 0; jc < TR_JC; ++jc) {
+            const int c = lane + 32 * jc;
+            P[jc] = P[jc] / zs;
+            if (c < C) {
+                P[jc] = (double)(T)P[jc];          // probabilities in the model dtype, as the reference holds them
+                pmax = fmax(pmax, P[jc]);
+                if (a.P) a.P[n * C + c] = (T)P[jc];
+            }
+        }
+        pmax = warp_max(pmax);
+        if (a.pred) {                                // first index of the maximum (np.argmax, mn:527)
+            int best = 1 << 30;
+#pragma unroll
+            for (int jc = 0; jc < TR_JC; ++jc) {
+                const int c = lane + 32 * jc;
+                if (c < C && P[jc] == pmax && c < best) best = c;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) best = min(best, __shfl_xor_sync(TR_FULL, best, off));
+            if (lane == 0) a.pred[n] = best;
+        }
+        if (a.y == nullptr) continue;
+
+        // second softmax (CrossEntropyLoss applied to probabilities, mn:364-366 / 448-450)
+        double Q[TR_JC];
+        double qs = 0.0;
+#pragma unroll
+        for (int jc = 0; jc < TR_JC; ++jc) {
+            const int c = lane + 32 * jc;
+            Q[jc] = c < C ? exp(P[jc] - pmax) : 0.0;
+            qs += Q[jc];
+        }
+        qs = warp_sum(qs);
+        const int yn = (int)a.y[n];
+        const double omega = a.class_w ? (double)a.class_w[yn] : 1.0;
+        double dP[TR_JC], dot = 0.0;
+#pragma unroll
+        for (int jc = 0; jc < TR_JC; ++jc) {
+            const int c = lane + 32 * jc;
+            dP[jc] = 0.0;
+            if (c < C) {
+                const double q = Q[jc] / qs;
+                if (c == yn) loss += -omega * ((P[jc] - pmax) - log(qs));
+                dP[jc] = omega * (q - (c == yn ? 1.0 : 0.0));
+                dot += dP[jc] * P[jc];
+            }
+        }
+        dot = warp_sum(dot);
+        double dZ[TR_JC];
+#pragma unroll
+        for (int jc = 0; jc < TR_JC; ++jc) {
+            const int c = lane + 32 * jc;
+            dZ[jc] = c < C ? P[jc] * (dP[jc] - dot) : 0.0;
+            if (c < C && a.dZ_ws) a.dZ_ws[n * C + c] = (T)dZ[jc];
+        }
+        // v[r] = w_r sum_c dZ[c] FC[c,r]
+#pragma unroll
+        for (int r = 0; r < TR_MAX_RANK_MN; ++r) {
+            if (r < R) {
+                double s = 0.0;
+#pragma unroll
+                for (int jc = 0; jc < TR_JC; ++jc) {
+                    const int c = lane + 32 * jc;
+                    if (c < C) s += dZ[jc] * sFC[c * R + r];
+                }
+                s = warp_sum(s) * sW[r];
+                if (lane == 0) {
+                    if (a.V) a.V[n * a.RKs + r] = (T)s;
+                    if (a.u_ws) a.u_ws[n * R + r] = (T)u[r];
+                }
+            }
+        }
+        if (a.V && lane >= R && lane < a.RKs) a.V[n * a.RKs + lane] = (T)0;   // padding channels
+    }
+    const double tl = block_sum(loss, sbuf);
+    if (threadIdx.x == 0 && a.part) a.part[blockIdx.x] = tl;
+}
+
+// dFC_part[b, c*R + r] = w_r * sum_{n in block b's range} dZ[n,c] * u[n,r]   (class-factor gradient)
+template <typename T>
+__global__ void __launch_bounds__(TR_TPB) k_dfc(const T* __restrict__ dZ, const T* __restrict__ u,
+                                                const T* __restrict__ w, long long N, int C, int R,
+                                                double* __restrict__ part) {
+    const long long per = (N + gridDim.x - 1) / gridDim.x;
+    const long long n0 = (long long)blockIdx.x * per;
+    const long long n1 = n0 + per < N ? n0 + per : N;
+    for (int j = threadIdx.x; j < C * R; j += TR_TPB) {
+        const int c = j / R, r = j % R;
+        double s = 0.0;
+        for (long long n = n0; n < n1; ++n) s += (double)dZ[n * C + c] * (double)u[n * R + r];
+        part[(long long)blockIdx.x * C * R + j] = s * (double)w[r];
+    }
+}
+
+// out[dst_off + j*dst_stride... ] column sums of a (rows, cols) double matrix: out[map(j)] = sum_b part[b, j]
+__global__ void k_colsum(const double* __restrict__ part, int rows, int cols, double* __restrict__ out) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < cols; j += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int b = 0; b < rows; ++b) s += part[(long long)b * cols + j];
+        out[j] = s;
+    }
+}
+
+// sum of a T vector (for tr_backward_std's dbias) -> out[0]; single block
+template <typename T>
+__global__ void __launch_bounds__(1024) k_vecsum(const T* __restrict__ v, long long N, double* __restrict__ out) {
+    __shared__ double sbuf[32];
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < N; i += blockDim.x) s += (double)v[i];
+    s = block_sum(s, sbuf);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// All-mode MTTKRP of the reduced G against the factors (the cp_to_tensor backward, K6).
+// One block per (mode m, row i_m):  dFt_m[i_m, r] = scale_r * sum_{i : i_m fixed} G(r)[i] prod_{j!=m} Ft_j[i_j, r]
+// ---------------------------------------------------------------------------------------------
+struct MtArgs {
+    const double* G;      // (RKs, D) if per_rank else (D)
+    const double* Ft64;
+    const void* w;        // rank weights (T) — applied when !per_rank
+    int w_is_f64;
+    int per_rank;
+    Geo geo;
+    double* gradsum;
+};
+
+__global__ void __launch_bounds__(TR_TPB) k_mttkrp(const MtArgs a) {
+    __shared__ double sbuf[32];
+    const int k = a.geo.k, R = a.geo.R;
+    int b = blockIdx.x, m = 0;
+    while (b >= a.geo.dims[m]) { b -= a.geo.dims[m]; ++m; }
+    const int im = b;
+    long long stride[TR_MAX_MODES];
+    stride[k - 1] = 1;
+    for (int j = k - 2; j >= 0; --j) stride[j] = stride[j + 1] * a.geo.dims[j + 1];
+    const long long D = a.geo.D;
+    const long long S = D / a.geo.dims[m];
+    for (int rb = 0; rb < R; rb += 8) {
+        double acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+        for (long long s = threadIdx.x; s < S; s += TR_TPB) {
+            long long rem = s, lin = (long long)im * stride[m];
+            int idx[TR_MAX_MODES];
+            for (int j = k - 1; j >= 0; --j) {
+                if (j == m) continue;
+                idx[j] = (int)(rem % a.geo.dims[j]);
+                rem /= a.geo.dims[j];
+                lin += idx[j] * stride[j];
+            }
+            const double g0 = a.per_rank ? 0.0 : a.G[lin];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r = rb + q;
+                if (r < R) {
+                    double p = a.per_rank ? a.G[(long long)r * D + lin] : g0;
+                    for (int j = 0; j < k; ++j)
+                        if (j != m) p *= a.Ft64[a.geo.foff[j] + idx[j] * R + r];
+                    acc[q] += p;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int r = rb + q;
+            if (r < R) {                                   // uniform across the block
+                const double tot = block_sum(acc[q], sbuf);
+                if (threadIdx.x == 0) {
+                    double sc = 1.0;
+                    if (!a.per_rank)
+                        sc = a.w_is_f64 ? ((const double*)a.w)[r] : (double)((const float*)a.w)[r];
+                    a.gradsum[a.geo.foff[m] + im * R + r] = tot * sc;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Finish: normalisation, softplus chain rule, penalty gradient and value (single block).
+// L2_penalty std:180-196 (sum of un-squared Frobenius norms of the RAW factors; bias excluded).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024) k_finish(const double* __restrict__ gradsum, int n_gs, double grad_scale,
+                                                 double loss_scale, const T* __restrict__ theta, Geo g,
+                                                 double lambda, uint32_t nn_mask, double beta, double thr,
+                                                 T* __restrict__ grad, double* __restrict__ loss) {
+    __shared__ double sbuf[32];
+    __shared__ double snorm[TR_MAX_MODES + 1];
+    const int nfac = g.k + (g.C > 0 ? 1 : 0);
+    for (int m = 0; m < nfac; ++m) {
+        const int p0 = g.foff[m], p1 = (m + 1 < nfac) ? g.foff[m + 1] : g.pf;
+        double s = 0.0;
+        for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) { const double x = (double)theta[p]; s += x * x; }
+        s = block_sum(s, sbuf);
+        if (threadIdx.x == 0) snorm[m] = sqrt(s);
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < g.pf; p += blockDim.x) {
+        int m = 0;
+        while (m + 1 < nfac && p >= g.foff[m + 1]) ++m;
+        const double x = (double)theta[p];
+        double d = gradsum[p] * grad_scale;
+        if ((nn_mask >> m) & 1u) {
+            const double bx = x * beta;
+            if (!(bx > thr)) d *= 1.0 / (1.0 + exp(-bx));
+        }
+        if (lambda != 0.0) d += lambda * x / snorm[m];   // lambda == 0: no penalty term (also keeps the VJP path finite at F == 0)
+        grad[p] = (T)d;
+    }
+    if (threadIdx.x == 0) {
+        if (g.C == 0) grad[g.pf] = (T)(gradsum[g.pf] * grad_scale);
+        double pen = 0.0;
+        for (int m = 0; m < nfac; ++m) pen += snorm[m];
+        const double ld = gradsum[n_gs - 1] * loss_scale;
+        loss[0] = ld;
+        loss[1] = ld + lambda * pen;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam (torch/optim/adam.py _single_tensor_adam; arithmetic in the parameter dtype like torch)
+// ---------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T tr_sqrt(T x);
+template <> __device__ __forceinline__ float tr_sqrt<float>(float x) { return sqrtf(x); }
+template <> __device__ __forceinline__ double tr_sqrt<double>(double x) { return sqrt(x); }
+
+template <typename T>
+__global__ void k_adam(T* __restrict__ theta, const T* __restrict__ grad, T* __restrict__ m, T* __restrict__ v,
+                       T* __restrict__ vmax, long long P, double beta1, double beta2, double eps, double wd,
+                       double step_size, double bc2_sqrt) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P;
+         p += (long long)gridDim.x * blockDim.x) {
+        T g = grad[p];
+        const T th = theta[p];
+        if (wd != 0.0) g = g + (T)wd * th;
+        T mm = m[p];
+        mm = mm + (T)(1.0 - beta1) * (g - mm);                       // lerp_(grad, 1-beta1)
+        T vv = v[p] * (T)beta2;
+        vv = vv + (T)(1.0 - beta2) * g * g;                           // mul_(beta2).addcmul_(g, g, 1-beta2)
+        m[p] = mm;
+        v[p] = vv;
+        T dn;
+        if (vmax) {
+            T vm = vmax[p];
+            vm = vm > vv ? vm : vv;
+            vmax[p] = vm;
+            dn = tr_sqrt<T>(vm) / (T)bc2_sqrt + (T)eps;
+        } else {
+            dn = tr_sqrt<T>(vv) / (T)bc2_sqrt + (T)eps;
+        }
+        theta[p] = th + (T)(-step_size) * (mm / dn);                  // addcdiv_(m, denom, value=-step_size)
+    }
+}

@@ -1,0 +1,239 @@
+"""Host-side driver of the C-ABI kernels: one ``Engine`` per model geometry.
+
+PyTorch is used only for device memory, streams and (optionally) ``torch.distributed``; every
+number on the fit path comes from libtrb200.so.  ``Engine`` has no CPU mode.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import TRError
+
+_DT = {torch.float32: _lib.TR_F32, torch.float64: _lib.TR_F64}
+
+
+def nn_mask_of(non_negative, n_factors):
+    """Bit m set <=> softplus on list position m (non_neg_fn, std:81-85 / mn:142-146).
+    Entries beyond the factor list (std's unused trailing entry, std:281-284) are ignored."""
+    mask = 0
+    for m in range(min(len(non_negative), n_factors)):
+        if bool(non_negative[m]):
+            mask |= 1 << m
+    return mask
+
+
+def factor_offsets(dims, rank, n_classes):
+    sizes = [int(d) * rank for d in dims] + ([n_classes * rank] if n_classes > 0 else [])
+    return sizes, np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+
+
+def shard_bounds(n_total, rank, world):
+    """Contiguous, balanced split of the sample axis: rank r owns [lo, hi)."""
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class Engine:
+    """Plan + workspace for one (dims, rank, n_classes, dtype, device)."""
+
+    def __init__(self, dims, rank, n_classes=0, dtype=torch.float32, device='cuda'):
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise TRError(f"device '{device}': tensor_regression_b200 runs on CUDA devices only (no CPU path)")
+        if not torch.cuda.is_available():
+            raise TRError('no CUDA device available (tensor_regression_b200 has no CPU path)')
+        if dtype not in _DT:
+            raise TRError(f'dtype {dtype} not supported (float32 / float64)')
+        if device.index is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device, self.dtype = device, dtype
+        self.dims = [int(d) for d in dims]
+        self.rank, self.n_classes = int(rank), int(n_classes)
+        self.D = int(np.prod(self.dims))
+        h = ctypes.c_void_p()
+        arr = (ctypes.c_int64 * len(self.dims))(*self.dims)
+        rc = _lib.lib.tr_create(ctypes.byref(h), _DT[dtype], len(self.dims), arr, self.rank, self.n_classes,
+                                device.index)
+        if rc != 0:
+            raise TRError(f'tr_create failed ({rc}): {_lib.lib.tr_last_error(None).decode()}')
+        self._h = h
+        P, Pf, ngs = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        self._ck(_lib.lib.tr_param_count(h, ctypes.byref(P), ctypes.byref(Pf)))
+        self._ck(_lib.lib.tr_gradsum_count(h, ctypes.byref(ngs)))
+        self.P, self.Pf, self.n_gradsum = P.value, Pf.value, ngs.value
+        self.launches = 0            # kernels launched through this engine (bench: gpu_launches)
+
+    # -- plumbing -----------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise TRError(f'libtrb200 error {rc}: {_lib.lib.tr_last_error(self._h).decode()}')
+
+    def close(self):
+        if getattr(self, '_h', None):
+            _lib.lib.tr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _x(self, X):
+        if not isinstance(X, torch.Tensor) or X.device != self.device or X.dtype != self.dtype:
+            raise TRError(f'X must be a {self.dtype} tensor on {self.device}')
+        if list(X.shape[1:]) != self.dims:
+            raise TRError(f'X.shape[1:]={list(X.shape[1:])} does not match the model dims {self.dims}')
+        return X if X.is_contiguous() else X.contiguous()
+
+    def _vec(self, t, n, name, dtype=None):
+        dtype = dtype or self.dtype
+        if not isinstance(t, torch.Tensor) or t.device != self.device or t.dtype != dtype or t.numel() != n \
+                or not t.is_contiguous():
+            raise TRError(f'{name} must be a contiguous {dtype} tensor with {n} elements on {self.device}')
+        return t
+
+    def _count(self):
+        info = (ctypes.c_int64 * 8)()
+        _lib.lib.tr_last_launch_info(self._h, info)
+        self.launches += int(info[0])
+        return list(info)
+
+    def reserve(self, n_samples):
+        self._ck(_lib.lib.tr_reserve(self._h, int(n_samples)))
+
+    def launch_info(self):
+        info = (ctypes.c_int64 * 8)()
+        _lib.lib.tr_last_launch_info(self._h, info)
+        keys = ['launches', 'grid_fwd', 'grid_grad', 'tiles_per_sample', 'groups_fwd', 'groups_grad', 'channels',
+                'vector_width']
+        return dict(zip(keys, [int(v) for v in info]))
+
+    def profile(self, enable=True):
+        """Start (and reset) / stop CUDA-event timing of the two streaming kernels."""
+        self._ck(_lib.lib.tr_profile_enable(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        out = (ctypes.c_double * 4)()
+        self._ck(_lib.lib.tr_profile_read(self._h, out))
+        return {'fwd_ms': out[0], 'fwd_launches': int(out[1]), 'grad_ms': out[2], 'grad_launches': int(out[3])}
+
+    # -- the hot path --------------------------------------------------------------------------
+    def forward_std(self, X, theta, w, nn_mask, beta, thr):
+        X = self._x(X)
+        N = X.shape[0]
+        yhat = torch.empty(N, dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(_lib.lib.tr_forward_std(self._h, X.data_ptr(), N, self._vec(theta, self.P, 'theta').data_ptr(),
+                                             self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
+                                             yhat.data_ptr(), self._stream()))
+        self._count()
+        return yhat
+
+    def forward_mn(self, X, theta, w, nn_mask, beta, thr, want_pred=True):
+        X = self._x(X)
+        N = X.shape[0]
+        P = torch.empty((N, self.n_classes), dtype=self.dtype, device=self.device)
+        pred = torch.empty(N, dtype=torch.int64, device=self.device) if want_pred else None
+        with torch.cuda.device(self.device):
+            self._ck(_lib.lib.tr_forward_mn(self._h, X.data_ptr(), N, self._vec(theta, self.P, 'theta').data_ptr(),
+                                            self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
+                                            P.data_ptr(), pred.data_ptr() if want_pred else None, self._stream()))
+        self._count()
+        return P, pred
+
+    def fwd_grad_std(self, X, y, theta, w, nn_mask, beta, thr, gradsum=None, yhat=None):
+        X = self._x(X)
+        N = X.shape[0]
+        if gradsum is None:
+            gradsum = torch.empty(self.n_gradsum, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(_lib.lib.tr_fwd_grad_std(self._h, X.data_ptr(), self._vec(y, N, 'y').data_ptr(), N,
+                                              self._vec(theta, self.P, 'theta').data_ptr(),
+                                              self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
+                                              self._vec(gradsum, self.n_gradsum, 'gradsum', torch.float64).data_ptr(),
+                                              yhat.data_ptr() if yhat is not None else None, self._stream()))
+        self._count()
+        return gradsum
+
+    def backward_std(self, X, dyhat, theta, w, nn_mask, beta, thr, gradsum=None):
+        X = self._x(X)
+        N = X.shape[0]
+        if gradsum is None:
+            gradsum = torch.empty(self.n_gradsum, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(_lib.lib.tr_backward_std(self._h, X.data_ptr(), self._vec(dyhat, N, 'dyhat').data_ptr(), N,
+                                              self._vec(theta, self.P, 'theta').data_ptr(),
+                                              self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
+                                              gradsum.data_ptr(), self._stream()))
+        self._count()
+        return gradsum
+
+    def fwd_grad_mn(self, X, y, class_w, theta, w, nn_mask, beta, thr, gradsum=None, P=None):
+        X = self._x(X)
+        N = X.shape[0]
+        if gradsum is None:
+            gradsum = torch.empty(self.n_gradsum, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(_lib.lib.tr_fwd_grad_mn(self._h, X.data_ptr(), self._vec(y, N, 'y', torch.int64).data_ptr(),
+                                             self._vec(class_w, self.n_classes, 'class weights').data_ptr(), N,
+                                             self._vec(theta, self.P, 'theta').data_ptr(),
+                                             self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
+                                             self._vec(gradsum, self.n_gradsum, 'gradsum', torch.float64).data_ptr(),
+                                             P.data_ptr() if P is not None else None, self._stream()))
+        self._count()
+        return gradsum
+
+    def finish(self, gradsum, grad_scale, loss_scale, theta, lambda_L2, nn_mask, beta, thr, grad=None, loss=None):
+        if grad is None:
+            grad = torch.empty(self.P, dtype=self.dtype, device=self.device)
+        if loss is None:
+            loss = torch.empty(2, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(_lib.lib.tr_finish_grad(self._h, gradsum.data_ptr(), float(grad_scale), float(loss_scale),
+                                             self._vec(theta, self.P, 'theta').data_ptr(), float(lambda_L2), nn_mask,
+                                             beta, thr, grad.data_ptr(), loss.data_ptr(), self._stream()))
+        self.launches += 1
+        return grad, loss
+
+    def adam_step(self, theta, grad, m, v, vmax, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        with torch.cuda.device(self.device):
+            self._ck(_lib.lib.tr_adam_step(self._h, theta.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                           vmax.data_ptr() if vmax is not None else None, int(step), float(lr),
+                                           float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                           self._stream()))
+        self.launches += 1
+
+
+class ShardedSum:
+    """Sums the packed ``gradsum`` vector over the ranks that each hold a slice of the sample
+    axis: one all-reduce of P+2 doubles per closure evaluation.  With
+    ``group=None`` and no initialised default group this is the identity (single GPU)."""
+
+    def __init__(self, group=None, enabled=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        if enabled is None:
+            enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.enabled = bool(enabled)
+
+    @property
+    def world(self):
+        return self.dist.get_world_size(self.group) if self.enabled else 1
+
+    def sum_(self, t):
+        if self.enabled:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def total(self, value, device):
+        """Global sum of a host scalar (N_total, sum of class weights) — done once, at fit start."""
+        t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+        return float(self.sum_(t).item())

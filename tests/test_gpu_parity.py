@@ -1,0 +1,375 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes) and through the
+reference-shaped Python API, against (a) the golden outputs of the unmodified reference
+(tests/golden), (b) the CPU oracle on freshly seeded inputs, (c) size-independent properties.
+
+Tolerances (north star): norm-relative 1e-5 for fp32, 1e-10 for fp64, i.e.
+max|a-b| / max|b| (per-element relative error is meaningless where y_hat ~ 0)."""
+import glob
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+STD = sorted(glob.glob(os.path.join(GOLDEN, 'std_*.npz')))
+MN = sorted(glob.glob(os.path.join(GOLDEN, 'mn_*.npz')))
+ADAM = {'lr': 0.01, 'amsgrad': True}
+LBFGS = {'lr': 1, 'max_iter': 20, 'max_eval': None, 'tolerance_grad': 1e-07, 'tolerance_change': 1e-09,
+         'history_size': 100, 'line_search_fn': 'strong_wolfe'}
+DEV = 'cuda:0'
+TOL = {torch.float32: 1e-5, torch.float64: 1e-10}
+
+
+def rel(a, b):
+    a = np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a, dtype=np.float64)
+    b = np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def load(path):
+    z = np.load(path)
+    k = len([n for n in z.files if n.startswith('Bcp_init_')])
+    return z, k
+
+
+def engine_for(dims, R, C, dtype):
+    from tensor_regression_b200 import engine
+    return engine.Engine(dims, R, C, dtype, DEV)
+
+
+def dev(t, dtype=None):
+    t = torch.as_tensor(t)
+    return t.to(device=DEV, dtype=dtype or t.dtype).contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# (a) golden fixtures: kernels through the C ABI
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('path', STD, ids=[os.path.basename(p)[:-4] for p in STD])
+def test_std_kernels_vs_reference_golden(path):
+    from tensor_regression_b200 import engine
+    z, k = load(path)
+    X, y = torch.from_numpy(z['X']), torch.from_numpy(z['y'])
+    dt = X.dtype
+    tol = TOL[dt]
+    B0 = [torch.from_numpy(z[f'Bcp_init_{i}']) for i in range(k)]
+    w = torch.from_numpy(z['weights'])
+    nn = [bool(v) for v in z['non_negative']]
+    bias = torch.tensor([float(z['bias_init'])], dtype=dt)
+    lam, N = float(z['lambda_L2']), X.shape[0]
+    eng = engine_for(X.shape[1:], int(z['R']), 0, dt)
+    theta = dev(O.pack(B0, bias))
+    mask = engine.nn_mask_of(nn, k)
+    Xd, yd, wd = dev(X), dev(y), dev(w)
+    yhat = eng.forward_std(Xd, theta, wd, mask, 50.0, 1.0)
+    assert rel(yhat, z['y_hat']) < tol
+    yh2 = torch.empty_like(yd)
+    gs = eng.fwd_grad_std(Xd, yd, theta, wd, mask, 50.0, 1.0, yhat=yh2)
+    assert rel(yh2, z['y_hat']) < tol
+    # unnormalised sums vs the fp64 closed form
+    cf = O.closed_form_std(X.double(), y.double(), [b.double() for b in B0], bias.double(), w.double(), nn)
+    assert rel(gs, cf['gradsum']) < tol
+    grad, loss = eng.finish(gs, 2.0 / N, 1.0 / N, theta, lam, mask, 50.0, 1.0)
+    want = np.concatenate([z[f'grad_{i}'].reshape(-1) for i in range(k)] + [z['dbias'].reshape(-1)])
+    assert rel(grad, want) < tol
+    assert abs(loss[0].item() - float(z['loss_data'])) < tol * abs(float(z['loss_data']))
+    assert abs(loss[1].item() - float(z['loss'])) < tol * abs(float(z['loss']))
+
+
+@pytest.mark.parametrize('path', MN, ids=[os.path.basename(p)[:-4] for p in MN])
+@pytest.mark.parametrize('dt', [torch.float32, torch.float64], ids=['f32', 'f64'])
+def test_mn_kernels_vs_reference_golden(path, dt):
+    """fp32 against the reference's own fp32 outputs; the fp64 instantiation of the same kernels
+    against the fp64 oracle at 1e-10 (pins the double-softmax / dZ / MTTKRP algebra exactly)."""
+    from tensor_regression_b200 import engine
+    z, k = load(path)
+    X, y = torch.from_numpy(z['X']).to(dt), torch.from_numpy(z['y'])
+    tol = TOL[dt]
+    B0 = [torch.from_numpy(z[f'Bcp_init_{i}']).to(dt) for i in range(k)]
+    w = torch.from_numpy(z['weights']).to(dt)
+    nn = [bool(v) for v in z['non_negative']]
+    cw = torch.from_numpy(z['class_weights']).to(dt)
+    lam, C, R = float(z['lambda_L2']), int(z['C']), int(z['R'])
+    eng = engine_for(X.shape[1:], R, C, dt)
+    theta = dev(O.pack(B0))
+    mask = engine.nn_mask_of(nn, k)
+    Xd, yd, wd, cwd = dev(X), dev(y), dev(w), dev(cw)
+    ref = O.mn_loss_grad(X.double(), y, [b.double() for b in B0], w.double(), nn, cw.double().numpy(), lam)
+    cf = O.closed_form_mn(X.double(), y, [b.double() for b in B0], w.double(), nn, cw.double())
+    P, pred = eng.forward_mn(Xd, theta, wd, mask, 50.0, 1.0)
+    assert rel(P, ref['P']) < tol
+    if dt == torch.float32:
+        assert rel(P, z['P']) < tol
+    assert np.array_equal(pred.cpu().numpy(), np.argmax(P.cpu().numpy(), axis=1))
+    P2 = torch.empty_like(P)
+    gs = eng.fwd_grad_mn(Xd, yd, cwd, theta, wd, mask, 50.0, 1.0, P=P2)
+    assert rel(P2, ref['P']) < tol
+    assert rel(gs, cf['gradsum']) < tol
+    W = cf['W'].item()
+    grad, loss = eng.finish(gs, 1.0 / W, 1.0 / W, theta, lam, mask, 50.0, 1.0)
+    want64 = torch.cat([g.reshape(-1) for g in ref['grads']])
+    assert rel(grad, want64) < tol
+    assert abs(loss[1].item() - ref['loss'].item()) < tol * abs(ref['loss'].item())
+    if dt == torch.float32:
+        want = np.concatenate([z[f'grad_{i}'].reshape(-1) for i in range(k)])
+        assert rel(grad, want) < tol
+        assert abs(loss[1].item() - float(z['loss'])) < tol * abs(float(z['loss']))
+
+
+# ------------------------------------------------------------------------------------------
+# (a') golden fixtures: the reference-shaped API (fit_Adam / fit / predict)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('path', STD, ids=[os.path.basename(p)[:-4] for p in STD])
+def test_std_api_fit_vs_reference_golden(path):
+    from tensor_regression_b200 import standard_tensor_regression as STR
+    z, k = load(path)
+    X, y = torch.from_numpy(z['X']), torch.from_numpy(z['y'])
+    dt = X.dtype
+    tol = 10 * TOL[dt]
+    B0 = [torch.from_numpy(z[f'Bcp_init_{i}']) for i in range(k)]
+    nn = [bool(v) for v in z['non_negative']]
+    wts = None if np.all(z['weights'] == 1) else z['weights']
+    lam = float(z['lambda_L2'])
+    m = STR.CP_linear_regression(X.shape, dtype=dt, rank=int(z['R']), non_negative=nn, weights=wts,
+                                 Bcp_init=[b.clone() for b in B0], bias_init=float(z['bias_init']), device=DEV)
+    conv = m.fit_Adam(X.to(DEV), y.to(DEV), lambda_L2=lam, max_iter=20, tol=1e-50, patience=100, verbose=False,
+                      Adam_kwargs=ADAM)
+    assert conv is False and len(m.loss_running) == 20
+    assert rel(m.loss_running, z['adam_loss_running']) < tol
+    for i in range(k):
+        assert rel(m.Bcp[i], z[f'adam_Bcp_{i}']) < tol
+    assert rel(m.bias, z['adam_bias']) < tol
+    assert rel(m.predict(z['X']), z['adam_predict']) < tol                  # numpy X: streamed path
+    assert rel(m.predict(X.to(DEV)), z['adam_predict']) < tol
+    if 'lbfgs_loss_running' in z.files:
+        m2 = STR.CP_linear_regression(X.shape, dtype=dt, rank=int(z['R']), non_negative=nn, weights=wts,
+                                      Bcp_init=[b.clone() for b in B0], bias_init=float(z['bias_init']), device=DEV)
+        m2.fit(X.to(DEV), y.to(DEV), lambda_L2=lam, max_iter=6, tol=1e-50, patience=10, verbose=False,
+               running_loss_logging_interval=1, LBFGS_kwargs=LBFGS)
+        assert rel(m2.loss_running, z['lbfgs_loss_running']) < 1e-7
+        for i in range(k):
+            assert rel(m2.Bcp[i], z[f'lbfgs_Bcp_{i}']) < 1e-6
+
+
+@pytest.mark.parametrize('path', MN, ids=[os.path.basename(p)[:-4] for p in MN])
+def test_mn_api_fit_vs_reference_golden(path):
+    from tensor_regression_b200 import multinomial_tensor_regression as MTR
+    z, k = load(path)
+    nn = [bool(v) for v in z['non_negative']]
+    wts = None if np.all(z['weights'] == 1) else z['weights']
+    B0 = [torch.from_numpy(z[f'Bcp_init_{i}']) for i in range(k)]
+    m = MTR.CP_logistic_regression(z['X'], z['y'], rank=int(z['R']), non_negative=nn, weights=wts,
+                                   Bcp_init=[b.clone() for b in B0], device=DEV)
+    assert m.n_classes == int(z['C'])
+    m.fit_Adam(lambda_L2=float(z['lambda_L2']), max_iter=20, tol=1e-50, patience=100, weights=z['class_weights'],
+               verbose=False, Adam_kwargs=ADAM)
+    assert rel(m.loss_running, z['adam_loss_running']) < 1e-4
+    for i in range(k):
+        assert rel(m.Bcp[i], z[f'adam_Bcp_{i}']) < 1e-4
+    prob, pred = m.predict()
+    assert rel(prob, z['adam_prob']) < 1e-4
+    assert np.mean(pred == z['adam_pred']) > 0.98
+    cm, acc = m.make_confusion_matrix()
+    assert cm.shape == (m.n_classes, m.n_classes) and 0 <= acc <= 1
+    with pytest.raises((TypeError, RuntimeError)):
+        m.fit_Adam(Adam_kwargs=ADAM)                    # class weights None raises like mn:449
+
+
+# ------------------------------------------------------------------------------------------
+# (b) oracle on BASELINE.json shapes at sizes the CPU finishes in seconds
+# ------------------------------------------------------------------------------------------
+SHAPES_STD = [
+    ('cfg1_full', 2000, (20, 30, 40), 5, torch.float32),
+    ('cfg2_shape', 300, (64, 64, 32), 8, torch.float32),
+    ('cfg4_shape_f64', 48, (16, 16, 16, 32), 12, torch.float64),
+    ('demo_shape_f64', 16, (500, 500), 10, torch.float64),
+    ('ragged_tail', 131, (9, 7, 11), 3, torch.float32),
+]
+
+
+@pytest.mark.parametrize('name,N,dims,R,dt', SHAPES_STD, ids=[s[0] for s in SHAPES_STD])
+def test_std_vs_oracle_on_baseline_shapes(name, N, dims, R, dt):
+    from tensor_regression_b200 import engine
+    X, y, _ = O.synth_std(N, dims, R, 1234 + 2, dtype=dt)
+    nn = [False] * (len(dims) + 1)
+    B0 = O.init_std(dims, R, nn, dtype=dt)
+    bias = torch.tensor([0.0], dtype=dt)
+    w = torch.ones(R, dtype=dt)
+    eng = engine_for(dims, R, 0, dt)
+    theta = dev(O.pack(B0, bias))
+    gs = eng.fwd_grad_std(dev(X), dev(y), theta, dev(w), 0, 50.0, 1.0)
+    grad, loss = eng.finish(gs, 2.0 / N, 1.0 / N, theta, 0.01, 0, 50.0, 1.0)
+    truth = O.std_loss_grad(X.double(), y.double(), [b.double() for b in B0], bias.double(), w.double(), nn, 0.01)
+    want = torch.cat([g.reshape(-1) for g in truth['grads']] + [truth['dbias'].reshape(-1)])
+    e_truth = rel(grad, want)
+    assert e_truth < TOL[dt], e_truth
+    assert abs(loss[1].item() - truth['loss'].item()) < TOL[dt] * abs(truth['loss'].item())
+    if dt == torch.float32:
+        # error of the reference's own fp32 evaluation against the same fp64 truth, for context
+        ref32 = O.std_loss_grad(X, y, B0, bias, w, nn, 0.01)
+        got32 = torch.cat([g.reshape(-1) for g in ref32['grads']] + [ref32['dbias'].reshape(-1)])
+        print(f'{name}: kernel vs fp64 {e_truth:.2e}; reference fp32 vs fp64 {rel(got32, want):.2e}; '
+              f'kernel vs reference fp32 {rel(grad, got32):.2e}')
+        assert rel(grad, got32) < TOL[dt]
+    info = eng.launch_info()
+    assert info['launches'] >= 6 and info['tiles_per_sample'] >= 1
+
+
+SHAPES_MN = [
+    ('cfg3_shape', 256, (100, 50, 20), 10, 6),
+    ('cfg5_shape', 200, (100, 50, 20), 4, 4),
+    ('rank16', 64, (12, 10), 3, 16),
+    ('many_classes', 150, (8, 6, 4), 40, 5),
+]
+
+
+@pytest.mark.parametrize('name,N,dims,C,R', SHAPES_MN, ids=[s[0] for s in SHAPES_MN])
+def test_mn_vs_oracle_on_baseline_shapes(name, N, dims, C, R):
+    from tensor_regression_b200 import engine
+    X, y, _ = O.synth_mn(N, dims, R, C, 1234 + 3)
+    nn = [False] * (len(dims) + 1)
+    B0 = O.init_mn(list(dims) + [C], R, nn, scale=0.2)
+    w = torch.ones(R)
+    counts = np.bincount(y.numpy(), minlength=C).astype(np.float64)
+    cw = torch.tensor(N / (C * np.maximum(counts, 1)), dtype=torch.float32)
+    eng = engine_for(dims, R, C, torch.float32)
+    theta = dev(O.pack(B0))
+    gs = eng.fwd_grad_mn(dev(X), dev(y), dev(cw), theta, dev(w), 0, 50.0, 1.0)
+    truth = O.mn_loss_grad(X.double(), y, [b.double() for b in B0], w.double(), nn, cw.double().numpy(), 0.01)
+    W = cw[y].double().sum().item()
+    grad, loss = eng.finish(gs, 1.0 / W, 1.0 / W, theta, 0.01, 0, 50.0, 1.0)
+    want = torch.cat([g.reshape(-1) for g in truth['grads']])
+    assert rel(grad, want) < 1e-5, rel(grad, want)
+    assert abs(loss[1].item() - truth['loss'].item()) < 1e-5 * abs(truth['loss'].item())
+
+
+# ------------------------------------------------------------------------------------------
+# (c) properties and edge cases
+# ------------------------------------------------------------------------------------------
+def test_shard_sum_equals_whole():
+    """Virtual ranks on one GPU: the packed sums of disjoint sample slices add up to the whole
+    (what the NCCL all-reduce relies on), incl. an unaligned slice start (scalar-load path)."""
+    from tensor_regression_b200 import engine
+    N, dims, R = 1003, (7, 9, 5), 4            # D = 315: rows are not 16-byte multiples
+    X, y, _ = O.synth_std(N, dims, R, 77, dtype=torch.float64)
+    B0 = O.init_std(dims, R, [False] * 4, dtype=torch.float64)
+    eng = engine_for(dims, R, 0, torch.float64)
+    theta = dev(O.pack(B0, torch.tensor([0.1], dtype=torch.float64)))
+    Xd, yd, wd = dev(X), dev(y), dev(torch.ones(R, dtype=torch.float64))
+    whole = eng.fwd_grad_std(Xd, yd, theta, wd, 0, 50.0, 1.0).clone()
+    parts = torch.zeros_like(whole)
+    for r in range(3):
+        lo, hi = engine.shard_bounds(N, r, 3)
+        parts += eng.fwd_grad_std(Xd[lo:hi], yd[lo:hi].contiguous(), theta, wd, 0, 50.0, 1.0)
+    assert rel(parts, whole) < 1e-12
+    empty = eng.fwd_grad_std(Xd[:0], yd[:0].contiguous(), theta, wd, 0, 50.0, 1.0)
+    assert float(empty.abs().max()) == 0.0
+
+
+def test_vector_and_scalar_load_paths_agree():
+    from tensor_regression_b200 import engine
+    N, dims, R = 257, (8, 8, 8), 3
+    X, y, _ = O.synth_std(N + 1, dims, R, 5)
+    eng = engine_for(dims, R, 0, torch.float32)
+    B0 = O.init_std(dims, R, [False] * 4)
+    theta = dev(O.pack(B0, torch.tensor([0.0])))
+    wd = dev(torch.ones(R))
+    flat = dev(torch.cat([torch.zeros(1), X.reshape(-1)]))
+    X_al = flat[1 + 512:].view(N, *dims)                 # 4-byte offset: not 16-byte aligned
+    assert X_al.data_ptr() % 16 != 0
+    a = eng.forward_std(X_al, theta, wd, 0, 50.0, 1.0)
+    assert eng.launch_info()['vector_width'] == 1
+    b = eng.forward_std(X_al.clone(), theta, wd, 0, 50.0, 1.0)
+    assert eng.launch_info()['vector_width'] == 4
+    assert rel(a, b) < 1e-6
+
+
+def test_backward_is_linear_and_matches_autograd():
+    from tensor_regression_b200 import standard_tensor_regression as STR
+    N, dims, R = 64, (6, 5, 8), 3
+    X, y, _ = O.synth_std(N, dims, R, 9, dtype=torch.float64)
+    nn = [True, False, False, False]
+    B0 = O.init_std(dims, R, nn, dtype=torch.float64)
+    bias = torch.tensor([0.3], dtype=torch.float64)
+    w = torch.tensor([0.5, 1.0, 2.0], dtype=torch.float64)
+    Bd = [dev(b).requires_grad_(True) for b in B0]
+    bd = dev(bias).requires_grad_(True)
+    yh = STR.lin_model(dev(X), Bd, dev(w), nn, bd)
+    loss = torch.nn.MSELoss()(yh, dev(y)) + 0.01 * STR.L2_penalty(Bd)
+    loss.backward()
+    ref = O.std_loss_grad(X, y, B0, bias, w, nn, 0.01)
+    assert rel(yh, ref['y_hat']) < 1e-12
+    for i in range(3):
+        assert rel(Bd[i].grad, ref['grads'][i]) < 1e-10
+    assert rel(bd.grad, ref['dbias']) < 1e-10
+
+
+def test_n_smaller_than_unroll_and_single_sample():
+    from tensor_regression_b200 import engine
+    dims, R = (5, 4, 8), 2
+    eng = engine_for(dims, R, 0, torch.float32)
+    for N in (1, 2, 3, 5):
+        X, y, _ = O.synth_std(N, dims, R, 40 + N)
+        B0 = O.init_std(dims, R, [False] * 4)
+        theta = dev(O.pack(B0, torch.tensor([0.2])))
+        gs = eng.fwd_grad_std(dev(X), dev(y).reshape(-1), theta, dev(torch.ones(R)), 0, 50.0, 1.0)
+        cf = O.closed_form_std(X.double(), y.double().reshape(-1), [b.double() for b in B0],
+                               torch.tensor([0.2], dtype=torch.float64), torch.ones(R, dtype=torch.float64), [False] * 4)
+        assert rel(gs, cf['gradsum']) < 1e-5
+
+
+def test_large_sample_count_long_sums():
+    """Many samples, small D: exercises the chunked fp32 gradient sums (slots) and several groups."""
+    from tensor_regression_b200 import engine
+    N, dims, R = 60000, (16, 8), 3
+    X, y, _ = O.synth_std(N, dims, R, 3)
+    B0 = O.init_std(dims, R, [False] * 3)
+    eng = engine_for(dims, R, 0, torch.float32)
+    theta = dev(O.pack(B0, torch.tensor([0.0])))
+    gs = eng.fwd_grad_std(dev(X), dev(y), theta, dev(torch.ones(R)), 0, 50.0, 1.0)
+    cf = O.closed_form_std(X.double(), y.double(), [b.double() for b in B0], torch.tensor([0.0], dtype=torch.float64),
+                           torch.ones(R, dtype=torch.float64), [False] * 3)
+    assert rel(gs, cf['gradsum']) < 1e-5, rel(gs, cf['gradsum'])
+
+
+def test_errors_and_pickle():
+    from tensor_regression_b200 import engine
+    from tensor_regression_b200 import standard_tensor_regression as STR
+    X, y, _ = O.synth_std(32, (4, 5), 2, 1)
+    m = STR.CP_linear_regression(X.shape, rank=2, device=DEV)
+    with pytest.raises(TypeError):
+        m.fit_Adam(X.to(DEV), y.to(DEV))                       # Adam_kwargs=None raises like std:453
+    with pytest.raises(TypeError):
+        m.fit(X.to(DEV), y.to(DEV))                            # LBFGS_kwargs=None raises like std:366
+    with pytest.raises(engine.TRError):
+        m.predict(torch.zeros(3, 4, 6, device=DEV))            # wrong feature dims
+    m.fit_Adam(X.to(DEV), y.to(DEV), max_iter=3, Adam_kwargs=ADAM)
+    m2 = pickle.loads(pickle.dumps(m))
+    assert rel(m2.predict(X.numpy()), m.predict(X.numpy())) == 0.0
+    p = m.get_params()
+    m3 = STR.CP_linear_regression(X.shape, rank=2, device=DEV)
+    m3.set_params(p)
+    m3.bias.copy_(m.bias)
+    assert rel(m3.predict(X.numpy()), m.predict(X.numpy())) == 0.0
+    assert [b.shape for b in m.return_Bcp_final()] == [(4, 2), (5, 2)]
+
+
+def test_convergence_rule_matches_reference():
+    """std:467-470: stop when sum |diff| of the last patience+1 losses < tol."""
+    from tensor_regression_b200 import standard_tensor_regression as STR
+    X, y, _ = O.synth_std(64, (4, 5), 2, 1)
+    nn = [False] * 3
+    B0 = O.init_std((4, 5), 2, nn)
+    m = STR.CP_linear_regression(X.shape, rank=2, Bcp_init=[b.clone() for b in B0], device=DEV)
+    conv = m.fit_Adam(X.to(DEV), y.to(DEV), lambda_L2=0.01, max_iter=400, tol=1e-2, patience=5,
+                      Adam_kwargs={'lr': 0.05})
+    ref = O.fit_adam_std(X, y, B0, torch.tensor([0.0]), torch.ones(2), nn, 0.01, len(m.loss_running), {'lr': 0.05})
+    L = ref['loss_running']
+    stop = next((ii for ii in range(len(L)) if ii > 5 and np.sum(np.abs(np.diff(L[ii - 5:ii + 1]))) < 1e-2), None)
+    assert conv is True and stop is not None and abs(len(m.loss_running) - (stop + 1)) <= 1
