@@ -237,3 +237,57 @@ class ShardedSum:
         """Global sum of a host scalar (N_total, sum of class weights) — done once, at fit start."""
         t = torch.tensor([float(value)], dtype=torch.float64, device=device)
         return float(self.sum_(t).item())
+
+
+class HostStreamer:
+    """Double-buffered host -> device streaming of a sample-major array that stays in host memory
+    (numpy array, np.memmap, CPU tensor, or anything with ``.shape`` and ``[lo:hi]`` slicing).
+
+    ``for lo, hi, xd in streamer.chunks(): ...`` yields device views valid until the next-but-one
+    iteration; the copy of chunk i+1 (pinned staging buffer -> device, on a side stream) overlaps
+    the kernels the caller enqueues for chunk i on the current stream.  Chunks that are already
+    pinned tensors are copied from in place (no staging copy)."""
+
+    def __init__(self, X, dtype, device, chunk_samples=None, chunk_bytes=1 << 30):
+        self.X, self.dtype, self.device = X, dtype, torch.device(device)
+        self.N = int(X.shape[0])
+        self.sample_shape = tuple(int(d) for d in X.shape[1:])
+        row = max(1, int(np.prod(self.sample_shape))) * torch.empty((), dtype=dtype).element_size()
+        if chunk_samples is None:
+            chunk_samples = max(1, chunk_bytes // row)
+        self.step = int(max(1, min(max(self.N, 1), chunk_samples)))
+        self.bytes_per_pass = self.N * row
+        self._copy = torch.cuda.Stream(device=self.device)
+        self._dev = [torch.empty((self.step, *self.sample_shape), dtype=dtype, device=self.device) for _ in range(2)]
+        self._pin = [None, None]
+        self._ready = [torch.cuda.Event() for _ in range(2)]
+        self._done = [torch.cuda.Event() for _ in range(2)]
+        self._used = [False, False]
+
+    def _host_chunk(self, lo, hi, s):
+        c = self.X[lo:hi]
+        if not isinstance(c, torch.Tensor):
+            c = torch.as_tensor(np.ascontiguousarray(c))
+        if c.dtype == self.dtype and c.is_contiguous() and c.is_pinned():
+            return c
+        if self._pin[s] is None:
+            self._pin[s] = torch.empty((self.step, *self.sample_shape), dtype=self.dtype, pin_memory=True)
+        self._pin[s][:hi - lo].copy_(c)
+        return self._pin[s][:hi - lo]
+
+    def chunks(self):
+        main = torch.cuda.current_stream(self.device)
+        for i, lo in enumerate(range(0, self.N, self.step)):
+            hi = min(self.N, lo + self.step)
+            s = i % 2
+            if self._used[s]:
+                self._done[s].synchronize()       # kernels reading dev[s] finished; staging buffer reusable
+            src = self._host_chunk(lo, hi, s)
+            self._copy.wait_event(self._done[s]) if self._used[s] else None
+            with torch.cuda.stream(self._copy):
+                self._dev[s][:hi - lo].copy_(src, non_blocking=True)
+                self._ready[s].record(self._copy)
+            main.wait_event(self._ready[s])
+            yield lo, hi, self._dev[s][:hi - lo]
+            self._done[s].record(main)
+            self._used[s] = True

@@ -313,12 +313,24 @@ class CP_linear_regression():
                  tol=1e-5,
                  patience=10,
                  verbose=False,
-                 Adam_kwargs=None):
+                 Adam_kwargs=None,
+                 *,
+                 out_of_core=False,
+                 chunk_samples=None):
         """std:400-476 — Adam; forward+gradient kernels, fused penalty/normalise kernel, fused
-        Adam kernel; one scalar device->host read per iteration (std:464)."""
+        Adam kernel; one scalar device->host read per iteration (std:464).
+
+        ``out_of_core=True`` (keyword-only extension; the reference's abandoned fit_batch_Adam,
+        std:478-620, done exactly): X stays in host memory (numpy / memmap / CPU tensor) and is
+        streamed to the device in chunks of ``chunk_samples`` every iteration; residuals depend
+        only on a chunk's own samples, so one host->device pass per iteration gives the exact
+        full-batch gradient."""
         if Adam_kwargs is None:
             raise TypeError('Adam_kwargs must be a dict of torch.optim.Adam keyword arguments (got None)')
         hyper = _adam_hyper(Adam_kwargs)
+        if out_of_core:
+            return self._fit_Adam_out_of_core(X, y, lambda_L2, max_iter, tol, patience, verbose, hyper,
+                                              chunk_samples)
         X, y = self._prep_xy(X, y)
         sharder = self._sharder()
         n_total = sharder.total(X.shape[0], X.device)
@@ -343,6 +355,49 @@ class CP_linear_regression():
             self.loss_running.append(loss[1].item())
             if verbose == 2:
                 print(f'Iteration: {ii}, Loss: {self.loss_running[-1]}  ;  Variance ratio (y_hat / y_true): {torch.var(y_hat).item() / torch.var(y).item()}')
+            if ii > patience:
+                if np.sum(np.abs(np.diff(self.loss_running[ii - patience:]))) < tol:
+                    convergence_reached = True
+                    break
+        if (verbose == True) or (verbose >= 1):  # noqa: E712
+            if convergence_reached:
+                print('Convergence reached')
+            else:
+                print('Reached maximum number of iterations without convergence')
+        return convergence_reached
+
+    def _fit_Adam_out_of_core(self, X, y, lambda_L2, max_iter, tol, patience, verbose, hyper, chunk_samples):
+        dev = self._torch_device()
+        y = torch.as_tensor(y).to(device=dev, dtype=self.dtype).reshape(-1).contiguous()
+        if int(X.shape[0]) != y.shape[0]:
+            raise ValueError('X.shape[0] must match len(y)')
+        streamer = _engine.HostStreamer(X, self.dtype, dev, chunk_samples=chunk_samples)
+        self.h2d_bytes_per_iteration = streamer.bytes_per_pass
+        sharder = self._sharder()
+        n_total = sharder.total(y.shape[0], dev)
+        eng = self._engine()
+        beta, thr = self._sp()
+        m = torch.zeros_like(self.theta)
+        v = torch.zeros_like(self.theta)
+        vmax = torch.zeros_like(self.theta) if hyper['amsgrad'] else None
+        gs = torch.zeros(eng.n_gradsum, dtype=torch.float64, device=dev)
+        gs_chunk = torch.empty_like(gs)
+        grad = torch.empty_like(self.theta)
+        loss = torch.empty(2, dtype=torch.float64, device=dev)
+        convergence_reached = False
+        for ii in range(max_iter):
+            gs.zero_()
+            for lo, hi, xd in streamer.chunks():
+                eng.fwd_grad_std(xd, y[lo:hi], self.theta, self.weights, self._mask(), beta, thr, gradsum=gs_chunk)
+                gs.add_(gs_chunk)
+            sharder.sum_(gs)
+            eng.finish(gs, 2.0 / n_total, 1.0 / n_total, self.theta, lambda_L2, self._mask(), beta, thr,
+                       grad=grad, loss=loss)
+            eng.adam_step(self.theta, grad, m, v, vmax, ii + 1, lr=hyper['lr'], betas=hyper['betas'],
+                          eps=hyper['eps'], weight_decay=hyper['weight_decay'])
+            self.loss_running.append(loss[1].item())
+            if verbose == 2:
+                print(f'Iteration: {ii}, Loss: {self.loss_running[-1]}')
             if ii > patience:
                 if np.sum(np.abs(np.diff(self.loss_running[ii - patience:]))) < tol:
                     convergence_reached = True
@@ -452,31 +507,10 @@ def _adam_hyper(Adam_kwargs):
 def _predict_streamed(X, dtype, device, fwd, chunk_bytes=256 << 20):
     """Forward over a host array in chunks: pinned staging buffers, copy stream overlapped with
     the kernels.  Returns numpy (N,) or (N, C)."""
-    Xt = torch.as_tensor(X)
-    if Xt.dtype != dtype:
-        Xt = Xt.to(dtype)
-    N = Xt.shape[0]
-    if N == 0:
-        return fwd(Xt.to(device)).cpu().numpy()
-    row = max(1, int(np.prod(Xt.shape[1:])) * Xt.element_size())
-    step = max(1, min(N, chunk_bytes // row))
-    outs = []
-    copy_stream = torch.cuda.Stream(device=device)
-    main = torch.cuda.current_stream(device)
-    bufs = [torch.empty((step, *Xt.shape[1:]), dtype=dtype, pin_memory=True) for _ in range(2)]
-    dev_bufs = [torch.empty((step, *Xt.shape[1:]), dtype=dtype, device=device) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    done = [torch.cuda.Event() for _ in range(2)]
-    for i, lo in enumerate(range(0, N, step)):
-        hi = min(N, lo + step)
-        s = i % 2
-        if i >= 2:
-            done[s].synchronize()                    # kernels that read dev_bufs[s] / pinned reuse
-        bufs[s][:hi - lo].copy_(Xt[lo:hi])
-        with torch.cuda.stream(copy_stream):
-            dev_bufs[s][:hi - lo].copy_(bufs[s][:hi - lo], non_blocking=True)
-            ready[s].record(copy_stream)
-        main.wait_event(ready[s])
-        outs.append(fwd(dev_bufs[s][:hi - lo]))
-        done[s].record(main)
+    if not hasattr(X, 'shape'):
+        X = np.asarray(X)
+    if X.shape[0] == 0:
+        return fwd(torch.as_tensor(np.asarray(X)).to(device=device, dtype=dtype)).cpu().numpy()
+    st = _engine.HostStreamer(X, dtype, device, chunk_bytes=chunk_bytes)
+    outs = [fwd(xd) for _, _, xd in st.chunks()]
     return torch.cat(outs).cpu().numpy()
