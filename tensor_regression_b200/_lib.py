@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libtrb200.so')
+LIB_PATH = os.environ.get('TR_B200_LIB') or os.path.join(_HERE, 'libtrb200.so')   # env override: kernel-variant experiments
 
 TR_F32, TR_F64 = 0, 1
 

@@ -320,7 +320,7 @@ int fwd_grad_std_t(tr_handle* h, const void* X, const void* y, long long N, cons
         k_epi_std<T><<<egrid, TR_TPB, 0, st>>>(ea);
         TR_LAUNCH_CHECK(h);
         // gradsum[pf] = sum res, gradsum[pf+1] = sum res^2
-        k_colsum<<<1, 32, 0, st>>>((const double*)h->epi_part.p, egrid, 2, gradsum + g.pf);
+        k_colsum<<<2, 128, 0, st>>>((const double*)h->epi_part.p, egrid, 2, gradsum + g.pf);
         TR_LAUNCH_CHECK(h);
         V = (const T*)h->V.p;
     } else {
@@ -360,13 +360,13 @@ int mn_t(tr_handle* h, const void* X, const long long* y, const void* class_w, l
     k_epi_mn<T><<<egrid, TR_TPB, esmem, st>>>(ea);
     TR_LAUNCH_CHECK(h);
     if (train) {
-        k_colsum<<<1, 32, 0, st>>>((const double*)h->epi_part.p, egrid, 1, gradsum + g.pf);
+        k_colsum<<<1, 128, 0, st>>>((const double*)h->epi_part.p, egrid, 1, gradsum + g.pf);
         TR_LAUNCH_CHECK(h);
         const int dgrid = (int)std::min<long long>((N + 63) / 64, (long long)h->sms * 2);
         k_dfc<T><<<dgrid, TR_TPB, 0, st>>>((const T*)h->dZ_ws.p, (const T*)h->u_ws.p, (const T*)w, N, g.C, g.R,
                                            (double*)h->dfc_part.p);
         TR_LAUNCH_CHECK(h);
-        k_colsum<<<(g.C * g.R + 127) / 128, 128, 0, st>>>((const double*)h->dfc_part.p, dgrid, g.C * g.R,
+        k_colsum<<<g.C * g.R, 128, 0, st>>>((const double*)h->dfc_part.p, dgrid, g.C * g.R,
                                                           gradsum + g.pfeat);
         TR_LAUNCH_CHECK(h);
         if ((rc = run_gradient<T>(h, (const T*)X, N, (const T*)h->V.p, (const T*)w, pl, e, gradsum, st))) return rc;

@@ -8,16 +8,16 @@ template <> struct VN<double> { static constexpr int v = 2; };
 
 template <typename T>
 struct KEntry {
-    int RK, E, U;                         // E in native 16-byte chunks per lane
+    int RK, E, Uf, Ug;                    // E in native 16-byte chunks per lane; samples in flight (fwd, grad)
     void (*fwd_vec)(FwdArgs<T>);
     void (*fwd_sc)(FwdArgs<T>);
     void (*grad_vec)(GradArgs<T>);
     void (*grad_sc)(GradArgs<T>);
 };
 
-#define TR_ENTRY(T, RK, E, U)                                                                       \
-    { RK, E, U, k_fwd<T, RK, E, U, VN<T>::v>, k_fwd<T, RK, E * VN<T>::v, U, 1>,                     \
-      k_grad<T, RK, E, U, VN<T>::v>, k_grad<T, RK, E * VN<T>::v, U, 1> }
+#define TR_ENTRY(T, RK, E, UF, UG)                                                                  \
+    { RK, E, UF, UG, k_fwd<T, RK, E, UF, VN<T>::v>, k_fwd<T, RK, E * VN<T>::v, UF, 1>,              \
+      k_grad<T, RK, E, UG, VN<T>::v>, k_grad<T, RK, E * VN<T>::v, UG, 1> }
 
 const KEntry<float>* tr_entries_f32_0(int* n);
 const KEntry<float>* tr_entries_f32_1(int* n);

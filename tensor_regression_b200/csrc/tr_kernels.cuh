@@ -20,6 +20,9 @@
 #include "tr_b200.h"
 
 #define TR_TPB 256
+#ifndef TR_MINB
+#define TR_MINB 2      // resident blocks per SM the streaming kernels are compiled for (<= 128 registers)
+#endif
 #define TR_WPB (TR_TPB / 32)
 #define TR_FULL 0xffffffffu
 
@@ -179,7 +182,7 @@ __device__ __noinline__ void tr_coef_at(const T* sF, const T* sW, const int* sDi
 }
 
 template <typename T, int RK, int E, int U, int VEC>
-__global__ void __launch_bounds__(TR_TPB, 2) k_fwd(const FwdArgs<T> a) {
+__global__ void __launch_bounds__(TR_TPB, TR_MINB) k_fwd(const FwdArgs<T> a) {
     extern __shared__ __align__(16) unsigned char tr_smem[];
     __shared__ int sDims[TR_MAX_MODES], sOff[TR_MAX_MODES + 2];
     T* sF = reinterpret_cast<T*>(tr_smem);
@@ -286,7 +289,7 @@ struct GradArgs {
 };
 
 template <typename T, int RK, int E, int U, int VEC>
-__global__ void __launch_bounds__(TR_TPB, 2) k_grad(const GradArgs<T> a) {
+__global__ void __launch_bounds__(TR_TPB, TR_MINB) k_grad(const GradArgs<T> a) {
     constexpr int TILE = 32 * E * VEC;
     const int lane = threadIdx.x & 31;
     const long long warp_global = (long long)blockIdx.x * TR_WPB + (threadIdx.x >> 5);

@@ -246,13 +246,15 @@ __global__ void __launch_bounds__(TR_TPB) k_dfc(const T* __restrict__ dZ, const 
     }
 }
 
-// out[dst_off + j*dst_stride... ] column sums of a (rows, cols) double matrix: out[map(j)] = sum_b part[b, j]
-__global__ void k_colsum(const double* __restrict__ part, int rows, int cols, double* __restrict__ out) {
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < cols; j += gridDim.x * blockDim.x) {
-        double s = 0.0;
-        for (int b = 0; b < rows; ++b) s += part[(long long)b * cols + j];
-        out[j] = s;
-    }
+// out[j] = sum_b part[b, j] for a (rows, cols) double matrix; one block per column (deterministic)
+__global__ void __launch_bounds__(128) k_colsum(const double* __restrict__ part, int rows, int cols,
+                                                 double* __restrict__ out) {
+    __shared__ double sbuf[32];
+    const int j = blockIdx.x;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < rows; b += blockDim.x) s += part[(long long)b * cols + j];
+    s = block_sum(s, sbuf);
+    if (threadIdx.x == 0) out[j] = s;
 }
 
 // sum of a T vector (for tr_backward_std's dbias) -> out[0]; single block
