@@ -245,6 +245,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--fused', type=int, default=-1, help='-1 auto, 0 two-pass kernels, 1 single-pass kernel')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -302,6 +303,7 @@ def main():
         model = None
         cw = torch.ones(C, device=device)
     n_total = sharder.total(n_local, device)
+    eng.set_option('fused', args.fused)
 
     theta = (model.theta if model is not None else
              torch.cat([b.reshape(-1) for b in B0]).to(device=device, dtype=torch.float32).contiguous())
@@ -363,18 +365,38 @@ def main():
     peak, peak_src = peaks()
     fwd_ms = prof['fwd_ms'] / max(1, prof['fwd_launches'])
     grad_ms = prof['grad_ms'] / max(1, prof['grad_launches'])
-    dom = 'k_grad' if grad_ms >= fwd_ms else 'k_fwd'
-    dom_ms = max(grad_ms, fwd_ms)
-    achieved = x_bytes / (dom_ms * 1e-3) / 1e9
+    fused_ms = prof['fused_ms'] / max(1, prof['fused_launches'])
+    ratios = {}
+    try:
+        ratios = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_ratios.json')))
+    except Exception:
+        pass
+    if prof['fused_launches'] > 0:
+        # single-pass kernel: does the work of both passes (algorithmic bytes = 2 x bytes(X))
+        # while reading X from HBM once -> "achieved" exceeds the HBM peak by design; traffic shows the real bytes
+        dom, dom_ms, alg = 'k_fused_std', fused_ms, 2 * x_bytes
+        extra = {'k_fused_ms': fused_ms, 'hbm_gbs_actual': x_bytes / (fused_ms * 1e-3) / 1e9,
+                 'hbm_frac_actual': x_bytes / (fused_ms * 1e-3) / 1e9 / peak,
+                 'note': 'single-pass kernel: the second pass over X is served from shared memory, so DRAM traffic '
+                         'is 1 x bytes(X) while the algorithmic (2-pass) byte count is 2 x bytes(X)',
+                 'share_of_step': {'k_fused_std': fused_ms / ms_per_step}}
+    else:
+        dom = 'k_grad' if grad_ms >= fwd_ms else 'k_fwd'
+        dom_ms, alg = max(grad_ms, fwd_ms), x_bytes
+        extra = {'k_fwd_ms': fwd_ms, 'k_grad_ms': grad_ms,
+                 'k_fwd_gbs': x_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None,
+                 'k_grad_gbs': x_bytes / (grad_ms * 1e-3) / 1e9 if grad_ms else None,
+                 'share_of_step': {'k_fwd': fwd_ms / ms_per_step, 'k_grad': grad_ms / ms_per_step}}
+    achieved = alg / (dom_ms * 1e-3) / 1e9
+    tr = ratios.get(dom)
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': x_bytes,
-                'k_fwd_ms': fwd_ms, 'k_grad_ms': grad_ms,
-                'k_fwd_gbs': x_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None,
-                'k_grad_gbs': x_bytes / (grad_ms * 1e-3) / 1e9 if grad_ms else None,
+                'frac': achieved / peak,
+                'traffic': (tr['dram_bytes_per_algorithmic_byte'] * alg) if tr else None,
+                'traffic_source': tr['source'] if tr else None,
+                'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg,
                 'iteration_gbs': 2 * x_bytes / (ms_per_step * 1e-3) / 1e9,
-                'iteration_frac_of_2pass_roofline': 2 * x_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
-                'share_of_step': {'k_fwd': fwd_ms / ms_per_step, 'k_grad': grad_ms / ms_per_step}}
+                'iteration_frac_of_2pass_roofline': 2 * x_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
+    roofline.update(extra)
 
     # ---- end to end through the public API with HOST buffers (std workloads) -----------------
     e2e = None

@@ -123,14 +123,21 @@ int tr_adam_step(tr_handle* h, void* theta, const void* grad, void* m, void* v, 
 
 /* Optional timing of the two streaming kernels with CUDA events recorded on the launching stream
  * (what bench.py's roofline uses).  tr_profile_enable(h, 1) resets the sums; tr_profile_read waits
- * for the last recorded launch and returns out4 = { forward-pass ms total, forward launches,
- * gradient-pass ms total, gradient launches } (host doubles). */
+ * for the last recorded launch and returns out6 = { forward-pass ms total, forward launches,
+ * gradient-pass ms total, gradient launches, fused single-pass ms total, fused launches }. */
 int tr_profile_enable(tr_handle* h, int enable);
-int tr_profile_read(tr_handle* h, double* out4);
+int tr_profile_read(tr_handle* h, double* out6);
+
+/* Options.  "fused": -1 = auto (default; env TR_B200_FUSED overrides), 0 = always the two-pass
+ * kernels, 1 = always the single-pass cluster kernel of tr_fwd_grad_std (error if the geometry
+ * does not fit a cluster's shared memory). */
+int tr_set_option(tr_handle* h, const char* name, int64_t value);
 
 /* How the last tr_fwd_grad_* / tr_forward_* call was executed (host ints):
  * info[0]=kernel launches, [1]=forward grid, [2]=gradient grid, [3]=tiles per sample,
- * [4]=sample groups (forward), [5]=sample groups (gradient), [6]=channels RK, [7]=vector width. */
+ * [4]=sample groups (forward), [5]=sample groups (gradient), [6]=channels RK, [7]=vector width.
+ * After a single-pass launch: [1]=grid, [2]=cluster size, [3]=stages, [4]=clusters, [5]=chunks,
+ * [7]= -(vector width). */
 int tr_last_launch_info(tr_handle* h, int64_t* info8);
 
 #ifdef __cplusplus

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -11,6 +12,7 @@
 #include "tr_kernels.cuh"
 #include "tr_dispatch.h"
 #include "tr_small.cuh"
+#include "tr_fused.cuh"
 
 namespace {
 
@@ -84,10 +86,13 @@ struct tr_handle {
     int launches = 0;
     // optional in-stream timing of the two streaming kernels (tr_profile_*)
     bool prof = false;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fwd begin/end, grad begin/end
-    bool ev_set[2] = {false, false};
-    double prof_ms[2] = {0.0, 0.0};
-    long long prof_n[2] = {0, 0};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fwd, grad, fused: begin/end
+    bool ev_set[3] = {false, false, false};
+    double prof_ms[3] = {0.0, 0.0, 0.0};
+    long long prof_n[3] = {0, 0, 0};
+    int fused_mode = -1;                // -1 auto, 0 never, 1 always (error when not eligible)
+    int last_fused = 0;
+    std::map<const void*, int> occ_clusters;
 };
 
 namespace {
@@ -218,7 +223,7 @@ inline bool vec_ok(const void* X, long long D, size_t elt) {
 
 // Adds the elapsed time of the previous (already finished) recorded launches to the running sums.
 int prof_fold(tr_handle* h, bool wait) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         if (!h->ev_set[i]) continue;
         if (wait) TR_CUDA(h, cudaEventSynchronize(h->ev[2 * i + 1]));
         else if (cudaEventQuery(h->ev[2 * i + 1]) != cudaSuccess) { cudaGetLastError(); TR_CUDA(h, cudaEventSynchronize(h->ev[2 * i + 1])); }
@@ -278,6 +283,143 @@ int run_gradient(tr_handle* h, const T* X, long long N, const T* V, const T* w, 
     return TR_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// single-pass fused path (standard model): plan + launch
+// ---------------------------------------------------------------------------------------------
+struct FusedPlan {
+    int CL, E, NS, NC, nchunk;
+    long long spc;
+    unsigned stage_bytes;
+    size_t smem;
+    int Dc;
+};
+
+template <typename T> using FusedKern = void (*)(FusedArgs<T>);
+template <typename T>
+FusedKern<T> fused_kernel(int E) {
+    switch (E) {
+        case 1: return k_fused_std<T, 1>;
+        case 2: return k_fused_std<T, 2>;
+        case 3: return k_fused_std<T, 3>;
+        case 4: return k_fused_std<T, 4>;
+        case 5: return k_fused_std<T, 5>;
+        case 6: return k_fused_std<T, 6>;
+        case 7: return k_fused_std<T, 7>;
+        case 8: return k_fused_std<T, 8>;
+    }
+    return nullptr;
+}
+
+// returns TR_OK and fp->CL > 0 when the geometry fits a cluster's shared memory, fp->CL = 0 otherwise
+template <typename T>
+int plan_fused(tr_handle* h, long long N, const void* X, FusedPlan* fp) {
+    fp->CL = 0;
+    const Geo& g = h->geo;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    if (g.C != 0 || !vec_ok(X, g.D, sizeof(T)) || N < 1) return TR_OK;
+    const size_t fixed = 128 + 2 * (TR_FUSED_NT / 32) * sizeof(double) + 2 * TR_FUSED_MAX_CL * sizeof(double) +
+                         ((size_t)(g.pfeat + g.R) * sizeof(T) + 15) / 16 * 16 + (2 * TR_MAX_MODES + 2) * sizeof(int);
+    const size_t budget = 226 * 1024;
+    for (int CL = 1; CL <= TR_FUSED_MAX_CL; CL *= 2) {
+        if (g.D % ((long long)CL * VEC) != 0) continue;
+        const long long Dc = g.D / CL;
+        const long long chunks = Dc / VEC;
+        const int E = (int)((chunks + TR_FUSED_NT - 1) / TR_FUSED_NT);
+        if (E > 8) continue;
+        const size_t stage = (size_t)Dc * sizeof(T);
+        if (fixed + 3 * stage > budget) continue;
+        int NS = (int)((budget - fixed) / stage);
+        if (NS > 6) NS = 6;
+        auto kern = fused_kernel<T>(E);
+        const size_t smem = fixed + (size_t)NS * stage;
+        // resident clusters of this (kernel, cluster size): queried once per handle
+        const void* key = (const void*)((uintptr_t)kern + (uintptr_t)CL);
+        int NC = 0;
+        auto it = h->occ_clusters.find(key);
+        if (it != h->occ_clusters.end()) {
+            NC = it->second;
+        } else {
+            TR_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (CL > 8) {
+                if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); h->occ_clusters[key] = 0; continue; }
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(CL * h->sms), 1, 1);
+            cfg.blockDim = dim3(TR_FUSED_NT, 1, 1);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&NC, kern, &cfg);
+            if (e != cudaSuccess) { cudaGetLastError(); NC = 0; }
+            h->occ_clusters[key] = NC;
+        }
+        if (NC < 1) continue;
+        if ((long long)NC * CL * 10 < (long long)h->sms * 6) continue;       // would leave > 40 % of the SMs idle
+        if (NC > N) NC = (int)N;
+        fp->CL = CL; fp->E = E; fp->NS = NS; fp->NC = NC; fp->stage_bytes = (unsigned)stage; fp->smem = smem; fp->Dc = (int)Dc;
+        const long long cnt = (N + NC - 1) / NC;
+        const long long target = sizeof(T) == 4 ? 2048 : (1LL << 40);
+        long long nchunk = std::max<long long>(1, (cnt + target - 1) / target);
+        const size_t slot_bytes = (size_t)g.D * sizeof(T);
+        while (nchunk > 1 && (size_t)nchunk * NC * slot_bytes > ((size_t)1 << 30)) --nchunk;
+        fp->nchunk = (int)nchunk;
+        fp->spc = std::max<long long>(1, (cnt + nchunk - 1) / nchunk);
+        return TR_OK;
+    }
+    return TR_OK;
+}
+
+template <typename T>
+int run_fused_std(tr_handle* h, const T* X, const T* y, long long N, const T* theta, const T* w, uint32_t nn_mask,
+                  double beta, double thr, const FusedPlan& fp, double* gradsum, T* yhat, cudaStream_t st) {
+    const Geo& g = h->geo;
+    int rc;
+    if ((rc = ensure(h, h->FtT, (size_t)g.pf * sizeof(T)))) return rc;
+    if ((rc = ensure(h, h->Ft64, (size_t)g.pf * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->Gpart, (size_t)fp.NC * fp.nchunk * g.D * sizeof(T)))) return rc;
+    if ((rc = ensure(h, h->Gred, (size_t)g.D * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->epi_part, (size_t)std::max(h->sms * 8, fp.NC) * 2 * sizeof(double)))) return rc;
+    k_prep<T><<<std::max(1, std::min(64, (g.pf + 255) / 256)), 256, 0, st>>>(theta, g, nn_mask, beta, thr,
+                                                                           (T*)h->FtT.p, (double*)h->Ft64.p);
+    TR_LAUNCH_CHECK(h);
+    FusedArgs<T> fa;
+    fa.X = X; fa.y = y; fa.N = N; fa.FtT = (const T*)h->FtT.p; fa.w = w; fa.theta = theta; fa.bias_off = g.pf; fa.geo = g;
+    fa.Gpart = (T*)h->Gpart.p; fa.Dpad = g.D; fa.yhat = yhat; fa.part = (double*)h->epi_part.p;
+    fa.CL = fp.CL; fa.NC = fp.NC; fa.Dc = fp.Dc; fa.NS = fp.NS; fa.nchunk = fp.nchunk; fa.spc = fp.spc;
+    fa.stage_bytes = fp.stage_bytes;
+    auto kern = fused_kernel<T>(fp.E);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(fp.CL * fp.NC), 1, 1);
+    cfg.blockDim = dim3(TR_FUSED_NT, 1, 1);
+    cfg.dynamicSmemBytes = fp.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)fp.CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (h->prof) { rc = prof_fold(h, false); if (rc) return rc; TR_CUDA(h, cudaEventRecord(h->ev[4], st)); }
+    TR_CUDA(h, cudaLaunchKernelEx(&cfg, kern, fa));
+    TR_LAUNCH_CHECK(h);
+    if (h->prof) { TR_CUDA(h, cudaEventRecord(h->ev[5], st)); h->ev_set[2] = true; }
+    k_colsum<<<2, 128, 0, st>>>((const double*)h->epi_part.p, fp.NC, 2, gradsum + g.pf);
+    TR_LAUNCH_CHECK(h);
+    const int rgrid = (int)std::min<long long>((g.D + 255) / 256, (long long)h->sms * 8);
+    k_reduce_G<T><<<rgrid, 256, 0, st>>>((const T*)h->Gpart.p, fp.NC * fp.nchunk, 1, g.D, g.D, (double*)h->Gred.p);
+    TR_LAUNCH_CHECK(h);
+    MtArgs ma;
+    ma.G = (const double*)h->Gred.p; ma.Ft64 = (const double*)h->Ft64.p; ma.w = w;
+    ma.w_is_f64 = sizeof(T) == 8; ma.per_rank = 0; ma.geo = g; ma.gradsum = gradsum;
+    int rows = 0;
+    for (int m = 0; m < g.k; ++m) rows += g.dims[m];
+    k_mttkrp<<<rows, TR_TPB, 0, st>>>(ma);
+    TR_LAUNCH_CHECK(h);
+    h->info[0] = h->launches; h->info[1] = fp.CL * fp.NC; h->info[2] = fp.CL; h->info[3] = fp.NS;
+    h->info[4] = fp.NC; h->info[5] = fp.nchunk; h->info[6] = 1; h->info[7] = -(16 / (int)sizeof(T));
+    return TR_OK;
+}
+
 void set_info(tr_handle* h, const Plan& pl) {
     h->info[0] = h->launches; h->info[1] = pl.grid_f; h->info[2] = pl.grid_g; h->info[3] = pl.WT;
     h->info[4] = pl.Gn_f; h->info[5] = pl.Gn_g; h->info[6] = pl.RKs; h->info[7] = pl.vec ? (int)(16 / h->elt) : 1;
@@ -307,6 +449,21 @@ int fwd_grad_std_t(tr_handle* h, const void* X, const void* y, long long N, cons
                    bool backward_only) {
     Plan pl; const KEntry<T>* e; int rc;
     const Geo& g = h->geo;
+    h->last_fused = 0;
+    if (!backward_only && h->fused_mode != 0) {
+        FusedPlan fp;
+        if ((rc = plan_fused<T>(h, N, X, &fp))) return rc;
+        // auto: the single-pass kernel pays once every cluster has a few samples to pipeline
+        const bool want = fp.CL > 0 && (h->fused_mode == 1 || N >= 8LL * fp.NC);
+        if (h->fused_mode == 1 && fp.CL == 0)
+            return fail(h, TR_ERR_UNSUPPORTED, "fused=1 requested but this geometry / alignment is not eligible for the single-pass kernel");
+        if (want) {
+            h->launches = 0;
+            h->last_fused = 1;
+            return run_fused_std<T>(h, (const T*)X, (const T*)y, N, (const T*)theta, (const T*)w, nn_mask, beta, thr,
+                                    fp, gradsum, (T*)yhat, st);
+        }
+    }
     if ((rc = make_plan<T>(h, N, 1, vec_ok(X, g.D, sizeof(T)), &pl, &e))) return rc;
     if ((rc = reserve_for<T>(h, N, pl))) return rc;
     h->launches = 0;
@@ -431,6 +588,7 @@ int tr_create(tr_handle** out, int dtype, int k, const int64_t* dims, int R, int
     if (e != cudaSuccess) { delete h; return fail(nullptr, TR_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
     if (prop.major < 10) { delete h; return fail(nullptr, TR_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); }
     h->sms = prop.multiProcessorCount;
+    if (const char* ev = getenv("TR_B200_FUSED")) h->fused_mode = atoi(ev) < 0 ? -1 : (atoi(ev) > 0 ? 1 : 0);
     *out = h;
     return TR_OK;
 }
@@ -441,7 +599,7 @@ int tr_destroy(tr_handle* h) {
     cudaDeviceSynchronize();
     Buf* bufs[] = {&h->FtT, &h->Ft64, &h->partial, &h->V, &h->u_ws, &h->dZ_ws, &h->Gpart, &h->Gred, &h->epi_part, &h->dfc_part};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
-    for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
     return TR_OK;
 }
@@ -603,21 +761,30 @@ int tr_profile_enable(tr_handle* h, int enable) {
     if (!h) return TR_ERR_INVALID;
     DeviceGuard dg(h->device);
     if (enable && !h->ev[0])
-        for (int i = 0; i < 4; ++i) TR_CUDA(h, cudaEventCreate(&h->ev[i]));
+        for (int i = 0; i < 6; ++i) TR_CUDA(h, cudaEventCreate(&h->ev[i]));
     if (h->prof && !enable) { int rc = prof_fold(h, true); if (rc) return rc; }
     h->prof = enable != 0;
-    if (enable) { h->prof_ms[0] = h->prof_ms[1] = 0.0; h->prof_n[0] = h->prof_n[1] = 0; h->ev_set[0] = h->ev_set[1] = false; }
+    if (enable) for (int i = 0; i < 3; ++i) { h->prof_ms[i] = 0.0; h->prof_n[i] = 0; h->ev_set[i] = false; }
     return TR_OK;
 }
 
-int tr_profile_read(tr_handle* h, double* out4) {
-    if (!h || !out4) return TR_ERR_INVALID;
+int tr_profile_read(tr_handle* h, double* out6) {
+    if (!h || !out6) return TR_ERR_INVALID;
     DeviceGuard dg(h->device);
     int rc = prof_fold(h, true);
     if (rc) return rc;
-    out4[0] = h->prof_ms[0]; out4[1] = (double)h->prof_n[0];
-    out4[2] = h->prof_ms[1]; out4[3] = (double)h->prof_n[1];
+    for (int i = 0; i < 3; ++i) { out6[2 * i] = h->prof_ms[i]; out6[2 * i + 1] = (double)h->prof_n[i]; }
     return TR_OK;
+}
+
+int tr_set_option(tr_handle* h, const char* name, int64_t value) {
+    if (!h || !name) return TR_ERR_INVALID;
+    if (strcmp(name, "fused") == 0) {
+        if (value < -1 || value > 1) return fail(h, TR_ERR_INVALID, "option fused: -1 (auto), 0 (two-pass), 1 (single-pass)");
+        h->fused_mode = (int)value;
+        return TR_OK;
+    }
+    return fail(h, TR_ERR_INVALID, "unknown option '%s'", name);
 }
 
 int tr_last_launch_info(tr_handle* h, int64_t* info8) {

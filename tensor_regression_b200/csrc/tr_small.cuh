@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(TR_TPB) k_epi_std(const EpiStdArgs<T> a) {
     for (long long n = warp_global; n < a.N; n += wtot) {
         const T* p = a.partial + n * a.WT;
         double s = 0.0;
-        for (int t = lane; t < a.WT; t += 32) s += (double)p[t];
+#pragma unroll 4
+        for (int t = lane; t < a.WT; t += 32) s += (double)__ldg(p + t);
         s = warp_sum(s);
         if (lane == 0) {
             const T yh = (T)(s + bias);                // yhat in the model dtype, as the reference returns it
@@ -113,18 +114,22 @@ __global__ void __launch_bounds__(TR_TPB) k_epi_mn(const EpiMnArgs<T> a) {
     const int R = a.R, C = a.C;
     double loss = 0.0;
     for (long long n = warp_global; n < a.N; n += wtot) {
-        // u[r] = sum over warp tiles
+        // u[r] = sum over warp tiles: lane t-strided, all channels of a tile are contiguous, so every
+        // lane keeps RKs independent accumulators and several tiles' loads in flight
         double u[TR_MAX_RANK_MN];
         const T* p = a.partial + n * a.WT * a.RKs;
 #pragma unroll
-        for (int r = 0; r < TR_MAX_RANK_MN; ++r) {
-            u[r] = 0.0;
-            if (r < R) {
-                double s = 0.0;
-                for (int t = lane; t < a.WT; t += 32) s += (double)p[t * a.RKs + r];
-                u[r] = warp_sum(s);
-            }
+        for (int r = 0; r < TR_MAX_RANK_MN; ++r) u[r] = 0.0;
+#pragma unroll 2
+        for (int t = lane; t < a.WT; t += 32) {
+            const T* pt = p + (long long)t * a.RKs;
+#pragma unroll
+            for (int r = 0; r < TR_MAX_RANK_MN; ++r)
+                if (r < R) u[r] += (double)__ldg(pt + r);
         }
+#pragma unroll
+        for (int r = 0; r < TR_MAX_RANK_MN; ++r)
+            if (r < R) u[r] = warp_sum(u[r]);
         // logits of this lane's classes, softmax
         double z[TR_JC], P[TR_JC];
         double zmax = -INFINITY;

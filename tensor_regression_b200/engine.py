@@ -111,18 +111,31 @@ class Engine:
     def launch_info(self):
         info = (ctypes.c_int64 * 8)()
         _lib.lib.tr_last_launch_info(self._h, info)
+        if int(info[7]) < 0:
+            keys = ['launches', 'grid', 'cluster_size', 'stages', 'clusters', 'chunks', 'channels', 'vector_width']
+            d = dict(zip(keys, [int(v) for v in info]))
+            d['vector_width'] = -d['vector_width']
+            d['path'] = 'single-pass (cluster-resident sample)'
+            return d
         keys = ['launches', 'grid_fwd', 'grid_grad', 'tiles_per_sample', 'groups_fwd', 'groups_grad', 'channels',
                 'vector_width']
-        return dict(zip(keys, [int(v) for v in info]))
+        d = dict(zip(keys, [int(v) for v in info]))
+        d['path'] = 'two-pass'
+        return d
 
     def profile(self, enable=True):
         """Start (and reset) / stop CUDA-event timing of the two streaming kernels."""
         self._ck(_lib.lib.tr_profile_enable(self._h, 1 if enable else 0))
 
     def profile_read(self):
-        out = (ctypes.c_double * 4)()
+        out = (ctypes.c_double * 6)()
         self._ck(_lib.lib.tr_profile_read(self._h, out))
-        return {'fwd_ms': out[0], 'fwd_launches': int(out[1]), 'grad_ms': out[2], 'grad_launches': int(out[3])}
+        return {'fwd_ms': out[0], 'fwd_launches': int(out[1]), 'grad_ms': out[2], 'grad_launches': int(out[3]),
+                'fused_ms': out[4], 'fused_launches': int(out[5])}
+
+    def set_option(self, name, value):
+        """'fused': -1 auto, 0 two-pass kernels only, 1 single-pass cluster kernel only."""
+        self._ck(_lib.lib.tr_set_option(self._h, name.encode(), int(value)))
 
     # -- the hot path --------------------------------------------------------------------------
     def forward_std(self, X, theta, w, nn_mask, beta, thr):

@@ -373,3 +373,63 @@ def test_convergence_rule_matches_reference():
     L = ref['loss_running']
     stop = next((ii for ii in range(len(L)) if ii > 5 and np.sum(np.abs(np.diff(L[ii - 5:ii + 1]))) < 1e-2), None)
     assert conv is True and stop is not None and abs(len(m.loss_running) - (stop + 1)) <= 1
+
+
+# ------------------------------------------------------------------------------------------
+# single-pass cluster kernel (tr_fwd_grad_std, option fused=1) vs two-pass vs oracle
+# ------------------------------------------------------------------------------------------
+FUSED_CASES = [
+    ('cfg2_shape_cl8', 300, (64, 64, 32), 8, torch.float32),
+    ('cfg1_cl2', 2000, (20, 30, 40), 5, torch.float32),
+    ('cfg4_shape_f64', 40, (16, 16, 16, 32), 12, torch.float64),
+    ('tiny_cl1', 257, (8, 6, 16), 3, torch.float32),
+    ('single_sample', 1, (64, 64, 32), 2, torch.float32),
+    ('fewer_samples_than_clusters', 5, (32, 16, 8), 2, torch.float64),
+    ('long_sums_chunked', 40000, (16, 16), 3, torch.float32),
+]
+
+
+@pytest.mark.parametrize('name,N,dims,R,dt', FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
+def test_fused_single_pass_matches_two_pass_and_oracle(name, N, dims, R, dt):
+    X, y, _ = O.synth_std(N, dims, R, 1234 + 7, dtype=dt)
+    y = y.reshape(-1)
+    nn = [True] + [False] * len(dims)
+    B0 = O.init_std(dims, R, nn, dtype=dt)
+    bias = torch.tensor([0.07], dtype=dt)
+    w = torch.linspace(0.5, 1.5, R, dtype=dt)
+    eng = engine_for(dims, R, 0, dt)
+    theta = dev(O.pack(B0, bias))
+    Xd, yd, wd = dev(X), dev(y), dev(w)
+    eng.set_option('fused', 0)
+    yh2 = torch.empty_like(yd)
+    two = eng.fwd_grad_std(Xd, yd, theta, wd, 1, 50.0, 1.0, yhat=yh2).clone()
+    assert eng.launch_info()['path'] == 'two-pass'
+    eng.set_option('fused', 1)
+    yh1 = torch.empty_like(yd)
+    one = eng.fwd_grad_std(Xd, yd, theta, wd, 1, 50.0, 1.0, yhat=yh1).clone()
+    info = eng.launch_info()
+    assert info['path'].startswith('single-pass'), info
+    cf = O.closed_form_std(X.double(), y.double(), [b.double() for b in B0], bias.double(), w.double(), nn)
+    tol = TOL[dt]
+    assert rel(yh1, cf['y_hat']) < tol and rel(yh2, cf['y_hat']) < tol
+    assert rel(one, cf['gradsum']) < tol, (rel(one, cf['gradsum']), info)
+    assert rel(two, cf['gradsum']) < tol
+    assert rel(one, two) < tol
+    # deterministic: same bits on a second launch
+    again = eng.fwd_grad_std(Xd, yd, theta, wd, 1, 50.0, 1.0)
+    assert torch.equal(again, one)
+    eng.set_option('fused', -1)
+
+
+def test_fused_not_eligible_falls_back_loudly():
+    from tensor_regression_b200 import engine
+    dims, R = (5, 7, 3), 2                       # D = 105: rows are not 16-byte multiples
+    X, y, _ = O.synth_std(64, dims, R, 3)
+    eng = engine_for(dims, R, 0, torch.float32)
+    theta = dev(O.pack(O.init_std(dims, R, [False] * 4), torch.tensor([0.0])))
+    eng.set_option('fused', 1)
+    with pytest.raises(engine.TRError):
+        eng.fwd_grad_std(dev(X), dev(y).reshape(-1), theta, dev(torch.ones(R)), 0, 50.0, 1.0)
+    eng.set_option('fused', -1)
+    eng.fwd_grad_std(dev(X), dev(y).reshape(-1), theta, dev(torch.ones(R)), 0, 50.0, 1.0)
+    assert eng.launch_info()['path'] == 'two-pass'
