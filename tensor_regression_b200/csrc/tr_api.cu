@@ -317,19 +317,18 @@ int plan_fused(tr_handle* h, long long N, const void* X, FusedPlan* fp) {
     const Geo& g = h->geo;
     constexpr int VEC = 16 / (int)sizeof(T);
     if (g.C != 0 || !vec_ok(X, g.D, sizeof(T)) || N < 1) return TR_OK;
-    const size_t fixed = 128 + 2 * (TR_FUSED_NT / 32) * sizeof(double) + 2 * TR_FUSED_MAX_CL * sizeof(double) +
-                         ((size_t)(g.pfeat + g.R) * sizeof(T) + 15) / 16 * 16 + (2 * TR_MAX_MODES + 2) * sizeof(int);
+    const size_t fixed = ((sizeof(FusedCtl) + 15) / 16) * 16 + ((size_t)(g.pfeat + g.R) * sizeof(T) + 15) / 16 * 16;
     const size_t budget = 226 * 1024;
     for (int CL = 1; CL <= TR_FUSED_MAX_CL; CL *= 2) {
         if (g.D % ((long long)CL * VEC) != 0) continue;
         const long long Dc = g.D / CL;
         const long long chunks = Dc / VEC;
-        const int E = (int)((chunks + TR_FUSED_NT - 1) / TR_FUSED_NT);
+        const int E = (int)((chunks + TR_FUSED_NCT - 1) / TR_FUSED_NCT);
         if (E > 8) continue;
         const size_t stage = (size_t)Dc * sizeof(T);
         if (fixed + 3 * stage > budget) continue;
         int NS = (int)((budget - fixed) / stage);
-        if (NS > 6) NS = 6;
+        if (NS > TR_FUSED_MAX_NS) NS = TR_FUSED_MAX_NS;
         auto kern = fused_kernel<T>(E);
         const size_t smem = fixed + (size_t)NS * stage;
         // resident clusters of this (kernel, cluster size): queried once per handle

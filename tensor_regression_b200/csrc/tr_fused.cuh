@@ -1,23 +1,32 @@
 // tr_fused.cuh — single-pass fused forward + gradient kernel for the standard model (SURVEY H8 ii).
 //
 // One thread-block CLUSTER holds one sample of X in its distributed shared memory: CTA c of a
-// CL-CTA cluster owns the contiguous slice [c*Dc, (c+1)*Dc) of the feature axis.  Per sample:
-//   1. the slice arrives in shared memory by TMA bulk copies (cp.async.bulk + mbarrier
-//      complete_tx), NS stages deep, issued one sample ahead of the compute;
-//   2. phase A: every thread dots its 16-byte chunks (read from shared memory) with its register-
-//      resident slice of the CP coefficient B[i]; block reduction -> the CTA's partial of y_hat;
-//   3. the CL partials are exchanged through DSMEM (st.shared::cluster to every peer) and a
-//      cluster barrier; every CTA forms y_hat_n, res_n in the same fixed order;
-//   4. phase B: G[i] += res_n * X[n,i] from the SAME shared-memory stage — the second pass over
-//      X never touches HBM (that is the whole point: X is streamed from HBM once per iteration).
-// The cluster barrier of sample i is overlapped with phase B of sample i-1 and phase A of i+1.
+// CL-CTA cluster owns the contiguous slice [c*Dc, (c+1)*Dc) of the feature axis, NS stages deep.
+// X is streamed from HBM ONCE per fit iteration; the second pass (gradient) reads the sample from
+// shared memory.  Everything is asynchronous and mbarrier-driven — no block-wide or cluster-wide
+// barrier sits in the sample loop, so the warps of a CTA drift freely within the NS-stage window:
+//
+//   producer thread   TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) of the CTA's slice of
+//                     sample j into stage j % NS as soon as all compute warps released it (empty[s]).
+//   16 compute warps  phase A(i): dot the warp's 16-byte chunks (shared memory) with the register-
+//                     resident CP coefficients B[i] -> warp partial of y_hat -> pA[i%NS][warp], arrive
+//                     on redA.  Then phase B(i-L), L = NS-2 samples behind: wait for res_{i-L},
+//                     G += res * x from the still-resident stage, release the stage.
+//   reducer thread    sums the 16 warp partials, publishes the CTA partial to EVERY CTA of the cluster
+//                     through DSMEM (st.shared::cluster + remote mbarrier arrive), waits until all CL
+//                     partials of the sample arrived, forms y_hat_n and res_n in a fixed order
+//                     (bit-identical in every CTA), hands res to the compute warps (rready).
+//
 // Outputs have the same layout as the two-pass path (Gpart slots, loss partials, y_hat), so the
-// reduction / MTTKRP / finish kernels are shared.
+// reduction / MTTKRP / finish kernels are shared.  Deterministic: no atomics, fixed summation orders.
 #pragma once
 #include "tr_kernels.cuh"
 
-#define TR_FUSED_NT 512
+#define TR_FUSED_NWC 16                               // compute warps
+#define TR_FUSED_NCT (TR_FUSED_NWC * 32)              // compute threads
+#define TR_FUSED_NT (TR_FUSED_NCT + 64)               // + producer warp + reducer warp
 #define TR_FUSED_MAX_CL 16
+#define TR_FUSED_MAX_NS 6
 
 template <typename T>
 struct FusedArgs {
@@ -36,7 +45,7 @@ struct FusedArgs {
     int CL;              // CTAs per cluster
     int NC;              // clusters in the grid
     int Dc;              // feature elements per CTA slice (D / CL)
-    int NS;              // shared-memory stages per CTA
+    int NS;              // shared-memory stages per CTA (>= 3)
     int nchunk;          // G is flushed to a fresh slot every spc samples (bounds fp32 sum length)
     long long spc;
     unsigned stage_bytes;  // Dc * sizeof(T), multiple of 16
@@ -51,6 +60,14 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster; release at cluster scope
+// orders the preceding st.shared::cluster of this thread before the arrival
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_addr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
     unsigned ok;
     asm volatile(
@@ -60,10 +77,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// bounded wait: a pipeline bug must trap, never hang the GPU
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded waits: a pipeline bug must trap, never hang the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     for (unsigned it = 0; !mbar_try_wait(bar, parity); ++it)
-        if (it > (1u << 26)) __trap();
+        if (it > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity) {
+    for (unsigned it = 0; !mbar_try_wait_cluster(bar, parity); ++it)
+        if (it > (1u << 24)) __trap();
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -84,6 +114,17 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, unsigned rank) {
 __device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
+// 8-byte store into a peer CTA's shared memory that signals complete_tx(8) on the peer's mbarrier:
+// data and notification travel together, no fence needed on the sender
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(remote_addr), "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
+}
+// one lane polls, the warp follows (keeps 31 lanes off the shared-memory port)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, unsigned parity, int lane) {
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
 template <typename T, int VEC> struct SLoad;
 template <> struct SLoad<float, 4> {
     static __device__ __forceinline__ void ld(const float* p, float (&x)[4]) {
@@ -99,181 +140,220 @@ template <> struct SLoad<double, 2> {
 };
 }  // namespace trf
 
-// shared memory carve-up (bytes):
-//   [0, NS*stage_bytes)                 X stages (128-byte aligned)
-//   then  full[NS] mbarriers (8 B each, padded to 128)
-//   then  sred[2][16] doubles, part[2][TR_FUSED_MAX_CL] doubles
-//   then  factor rows + rank weights (T), dims/offset ints
+// control block in the dynamic shared memory, after the NS stages
+struct FusedCtl {
+    uint64_t full[TR_FUSED_MAX_NS];                      // TMA landed (tx barrier, 1 arrival)
+    uint64_t empty[TR_FUSED_MAX_NS];                     // stage released by the NWC compute warps
+    uint64_t redA[TR_FUSED_MAX_NS];                      // NWC warp partials of a sample written
+    uint64_t rready[TR_FUSED_MAX_NS];                    // res of a sample available
+    uint64_t cready[2 * TR_FUSED_MAX_NS];                // CL cluster partials of a sample arrived
+    double pA[TR_FUSED_MAX_NS][TR_FUSED_NWC];
+    double resv[TR_FUSED_MAX_NS];
+    double cpart[2 * TR_FUSED_MAX_NS][TR_FUSED_MAX_CL];  // written remotely (DSMEM)
+    int dims[TR_MAX_MODES];
+    int foff[TR_MAX_MODES + 2];
+};
+
 template <typename T, int E>
 __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T> a) {
     constexpr int VEC = 16 / (int)sizeof(T);
-    constexpr int NT = TR_FUSED_NT;
-    constexpr int NW = NT / 32;
+    constexpr int NCT = TR_FUSED_NCT;
+    constexpr int NWC = TR_FUSED_NWC;
     extern __shared__ __align__(128) unsigned char tr_smem_fused[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned crank = trf::cluster_ctarank();
     const int cid = blockIdx.x / a.CL;
+    const int NS = a.NS, QC = 2 * a.NS, L = a.NS - 2;
 
-    unsigned char* sp = tr_smem_fused;
-    T* stage0 = reinterpret_cast<T*>(sp);
-    sp += (size_t)a.NS * a.stage_bytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sp);
-    sp += 128;
-    double* sred = reinterpret_cast<double*>(sp);            // [2][NW]
-    sp += 2 * NW * sizeof(double);
-    double* part = reinterpret_cast<double*>(sp);            // [2][TR_FUSED_MAX_CL]
-    sp += 2 * TR_FUSED_MAX_CL * sizeof(double);
-    T* sF = reinterpret_cast<T*>(sp);
+    T* stage0 = reinterpret_cast<T*>(tr_smem_fused);
+    FusedCtl* ctl = reinterpret_cast<FusedCtl*>(tr_smem_fused + (size_t)NS * a.stage_bytes);
+    T* sF = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ctl) + ((sizeof(FusedCtl) + 15) / 16) * 16);
     const int k = a.geo.k, R = a.geo.R, pfeat = a.geo.pfeat;
-    sp += (size_t)((pfeat + R) * sizeof(T) + 15) / 16 * 16;
-    int* sDims = reinterpret_cast<int*>(sp);
-    int* sOff = sDims + TR_MAX_MODES;
 
-    for (int i = tid; i < pfeat + R; i += NT) sF[i] = i < pfeat ? a.FtT[i] : a.w[i - pfeat];
-    if (tid < TR_MAX_MODES) sDims[tid] = a.geo.dims[tid];
-    if (tid < TR_MAX_MODES + 2) sOff[tid] = a.geo.foff[tid];
+    for (int i = tid; i < pfeat + R; i += TR_FUSED_NT) sF[i] = i < pfeat ? a.FtT[i] : a.w[i - pfeat];
+    if (tid < TR_MAX_MODES) ctl->dims[tid] = a.geo.dims[tid];
+    if (tid < TR_MAX_MODES + 2) ctl->foff[tid] = a.geo.foff[tid];
     if (tid == 0) {
-        for (int s = 0; s < a.NS; ++s) trf::mbar_init(&full[s], 1);
+        for (int s = 0; s < NS; ++s) {
+            trf::mbar_init(&ctl->full[s], 1);
+            trf::mbar_init(&ctl->empty[s], NWC);
+            trf::mbar_init(&ctl->redA[s], NWC);
+            trf::mbar_init(&ctl->rready[s], 1);
+        }
+        for (int q = 0; q < QC; ++q) trf::mbar_init(&ctl->cready[q], 1);     // 1 local arrive + CL*8 bytes of tx
         trf::fence_mbar_init();
     }
     __syncthreads();
-
-    // samples of this cluster: n = cid + j*NC, j = 0..cnt-1
-    const long long cnt = cid < a.N ? (a.N - cid + a.NC - 1) / a.NC : 0;
-    const T* xslice = a.X + (long long)crank * a.Dc;          // + n*D per sample
-
-    auto issue = [&](long long j) {                            // called by tid 0 only
-        const int s = (int)(j % a.NS);
-        const long long n = cid + j * a.NC;
-        trf::mbar_arrive_expect_tx(&full[s], a.stage_bytes);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(xslice + n * a.geo.D);
-        unsigned char* dst = reinterpret_cast<unsigned char*>(stage0) + (size_t)s * a.stage_bytes;
-        for (unsigned off = 0; off < a.stage_bytes; off += 16384u) {
-            const unsigned len = a.stage_bytes - off < 16384u ? a.stage_bytes - off : 16384u;
-            trf::bulk_g2s(dst + off, src + off, len, &full[s]);
-        }
-    };
-    if (tid == 0)
-        for (long long j = 0; j < a.NS && j < cnt; ++j) issue(j);
-    // every CTA of the cluster must be running before its shared memory is written remotely
+    // every CTA of the cluster must have initialised its barriers before any remote arrive / store
     trf::cluster_arrive();
     trf::cluster_wait();
 
-    // register-resident coefficient slice and gradient accumulators
-    T coef[E][VEC], acc[E][VEC];
-    unsigned cmask = 0;
-    const int chunks = a.Dc / VEC;
-#pragma unroll
-    for (int j = 0; j < E; ++j) {
-        const int ch = j * NT + tid;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            T tmp[1] = {(T)0};
-            if (ch < chunks) {
-                cmask |= 1u << j;
-                const unsigned i = (unsigned)((long long)crank * a.Dc + (long long)ch * VEC + v);
-                tr_coef_at<T, 1>(sF, sF + pfeat, sDims, sOff, k, R, 0, i, tmp);
-            }
-            coef[j][v] = tmp[0];
-            acc[j][v] = (T)0;
-        }
-    }
-    const double bias = (double)a.theta[a.bias_off];
-    const uint32_t part_u32 = trf::smem_u32(part);
+    // samples of this cluster: n = cid + j*NC, j = 0..cnt-1.  All ring positions and mbarrier phase
+    // bits are carried incrementally (no 64-bit division in the sample loop).
+    const int cnt = cid < a.N ? (int)((a.N - cid + a.NC - 1) / a.NC) : 0;
+    const size_t sample_stride = (size_t)a.NC * (size_t)a.geo.D;      // elements between this cluster's samples
 
-    double l1 = 0.0, l2 = 0.0;         // sum res, sum res^2 (rank 0, thread 0)
-    double res_prev = 0.0;
-    for (long long i = 0; i <= cnt; ++i) {
-        double pc = 0.0;
-        if (i < cnt) {
-            // ---- phase A (compute part): partial of y_hat over this CTA's slice ----
-            const int s = (int)(i % a.NS);
-            trf::mbar_wait(&full[s], (unsigned)((i / a.NS) & 1));
-            const T* xs = stage0 + (size_t)s * (a.stage_bytes / sizeof(T));
-            T p0 = (T)0, p1 = (T)0;
+    if (wid == NWC) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            const T* src = a.X + (size_t)cid * (size_t)a.geo.D + (size_t)crank * a.Dc;
+            int s = 0;
+            unsigned ph = 0;                       // parity of the empty-phase to wait for (from the 2nd lap on)
+            for (int j = 0; j < cnt; ++j) {
+                if (j >= NS) trf::mbar_wait(&ctl->empty[s], ph);
+                trf::mbar_arrive_expect_tx(&ctl->full[s], a.stage_bytes);
+                const unsigned char* sp = reinterpret_cast<const unsigned char*>(src);
+                unsigned char* dst = reinterpret_cast<unsigned char*>(stage0) + (size_t)s * a.stage_bytes;
+                for (unsigned off = 0; off < a.stage_bytes; off += 32768u) {
+                    const unsigned len = a.stage_bytes - off < 32768u ? a.stage_bytes - off : 32768u;
+                    trf::bulk_g2s(dst + off, sp + off, len, &ctl->full[s]);
+                }
+                src += sample_stride;
+                if (++s == NS) { s = 0; if (j >= NS) ph ^= 1u; }
+            }
+        }
+    } else if (wid == NWC + 1) {
+        // ========================= reducer / cluster exchange =========================
+        // all 32 lanes take part: lane c sends this CTA's partial to peer c (st.async), lane 0 owns
+        // the waits and the scalar math
+        const double bias = (double)a.theta[a.bias_off];
+        double l1 = 0.0, l2 = 0.0;
+        int q = 0, qc = 0;
+        unsigned phq = 0, phc = 0;
+        const T* yp = a.y + cid;
+        T* yhp = a.yhat ? a.yhat + cid : nullptr;
+        for (int i = 0; i < cnt; ++i) {
+            double yn = 0.0;
+            if (lane == 0) {
+                yn = (double)__ldg(yp);                                 // in flight while we wait below
+                trf::mbar_arrive_expect_tx(&ctl->cready[qc], (unsigned)(a.CL * sizeof(double)));
+            }
+            trf::mbar_wait_warp(&ctl->redA[q], phq, lane);
+            double pc = 0.0;
 #pragma unroll
-            for (int j = 0; j < E; ++j) {
-                if ((cmask >> j) & 1u) {
-                    T x[VEC];
-                    trf::SLoad<T, VEC>::ld(xs + (size_t)(j * NT + tid) * VEC, x);
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        if (j & 1) p1 = tr_fma<T>(x[v], coef[j][v], p1);
-                        else p0 = tr_fma<T>(x[v], coef[j][v], p0);
-                    }
+            for (int w8 = 0; w8 < NWC; ++w8) pc += ctl->pA[q][w8];     // same order in every lane
+            if (lane < a.CL)
+                trf::st_async_f64(trf::mapa(trf::smem_u32(&ctl->cpart[qc][crank]), (unsigned)lane), pc,
+                                  trf::mapa(trf::smem_u32(&ctl->cready[qc]), (unsigned)lane));
+            if (lane == 0) {
+                trf::mbar_wait(&ctl->cready[qc], phc);
+                double yh = bias;
+                for (int c = 0; c < a.CL; ++c) yh += ctl->cpart[qc][c];
+                const T yhT = (T)yh;
+                const double res = (double)yhT - yn;
+                ctl->resv[q] = res;
+                trf::mbar_arrive(&ctl->rready[q]);
+                if (crank == 0) {
+                    if (yhp) *yhp = yhT;
+                    l1 += res;
+                    l2 += res * res;
                 }
             }
-            double pw = warp_sum((double)p0 + (double)p1);
-            if (lane == 0) sred[(i & 1) * NW + wid] = pw;
+            __syncwarp();
+            yp += a.NC;
+            if (yhp) yhp += a.NC;
+            if (++q == NS) { q = 0; phq ^= 1u; }
+            if (++qc == QC) { qc = 0; phc ^= 1u; }
         }
-        __syncthreads();                                        // (S1) sred visible; everyone is past B(i-2)
-        if (i < cnt) {
+        if (lane == 0 && crank == 0) { a.part[cid * 2 + 0] = l1; a.part[cid * 2 + 1] = l2; }
+    } else {
+        // ================================ compute warps ================================
+        T coef[E][VEC], acc[E][VEC];
+        unsigned cmask = 0;
+        const int chunks = a.Dc / VEC;
 #pragma unroll
-            for (int w8 = 0; w8 < NW; ++w8) pc += sred[(i & 1) * NW + w8];
-        }
-        // ---- barrier of sample i-1 completes: its partials from all CTAs are in part[(i-1)&1] ----
-        if (i > 0) {
-            trf::cluster_wait();
-            double yh = bias;
-            for (int c = 0; c < a.CL; ++c) yh += part[((i - 1) & 1) * TR_FUSED_MAX_CL + c];
-            const long long n = cid + (i - 1) * a.NC;
-            const T yhT = (T)yh;
-            const double res = (double)yhT - (double)__ldg(a.y + n);
-            res_prev = res;
-            if (crank == 0 && tid == 0) {
-                if (a.yhat) a.yhat[n] = yhT;
-                l1 += res;
-                l2 += res * res;
-            }
-        }
-        // ---- publish this CTA's partial of sample i to every CTA of the cluster ----
-        if (i < cnt) {
-            if (tid < a.CL)
-                trf::st_cluster_f64(trf::mapa(part_u32 + (uint32_t)(((i & 1) * TR_FUSED_MAX_CL + crank) * sizeof(double)),
-                                              (unsigned)tid), pc);
-            trf::cluster_arrive();
-        }
-        // ---- phase B of sample i-1: G += res * x, from the stage that is still resident ----
-        if (i > 0) {
-            const int s = (int)((i - 1) % a.NS);
-            const T* xs = stage0 + (size_t)s * (a.stage_bytes / sizeof(T));
-            const T r = (T)res_prev;
+        for (int j = 0; j < E; ++j) {
+            const int ch = j * NCT + tid;
 #pragma unroll
-            for (int j = 0; j < E; ++j) {
-                if ((cmask >> j) & 1u) {
-                    T x[VEC];
-                    trf::SLoad<T, VEC>::ld(xs + (size_t)(j * NT + tid) * VEC, x);
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) acc[j][v] = tr_fma<T>(r, x[v], acc[j][v]);
+            for (int v = 0; v < VEC; ++v) {
+                T tmp[1] = {(T)0};
+                if (ch < chunks) {
+                    cmask |= 1u << j;
+                    const unsigned i = (unsigned)((long long)crank * a.Dc + (long long)ch * VEC + v);
+                    tr_coef_at<T, 1>(sF, sF + pfeat, ctl->dims, ctl->foff, k, R, 0, i, tmp);
                 }
+                coef[j][v] = tmp[0];
+                acc[j][v] = (T)0;
             }
-            // chunk boundary: flush G to its slot (bounds the length of every fp32 running sum)
-            const long long jj = i - 1;
-            if ((jj + 1) % a.spc == 0 || jj == cnt - 1) {
-                const long long slot = (long long)cid * a.nchunk + jj / a.spc;
-                T* gp = a.Gpart + slot * a.Dpad + (long long)crank * a.Dc;
+        }
+        const unsigned stage_elems = a.stage_bytes / (unsigned)sizeof(T);
+        const T* xthread = stage0 + (size_t)tid * VEC;                  // this thread's first chunk of stage 0
+        int sA = 0, sB = 0;
+        unsigned phA = 0, phB = 0;
+        int left = (int)(a.spc < cnt ? a.spc : cnt);                    // samples until the next flush of G
+        int done = 0;                                                   // samples whose phase B is finished
+        T* gp = a.Gpart + (size_t)cid * a.nchunk * (size_t)a.Dpad + (size_t)crank * a.Dc + (size_t)tid * VEC;
+        const int iters = cnt + L;
+        for (int i = 0; i < iters; ++i) {
+            if (i < cnt) {
+                // ---- phase A: this warp's part of <X_n, B> over the CTA slice ----
+                trf::mbar_wait_warp(&ctl->full[sA], phA, lane);
+                const T* xs = xthread + (size_t)sA * stage_elems;
+                T p0 = (T)0, p1 = (T)0;
 #pragma unroll
                 for (int j = 0; j < E; ++j) {
                     if ((cmask >> j) & 1u) {
+                        T x[VEC];
+                        trf::SLoad<T, VEC>::ld(xs + (size_t)j * NCT * VEC, x);
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) {
-                            gp[(size_t)(j * NT + tid) * VEC + v] = acc[j][v];
-                            acc[j][v] = (T)0;
+                            if (j & 1) p1 = tr_fma<T>(x[v], coef[j][v], p1);
+                            else p0 = tr_fma<T>(x[v], coef[j][v], p0);
                         }
                     }
                 }
+                const double pw = warp_sum((double)p0 + (double)p1);
+                if (lane == 0) {
+                    ctl->pA[sA][wid] = pw;
+                    trf::mbar_arrive(&ctl->redA[sA]);
+                }
+                if (++sA == NS) { sA = 0; phA ^= 1u; }
+            }
+            if (i >= L) {
+                // ---- phase B: G += res * x from the stage that is still resident ----
+                trf::mbar_wait_warp(&ctl->rready[sB], phB, lane);
+                const T r = (T)ctl->resv[sB];
+                const T* xs = xthread + (size_t)sB * stage_elems;
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    if ((cmask >> j) & 1u) {
+                        T x[VEC];
+                        trf::SLoad<T, VEC>::ld(xs + (size_t)j * NCT * VEC, x);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) acc[j][v] = tr_fma<T>(r, x[v], acc[j][v]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) trf::mbar_arrive(&ctl->empty[sB]);      // all lanes' reads of the stage are done
+                if (++sB == NS) { sB = 0; phB ^= 1u; }
+                ++done;
+                // chunk boundary: flush G to its slot (bounds the length of every fp32 running sum)
+                if (--left == 0) {
+#pragma unroll
+                    for (int j = 0; j < E; ++j) {
+                        if ((cmask >> j) & 1u) {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                gp[(size_t)j * NCT * VEC + v] = acc[j][v];
+                                acc[j][v] = (T)0;
+                            }
+                        }
+                    }
+                    gp += a.Dpad;
+                    const int rem = cnt - done;
+                    left = (int)(a.spc < rem ? a.spc : rem);
+                }
             }
         }
-        __syncthreads();                                        // (S2) stage (i-1)%NS is free
-        if (tid == 0 && i > 0 && i - 1 + a.NS < cnt) issue(i - 1 + a.NS);
-    }
-    if (crank == 0 && tid == 0) { a.part[cid * 2 + 0] = l1; a.part[cid * 2 + 1] = l2; }
-    // slots of chunks this cluster never reached must still be defined for the reduction
-    {
-        const long long used = cnt > 0 ? (cnt - 1) / a.spc + 1 : 0;
-        for (long long c2 = used; c2 < a.nchunk; ++c2) {
-            T* gp = a.Gpart + ((long long)cid * a.nchunk + c2) * a.Dpad + (long long)crank * a.Dc;
-            for (int e = tid; e < a.Dc; e += NT) gp[e] = (T)0;
+        // slots of chunks this cluster never reached must still be defined for the reduction
+        const int used = cnt > 0 ? (int)((cnt - 1) / a.spc) + 1 : 0;
+        for (int c2 = used; c2 < a.nchunk; ++c2) {
+            T* gz = a.Gpart + ((size_t)cid * a.nchunk + c2) * (size_t)a.Dpad + (size_t)crank * a.Dc;
+            for (int e = tid; e < a.Dc; e += NCT) gz[e] = (T)0;
         }
     }
+    // no CTA may exit while a peer can still write into its shared memory
+    __syncwarp();
+    trf::cluster_arrive();
+    trf::cluster_wait();
 }
