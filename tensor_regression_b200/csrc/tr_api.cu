@@ -91,6 +91,7 @@ struct tr_handle {
     double prof_ms[3] = {0.0, 0.0, 0.0};
     long long prof_n[3] = {0, 0, 0};
     int fused_mode = -1;                // -1 auto, 0 never, 1 always (error when not eligible)
+    int fused_pace = 0;                 // cycles between TMA issues (tuning knob, option "fused_pace")
     int last_fused = 0;
     std::map<const void*, int> occ_clusters;
 };
@@ -306,6 +307,10 @@ FusedKern<T> fused_kernel(int E) {
         case 6: return k_fused_std<T, 6>;
         case 7: return k_fused_std<T, 7>;
         case 8: return k_fused_std<T, 8>;
+        case 9: case 10: return k_fused_std<T, 10>;
+        case 11: case 12: return k_fused_std<T, 12>;
+        case 13: case 14: return k_fused_std<T, 14>;
+        case 15: case 16: return k_fused_std<T, 16>;
     }
     return nullptr;
 }
@@ -324,7 +329,7 @@ int plan_fused(tr_handle* h, long long N, const void* X, FusedPlan* fp) {
         const long long Dc = g.D / CL;
         const long long chunks = Dc / VEC;
         const int E = (int)((chunks + TR_FUSED_NCT - 1) / TR_FUSED_NCT);
-        if (E > 8) continue;
+        if (E > 16) continue;
         const size_t stage = (size_t)Dc * sizeof(T);
         if (fixed + 3 * stage > budget) continue;
         int NS = (int)((budget - fixed) / stage);
@@ -388,6 +393,8 @@ int run_fused_std(tr_handle* h, const T* X, const T* y, long long N, const T* th
     fa.Gpart = (T*)h->Gpart.p; fa.Dpad = g.D; fa.yhat = yhat; fa.part = (double*)h->epi_part.p;
     fa.CL = fp.CL; fa.NC = fp.NC; fa.Dc = fp.Dc; fa.NS = fp.NS; fa.nchunk = fp.nchunk; fa.spc = fp.spc;
     fa.stage_bytes = fp.stage_bytes;
+    fa.trace = nullptr;
+    fa.pace = h->fused_pace;
     auto kern = fused_kernel<T>(fp.E);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(fp.CL * fp.NC), 1, 1);
@@ -588,6 +595,7 @@ int tr_create(tr_handle** out, int dtype, int k, const int64_t* dims, int R, int
     if (prop.major < 10) { delete h; return fail(nullptr, TR_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); }
     h->sms = prop.multiProcessorCount;
     if (const char* ev = getenv("TR_B200_FUSED")) h->fused_mode = atoi(ev) < 0 ? -1 : (atoi(ev) > 0 ? 1 : 0);
+    if (const char* ev = getenv("TR_B200_FUSED_PACE")) h->fused_pace = atoi(ev);
     *out = h;
     return TR_OK;
 }
@@ -783,6 +791,7 @@ int tr_set_option(tr_handle* h, const char* name, int64_t value) {
         h->fused_mode = (int)value;
         return TR_OK;
     }
+    if (strcmp(name, "fused_pace") == 0) { h->fused_pace = (int)value; return TR_OK; }
     return fail(h, TR_ERR_INVALID, "unknown option '%s'", name);
 }
 

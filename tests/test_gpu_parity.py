@@ -218,7 +218,7 @@ def test_std_vs_oracle_on_baseline_shapes(name, N, dims, R, dt):
               f'kernel vs reference fp32 {rel(grad, got32):.2e}')
         assert rel(grad, got32) < TOL[dt]
     info = eng.launch_info()
-    assert info['launches'] >= 6 and info['tiles_per_sample'] >= 1
+    assert info['launches'] >= 5 and info['path'] in ('two-pass', 'single-pass (cluster-resident sample)')
 
 
 SHAPES_MN = [
