@@ -92,6 +92,7 @@ struct tr_handle {
     long long prof_n[3] = {0, 0, 0};
     int fused_mode = -1;                // -1 auto, 0 never, 1 always (error when not eligible)
     int fused_pace = 0;                 // cycles between TMA issues (tuning knob, option "fused_pace")
+    int fused_piece = 32768;            // bytes per bulk-copy instruction (option "fused_piece")
     int last_fused = 0;
     std::map<const void*, int> occ_clusters;
 };
@@ -322,7 +323,7 @@ int plan_fused(tr_handle* h, long long N, const void* X, FusedPlan* fp) {
     const Geo& g = h->geo;
     constexpr int VEC = 16 / (int)sizeof(T);
     if (g.C != 0 || !vec_ok(X, g.D, sizeof(T)) || N < 1) return TR_OK;
-    const size_t fixed = ((sizeof(FusedCtl) + 15) / 16) * 16 + ((size_t)(g.pfeat + g.R) * sizeof(T) + 15) / 16 * 16;
+    const size_t fixed = ((((sizeof(FusedCtl) + 15) / 16) * 16 + (size_t)(g.pfeat + g.R) * sizeof(T)) + 1023) / 1024 * 1024;
     const size_t budget = 226 * 1024;
     for (int CL = 1; CL <= TR_FUSED_MAX_CL; CL *= 2) {
         if (g.D % ((long long)CL * VEC) != 0) continue;
@@ -384,17 +385,19 @@ int run_fused_std(tr_handle* h, const T* X, const T* y, long long N, const T* th
     if ((rc = ensure(h, h->Ft64, (size_t)g.pf * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->Gpart, (size_t)fp.NC * fp.nchunk * g.D * sizeof(T)))) return rc;
     if ((rc = ensure(h, h->Gred, (size_t)g.D * sizeof(double)))) return rc;
-    if ((rc = ensure(h, h->epi_part, (size_t)std::max(h->sms * 8, fp.NC) * 2 * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->epi_part, (size_t)h->sms * 8 * 2 * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->V, (size_t)N * sizeof(T)))) return rc;
     k_prep<T><<<std::max(1, std::min(64, (g.pf + 255) / 256)), 256, 0, st>>>(theta, g, nn_mask, beta, thr,
                                                                            (T*)h->FtT.p, (double*)h->Ft64.p);
     TR_LAUNCH_CHECK(h);
     FusedArgs<T> fa;
     fa.X = X; fa.y = y; fa.N = N; fa.FtT = (const T*)h->FtT.p; fa.w = w; fa.theta = theta; fa.bias_off = g.pf; fa.geo = g;
-    fa.Gpart = (T*)h->Gpart.p; fa.Dpad = g.D; fa.yhat = yhat; fa.part = (double*)h->epi_part.p;
+    fa.Gpart = (T*)h->Gpart.p; fa.Dpad = g.D; fa.yhat = yhat; fa.res = (T*)h->V.p;
     fa.CL = fp.CL; fa.NC = fp.NC; fa.Dc = fp.Dc; fa.NS = fp.NS; fa.nchunk = fp.nchunk; fa.spc = fp.spc;
     fa.stage_bytes = fp.stage_bytes;
     fa.trace = nullptr;
     fa.pace = h->fused_pace;
+    fa.piece = (unsigned)h->fused_piece;
     auto kern = fused_kernel<T>(fp.E);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(fp.CL * fp.NC), 1, 1);
@@ -409,7 +412,10 @@ int run_fused_std(tr_handle* h, const T* X, const T* y, long long N, const T* th
     TR_CUDA(h, cudaLaunchKernelEx(&cfg, kern, fa));
     TR_LAUNCH_CHECK(h);
     if (h->prof) { TR_CUDA(h, cudaEventRecord(h->ev[5], st)); h->ev_set[2] = true; }
-    k_colsum<<<2, 128, 0, st>>>((const double*)h->epi_part.p, fp.NC, 2, gradsum + g.pf);
+    const int sgrid = (int)std::min<long long>((N + 255) / 256, (long long)h->sms * 2);
+    k_ressum<T><<<sgrid, 256, 0, st>>>((const T*)h->V.p, N, (double*)h->epi_part.p);
+    TR_LAUNCH_CHECK(h);
+    k_colsum<<<2, 128, 0, st>>>((const double*)h->epi_part.p, sgrid, 2, gradsum + g.pf);
     TR_LAUNCH_CHECK(h);
     const int rgrid = (int)std::min<long long>((g.D + 255) / 256, (long long)h->sms * 8);
     k_reduce_G<T><<<rgrid, 256, 0, st>>>((const T*)h->Gpart.p, fp.NC * fp.nchunk, 1, g.D, g.D, (double*)h->Gred.p);
@@ -596,6 +602,7 @@ int tr_create(tr_handle** out, int dtype, int k, const int64_t* dims, int R, int
     h->sms = prop.multiProcessorCount;
     if (const char* ev = getenv("TR_B200_FUSED")) h->fused_mode = atoi(ev) < 0 ? -1 : (atoi(ev) > 0 ? 1 : 0);
     if (const char* ev = getenv("TR_B200_FUSED_PACE")) h->fused_pace = atoi(ev);
+    if (const char* ev = getenv("TR_B200_FUSED_PIECE")) { const int v = atoi(ev); if (v >= 16 && v % 16 == 0) h->fused_piece = v; }
     *out = h;
     return TR_OK;
 }
@@ -792,6 +799,11 @@ int tr_set_option(tr_handle* h, const char* name, int64_t value) {
         return TR_OK;
     }
     if (strcmp(name, "fused_pace") == 0) { h->fused_pace = (int)value; return TR_OK; }
+    if (strcmp(name, "fused_piece") == 0) {
+        if (value < 16 || value % 16) return fail(h, TR_ERR_INVALID, "fused_piece must be a positive multiple of 16");
+        h->fused_piece = (int)value;
+        return TR_OK;
+    }
     return fail(h, TR_ERR_INVALID, "unknown option '%s'", name);
 }
 

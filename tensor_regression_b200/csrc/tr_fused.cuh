@@ -42,7 +42,7 @@ struct FusedArgs {
     T* Gpart;            // (NC * nchunk, 1, Dpad)
     long long Dpad;
     T* yhat;             // may be null
-    double* part;        // (NC, 2): sum res, sum res^2
+    T* res;              // (N) residuals y_hat - y out (loss sums are formed from it by k_ressum)
     int CL;              // CTAs per cluster
     int NC;              // clusters in the grid
     int Dc;              // feature elements per CTA slice (D / CL)
@@ -50,6 +50,7 @@ struct FusedArgs {
     int nchunk;          // G is flushed to a fresh slot every spc samples (bounds fp32 sum length)
     long long spc;
     unsigned stage_bytes;  // Dc * sizeof(T), multiple of 16
+    unsigned piece;        // bytes per cp.async.bulk instruction (multiple of 16)
     int pace;              // minimum cycles between two TMA issues of a CTA (anti-bunching), 0 = off
     long long* trace;      // debug (tools/fused_trace.cu): clock64 stamps of cluster 0 / rank 0, else null
 };
@@ -92,7 +93,6 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, unsigned pa
 // bounded waits: a pipeline bug must trap, never hang the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     for (unsigned it = 0; !mbar_try_wait(bar, parity); ++it) {
-        if (it > 8) __nanosleep(32);               // back off: leave the issue slots to warps with work
         if (it > (1u << 24)) __trap();
     }
 }
@@ -146,14 +146,22 @@ template <> struct SLoad<double, 2> {
 }  // namespace trf
 
 // debug timeline: event e of sample i (cluster 0, CTA rank 0 only), TR_TRACE_N samples from TR_TRACE_I0
+#ifndef TR_TRACE_I0
 #define TR_TRACE_I0 64
-#define TR_TRACE_N 48
-#define TR_TRACE_EV 8
+#endif
+#define TR_TRACE_N 24
+#define TR_TRACE_EV 48
+// stamps go to shared memory (a global store before an mbarrier.arrive would make the arrive's release
+// wait for the store to be performed and distort the timeline) and are copied out at kernel end
+#ifdef TR_FUSED_TRACE
 #define TR_TRACE(ev, i)                                                                              \
     do {                                                                                             \
         if (a.trace && cid == 0 && crank == 0 && (i) >= TR_TRACE_I0 && (i) < TR_TRACE_I0 + TR_TRACE_N) \
-            a.trace[((i) - TR_TRACE_I0) * TR_TRACE_EV + (ev)] = clock64();                           \
+            strace[((i) - TR_TRACE_I0) * TR_TRACE_EV + (ev)] = clock64();                            \
     } while (0)
+#else
+#define TR_TRACE(ev, i) do { } while (0)
+#endif
 
 // control block in the dynamic shared memory, after the NS stages
 struct FusedCtl {
@@ -162,7 +170,7 @@ struct FusedCtl {
     uint64_t redA[TR_FUSED_MAX_NS];                      // NWC warp partials of a sample written
     uint64_t rready[TR_FUSED_MAX_NS];                    // res of a sample available
     uint64_t cready[2 * TR_FUSED_MAX_NS];                // CL cluster partials of a sample arrived
-    double pA[TR_FUSED_MAX_NS][TR_FUSED_NWC];
+    double pA[TR_FUSED_MAX_NS][TR_FUSED_NWC];            // fp32 kernels store floats in the low halves
     double resv[TR_FUSED_MAX_NS];
     double cpart[2 * TR_FUSED_MAX_NS][TR_FUSED_MAX_CL];  // written remotely (DSMEM)
     int dims[TR_MAX_MODES];
@@ -176,21 +184,29 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
     constexpr int NWC = TR_FUSED_NWC;
     extern __shared__ __align__(128) unsigned char tr_smem_fused[];
     const int lane = threadIdx.x & 31;
-    // role -> warp id: producer 0, reducer 1, gradient warps 2..9, forward warps 10..17.  The issue
-    // arbiter favours high warp ids, so data-ready forward work goes first and the pollers last.
+    // role -> warp id.  Warp w issues on sub-partition w % 4, and each sub-partition has its own
+    // in-order shared-memory (MIO) instruction queue: forward warps sit on sub-partitions 0,1 and
+    // gradient warps on 2,3 so that the forward warps' dependent shuffle chain never queues behind
+    // the gradient warps' bursts of LDS.128 (measured: ~2400 cycles per sample, tools/fused_trace).
     const int hw_wid = threadIdx.x >> 5;
-    const int wid = hw_wid >= 2 + TR_FUSED_NWC ? hw_wid - (2 + TR_FUSED_NWC)                 // forward: 0..7
-                    : (hw_wid >= 2 ? hw_wid - 2 + TR_FUSED_NWC                                // gradient: 8..15
-                                   : 2 * TR_FUSED_NWC + hw_wid);                              // producer 16, reducer 17
+    const int wid = hw_wid >= 2 * TR_FUSED_NWC ? hw_wid                                       // producer 16, reducer 17
+                    : ((hw_wid & 3) < 2 ? (hw_wid >> 2) * 2 + (hw_wid & 3)                    // forward: 0..7
+                                        : TR_FUSED_NWC + (hw_wid >> 2) * 2 + (hw_wid & 3) - 2);  // gradient: 8..15
     const int tid = wid * 32 + lane;                                                          // role-relative thread id
     const unsigned crank = trf::cluster_ctarank();
     const int cid = blockIdx.x / a.CL;
     const int NS = a.NS, QC = 2 * a.NS;
 
-    T* stage0 = reinterpret_cast<T*>(tr_smem_fused);
-    FusedCtl* ctl = reinterpret_cast<FusedCtl*>(tr_smem_fused + (size_t)NS * a.stage_bytes);
-    T* sF = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ctl) + ((sizeof(FusedCtl) + 15) / 16) * 16);
+    // layout: [control block | factor rows + rank weights | pad to 1024 | NS stages]
     const int k = a.geo.k, R = a.geo.R, pfeat = a.geo.pfeat;
+    FusedCtl* ctl = reinterpret_cast<FusedCtl*>(tr_smem_fused);
+    T* sF = reinterpret_cast<T*>(tr_smem_fused + ((sizeof(FusedCtl) + 15) / 16) * 16);
+    const size_t head = ((((sizeof(FusedCtl) + 15) / 16) * 16 + (size_t)(pfeat + R) * sizeof(T)) + 1023) / 1024 * 1024;
+    T* stage0 = reinterpret_cast<T*>(tr_smem_fused + head);
+#ifdef TR_FUSED_TRACE
+    long long* strace = reinterpret_cast<long long*>(tr_smem_fused + head + (size_t)NS * a.stage_bytes);
+    for (int i = threadIdx.x; i < TR_TRACE_N * TR_TRACE_EV; i += TR_FUSED_NT) strace[i] = 0;
+#endif
 
     for (int i = threadIdx.x; i < pfeat + R; i += TR_FUSED_NT) sF[i] = i < pfeat ? a.FtT[i] : a.w[i - pfeat];
     if (threadIdx.x < TR_MAX_MODES) ctl->dims[threadIdx.x] = a.geo.dims[threadIdx.x];
@@ -234,8 +250,8 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
                 trf::mbar_arrive_expect_tx(&ctl->full[s], a.stage_bytes);
                 const unsigned char* sp = reinterpret_cast<const unsigned char*>(src);
                 unsigned char* dst = reinterpret_cast<unsigned char*>(stage0) + (size_t)s * a.stage_bytes;
-                for (unsigned off = 0; off < a.stage_bytes; off += 32768u) {
-                    const unsigned len = a.stage_bytes - off < 32768u ? a.stage_bytes - off : 32768u;
+                for (unsigned off = 0; off < a.stage_bytes; off += a.piece) {
+                    const unsigned len = a.stage_bytes - off < a.piece ? a.stage_bytes - off : a.piece;
                     trf::bulk_g2s(dst + off, sp + off, len, &ctl->full[s]);
                 }
                 src += sample_stride;
@@ -246,48 +262,49 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
         // ========================= reducer / cluster exchange =========================
         // all 32 lanes take part: lane c sends this CTA's partial to peer c (st.async), lane 0 owns
         // the waits and the scalar math
-        const double bias = (double)a.theta[a.bias_off];
-        double l1 = 0.0, l2 = 0.0;
+        const T bias = a.theta[a.bias_off];
         int q = 0, qc = 0;
         unsigned phq = 0, phc = 0;
         const T* yp = a.y + cid;
         T* yhp = a.yhat ? a.yhat + cid : nullptr;
+        T* rp = a.res + cid;                                            // residuals out: loss sums are formed later, in fp64
         for (int i = 0; i < cnt; ++i) {
-            double yn = 0.0;
+            T yn = (T)0;
             if (lane == 0) {
-                yn = (double)__ldg(yp);                                 // in flight while we wait below
+                yn = __ldg(yp);                                         // in flight while we wait below
                 trf::mbar_arrive_expect_tx(&ctl->cready[qc], (unsigned)(a.CL * sizeof(double)));
             }
             trf::mbar_wait_warp(&ctl->redA[q], phq, lane);
             if (lane == 0) TR_TRACE(3, i);
-            double pc = 0.0;
+            T pc = (T)0;
 #pragma unroll
-            for (int w8 = 0; w8 < NWC; ++w8) pc += ctl->pA[q][w8];     // same order in every lane
-            if (lane < a.CL)
-                trf::st_async_f64(trf::mapa(trf::smem_u32(&ctl->cpart[qc][crank]), (unsigned)lane), pc,
+            for (int w8 = 0; w8 < NWC; ++w8) pc += reinterpret_cast<const T*>(&ctl->pA[q][w8])[0];   // same order in every lane
+            if (lane < a.CL) {
+                double slot = 0.0;
+                reinterpret_cast<T*>(&slot)[0] = pc;
+                trf::st_async_f64(trf::mapa(trf::smem_u32(&ctl->cpart[qc][crank]), (unsigned)lane), slot,
                                   trf::mapa(trf::smem_u32(&ctl->cready[qc]), (unsigned)lane));
+            }
             if (lane == 0) {
                 trf::mbar_wait(&ctl->cready[qc], phc);
                 TR_TRACE(4, i);
-                double yh = bias;
-                for (int c = 0; c < a.CL; ++c) yh += ctl->cpart[qc][c];
-                const T yhT = (T)yh;
-                const double res = (double)yhT - yn;
-                ctl->resv[q] = res;
+                T yh = bias;
+                for (int c = 0; c < a.CL; ++c) yh += reinterpret_cast<const T*>(&ctl->cpart[qc][c])[0];
+                const T res = yh - yn;
+                reinterpret_cast<T*>(&ctl->resv[q])[0] = res;
                 trf::mbar_arrive(&ctl->rready[q]);
                 if (crank == 0) {
-                    if (yhp) *yhp = yhT;
-                    l1 += res;
-                    l2 += res * res;
+                    if (yhp) *yhp = yh;
+                    *rp = res;
                 }
             }
             __syncwarp();
             yp += a.NC;
+            rp += a.NC;
             if (yhp) yhp += a.NC;
             if (++q == NS) { q = 0; phq ^= 1u; }
             if (++qc == QC) { qc = 0; phc ^= 1u; }
         }
-        if (lane == 0 && crank == 0) { a.part[cid * 2 + 0] = l1; a.part[cid * 2 + 1] = l2; }
     } else if (wid < NWC) {
         // ============================ forward warps: phase A ============================
         T coef[E][VEC];
@@ -314,6 +331,7 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
         for (int i = 0; i < cnt; ++i) {
             trf::mbar_wait_warp(&ctl->full[sA], phA, lane);
             if (tid == 0) TR_TRACE(1, i);
+            if (lane == 0) TR_TRACE(8 + wid * 2, i);
             const T* xs = xthread + (size_t)sA * stage_elems;
             T p[4] = {(T)0, (T)0, (T)0, (T)0};
 #pragma unroll
@@ -325,12 +343,18 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
                     for (int v = 0; v < VEC; ++v) p[j & 3] = tr_fma<T>(x[v], coef[j][v], p[j & 3]);
                 }
             }
-            const double pw = warp_sum(((double)p[0] + (double)p[1]) + ((double)p[2] + (double)p[3]));
+            if (tid == 0) TR_TRACE(7, i);
+            // warp reduction in T: for fp32 the whole per-sample chain stays off the fp64 pipe (whose
+            // first use after an idle spell costs thousands of cycles on B200 — measured, tools/fused_trace)
+            T pw = (p[0] + p[1]) + (p[2] + p[3]);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) pw += __shfl_xor_sync(TR_FULL, pw, off);
             if (lane == 0) {
-                ctl->pA[sA][wid] = pw;
+                reinterpret_cast<T*>(&ctl->pA[sA][wid])[0] = pw;
                 trf::mbar_arrive(&ctl->redA[sA]);
             }
             if (tid == 0) TR_TRACE(2, i);
+            if (lane == 0) TR_TRACE(9 + wid * 2, i);
             if (++sA == NS) { sA = 0; phA ^= 1u; }
         }
     } else {
@@ -354,7 +378,8 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
         for (int i = 0; i < cnt; ++i) {
             trf::mbar_wait_warp(&ctl->rready[sB], phB, lane);
             if (tb == 0) TR_TRACE(5, i);
-            const T r = (T)ctl->resv[sB];
+            if (lane == 0) TR_TRACE(24 + (wid - NWC) * 2, i);
+            const T r = reinterpret_cast<const T*>(&ctl->resv[sB])[0];
             const T* xs = xthread + (size_t)sB * stage_elems;
 #pragma unroll
             for (int j = 0; j < E; ++j) {
@@ -368,6 +393,7 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
             __syncwarp();
             if (lane == 0) trf::mbar_arrive(&ctl->empty[sB]);          // all lanes' reads of the stage are done
             if (tb == 0) TR_TRACE(6, i);
+            if (lane == 0) TR_TRACE(25 + (wid - NWC) * 2, i);
             if (++sB == NS) { sB = 0; phB ^= 1u; }
             // chunk boundary: flush G to its slot (bounds the length of every fp32 running sum)
             if (--left == 0) {
@@ -397,4 +423,9 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
     __syncwarp();
     trf::cluster_arrive();
     trf::cluster_wait();
+#ifdef TR_FUSED_TRACE
+    __syncthreads();
+    if (a.trace && cid == 0 && crank == 0)
+        for (int i = threadIdx.x; i < TR_TRACE_N * TR_TRACE_EV; i += TR_FUSED_NT) a.trace[i] = strace[i];
+#endif
 }

@@ -262,6 +262,21 @@ __global__ void __launch_bounds__(128) k_colsum(const double* __restrict__ part,
     if (threadIdx.x == 0) out[j] = s;
 }
 
+// part[b] = { sum res, sum res^2 } over block b's grid-stride share of a residual vector (fp64)
+template <typename T>
+__global__ void __launch_bounds__(256) k_ressum(const T* __restrict__ res, long long N, double* __restrict__ part) {
+    __shared__ double sbuf[32];
+    double l1 = 0.0, l2 = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const double r = (double)res[i];
+        l1 += r;
+        l2 += r * r;
+    }
+    const double t1 = block_sum(l1, sbuf);
+    const double t2 = block_sum(l2, sbuf);
+    if (threadIdx.x == 0) { part[blockIdx.x * 2 + 0] = t1; part[blockIdx.x * 2 + 1] = t2; }
+}
+
 // sum of a T vector (for tr_backward_std's dbias) -> out[0]; single block
 template <typename T>
 __global__ void __launch_bounds__(1024) k_vecsum(const T* __restrict__ v, long long N, double* __restrict__ out) {
