@@ -90,11 +90,10 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, unsigned pa
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// bounded waits: a pipeline bug must trap, never hang the GPU
+// bounded waits: a pipeline bug must trap, never hang the GPU (try_wait suspends the thread in hardware)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    for (unsigned it = 0; !mbar_try_wait(bar, parity); ++it) {
+    for (unsigned it = 0; !mbar_try_wait(bar, parity); ++it)
         if (it > (1u << 24)) __trap();
-    }
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity) {
     for (unsigned it = 0; !mbar_try_wait_cluster(bar, parity); ++it)
@@ -124,11 +123,6 @@ __device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
 __device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
                  ::"r"(remote_addr), "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
-}
-// one lane polls, the warp follows (keeps 31 lanes off the shared-memory port)
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, unsigned parity, int lane) {
-    if (lane == 0) mbar_wait(bar, parity);
-    __syncwarp();
 }
 template <typename T, int VEC> struct SLoad;
 template <> struct SLoad<float, 4> {
@@ -274,7 +268,8 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
                 yn = __ldg(yp);                                         // in flight while we wait below
                 trf::mbar_arrive_expect_tx(&ctl->cready[qc], (unsigned)(a.CL * sizeof(double)));
             }
-            trf::mbar_wait_warp(&ctl->redA[q], phq, lane);
+            trf::mbar_wait(&ctl->redA[q], phq);                         // all 32 lanes wait on the barrier itself
+            __syncwarp();
             if (lane == 0) TR_TRACE(3, i);
             T pc = (T)0;
 #pragma unroll
@@ -326,29 +321,36 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
         }
         const unsigned stage_elems = a.stage_bytes / (unsigned)sizeof(T);
         const T* xthread = stage0 + (size_t)tid * VEC;                  // this thread's first chunk of stage 0
-        int sA = 0;
-        unsigned phA = 0;
-        for (int i = 0; i < cnt; ++i) {
-            trf::mbar_wait_warp(&ctl->full[sA], phA, lane);
-            if (tid == 0) TR_TRACE(1, i);
-            if (lane == 0) TR_TRACE(8 + wid * 2, i);
-            const T* xs = xthread + (size_t)sA * stage_elems;
+        // one pass of phase A over the stage at xs: <x, coef> over this thread's chunks, warp-reduced in T
+        auto phaseA = [&](const T* xs, unsigned m) -> T {
             T p[4] = {(T)0, (T)0, (T)0, (T)0};
 #pragma unroll
             for (int j = 0; j < E; ++j) {
-                if ((cmask >> j) & 1u) {
+                if ((m >> j) & 1u) {
                     T x[VEC];
                     trf::SLoad<T, VEC>::ld(xs + (size_t)j * NCT * VEC, x);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) p[j & 3] = tr_fma<T>(x[v], coef[j][v], p[j & 3]);
                 }
             }
-            if (tid == 0) TR_TRACE(7, i);
-            // warp reduction in T: for fp32 the whole per-sample chain stays off the fp64 pipe (whose
-            // first use after an idle spell costs thousands of cycles on B200 — measured, tools/fused_trace)
             T pw = (p[0] + p[1]) + (p[2] + p[3]);
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) pw += __shfl_xor_sync(TR_FULL, pw, off);
+            return pw;
+        };
+        int sA = 0;
+        unsigned phA = 0;
+        for (int i = 0; i < cnt; ++i) {
+            // EVERY lane waits on the mbarrier itself (hardware-suspended try_wait).  Do not let one lane poll
+            // while the other 31 park in __syncwarp(): after a wait of a few thousand cycles the parked lanes
+            // take ~2 300 cycles to resume, which made the first forward / gradient phase after every idle
+            // spell 3x slower and cost 30 % of the kernel (measured with tools/fused_trace.cu).
+            trf::mbar_wait(&ctl->full[sA], phA);
+            __syncwarp();
+            if (tid == 0) TR_TRACE(1, i);
+            if (lane == 0) TR_TRACE(8 + wid * 2, i);
+            // warp reduction in T: for fp32 the whole per-sample chain stays off the fp64 pipe
+            const T pw = phaseA(xthread + (size_t)sA * stage_elems, cmask);
             if (lane == 0) {
                 reinterpret_cast<T*>(&ctl->pA[sA][wid])[0] = pw;
                 trf::mbar_arrive(&ctl->redA[sA]);
@@ -371,25 +373,28 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
         }
         const unsigned stage_elems = a.stage_bytes / (unsigned)sizeof(T);
         const T* xthread = stage0 + (size_t)tb * VEC;
-        int sB = 0;
-        unsigned phB = 0;
-        int left = (int)(a.spc < cnt ? a.spc : cnt);                    // samples until the next flush of G
-        T* gp = a.Gpart + (size_t)cid * a.nchunk * (size_t)a.Dpad + (size_t)crank * a.Dc + (size_t)tb * VEC;
-        for (int i = 0; i < cnt; ++i) {
-            trf::mbar_wait_warp(&ctl->rready[sB], phB, lane);
-            if (tb == 0) TR_TRACE(5, i);
-            if (lane == 0) TR_TRACE(24 + (wid - NWC) * 2, i);
-            const T r = reinterpret_cast<const T*>(&ctl->resv[sB])[0];
-            const T* xs = xthread + (size_t)sB * stage_elems;
+        auto phaseB = [&](const T* xs, unsigned m, T r) {
 #pragma unroll
             for (int j = 0; j < E; ++j) {
-                if ((cmask >> j) & 1u) {
+                if ((m >> j) & 1u) {
                     T x[VEC];
                     trf::SLoad<T, VEC>::ld(xs + (size_t)j * NCT * VEC, x);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) acc[j][v] = tr_fma<T>(r, x[v], acc[j][v]);
                 }
             }
+        };
+        int sB = 0;
+        unsigned phB = 0;
+        int left = (int)(a.spc < cnt ? a.spc : cnt);                    // samples until the next flush of G
+        T* gp = a.Gpart + (size_t)cid * a.nchunk * (size_t)a.Dpad + (size_t)crank * a.Dc + (size_t)tb * VEC;
+        for (int i = 0; i < cnt; ++i) {
+            trf::mbar_wait(&ctl->rready[sB], phB);                     // all lanes wait (see phase A)
+            __syncwarp();
+            if (tb == 0) TR_TRACE(5, i);
+            if (lane == 0) TR_TRACE(24 + (wid - NWC) * 2, i);
+            const T r = reinterpret_cast<const T*>(&ctl->resv[sB])[0];
+            phaseB(xthread + (size_t)sB * stage_elems, cmask, r);
             __syncwarp();
             if (lane == 0) trf::mbar_arrive(&ctl->empty[sB]);          // all lanes' reads of the stage are done
             if (tb == 0) TR_TRACE(6, i);
