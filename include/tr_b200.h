@@ -121,6 +121,22 @@ int tr_adam_step(tr_handle* h, void* theta, const void* grad, void* m, void* v, 
                  int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
                  void* stream);
 
+/* L-BFGS building blocks (torch.optim.LBFGS as used by fit, std:366,392 / mn:355,381; algorithm of
+ * torch/optim/lbfgs.py:333-536).  The update history, the two-loop recursion and every dot
+ * product stay on the device; the host keeps only the strong-Wolfe control flow and reads back
+ * the scalars it branches on.  Caller-owned state: S, Y (history x P, dtype), prev_g, d (P, dtype),
+ * lstate (4 + history doubles, zero-initialised: H_diag, num_old, ring head, -, ro[history]).
+ *
+ * tr_lbfgs_direction: first != 0 -> d = -g and the history is cleared; otherwise y = g - prev_g,
+ *   s = t*d are pushed when y.s > 1e-10 (H_diag = y.s / y.y) and d = two-loop(g).  Then prev_g = g
+ *   and scal4 = { g.d, sum|g|, max|g|, max|d| } (device doubles).
+ * tr_lbfgs_point: out = x + t*d (the trial point of a line-search evaluation / the accepted step).
+ * tr_lbfgs_gtd: scal2 = { g.d, max|g| } (d may be NULL: only max|g|). */
+int tr_lbfgs_direction(tr_handle* h, const void* g, void* prev_g, void* d, double t, int first, void* S, void* Y,
+                       double* lstate, int history, double* scal4, void* stream);
+int tr_lbfgs_point(tr_handle* h, void* out, const void* x, double t, const void* d, void* stream);
+int tr_lbfgs_gtd(tr_handle* h, const void* g, const void* d, double* scal2, void* stream);
+
 /* Optional timing of the two streaming kernels with CUDA events recorded on the launching stream
  * (what bench.py's roofline uses).  tr_profile_enable(h, 1) resets the sums; tr_profile_read waits
  * for the last recorded launch and returns out6 = { forward-pass ms total, forward launches,

@@ -165,6 +165,33 @@ def fit_lbfgs_std(X, y, Bcp, bias, weights, non_negative, lambda_L2, max_iter, t
             'converged': converged}
 
 
+def fit_lbfgs_mn(X, y, Bcp, weights, non_negative, class_weights, lambda_L2, max_iter, tol, patience,
+                 lbfgs_kwargs, softplus_kwargs=None, running_loss_logging_interval=1):
+    """mn:355-381 (L-BFGS outer loop, CE on probabilities, logging without the penalty)."""
+    Bcp = _leaf(Bcp)
+    opt = torch.optim.LBFGS(Bcp, **lbfgs_kwargs)
+    loss_fn = torch.nn.CrossEntropyLoss(weight=torch.as_tensor(class_weights, dtype=X.dtype))
+
+    def closure():
+        opt.zero_grad()
+        P = mn_model(X, Bcp, weights, non_negative, softplus_kwargs)
+        loss = loss_fn(P, y) + lambda_L2 * L2_penalty(Bcp)
+        loss.backward()
+        return loss
+
+    losses, converged = [], False
+    for ii in range(max_iter):
+        if ii % running_loss_logging_interval == 0:
+            with torch.no_grad():
+                losses.append(loss_fn(mn_model(X, Bcp, weights, non_negative, softplus_kwargs), y).item())
+        if ii > patience:
+            if np.sum(np.abs(np.diff(losses[ii - patience:]))) < tol:
+                converged = True
+                break
+        opt.step(closure)
+    return {'Bcp': [b.detach() for b in Bcp], 'loss_running': losses, 'converged': converged}
+
+
 # ----------------------------------------------------------------------------
 # Part 2: closed form (SURVEY.md Appendix A), no autograd, packed layout
 # ----------------------------------------------------------------------------

@@ -12,7 +12,7 @@ SYMBOLS = [
     'tr_version', 'tr_create', 'tr_destroy', 'tr_last_error', 'tr_param_count', 'tr_gradsum_count',
     'tr_reserve', 'tr_forward_std', 'tr_forward_mn', 'tr_fwd_grad_std', 'tr_fwd_grad_mn',
     'tr_backward_std', 'tr_finish_grad', 'tr_adam_step', 'tr_last_launch_info', 'tr_profile_enable',
-    'tr_profile_read', 'tr_set_option',
+    'tr_profile_read', 'tr_set_option', 'tr_lbfgs_direction', 'tr_lbfgs_point', 'tr_lbfgs_gtd',
 ]
 
 
@@ -47,6 +47,9 @@ def _load():
     lib.tr_profile_enable.argtypes = [vp, i32]
     lib.tr_profile_read.argtypes = [vp, ctypes.POINTER(dbl)]
     lib.tr_set_option.argtypes = [vp, ctypes.c_char_p, i64]
+    lib.tr_lbfgs_direction.argtypes = [vp, vp, vp, vp, dbl, i32, vp, vp, vp, i32, vp, vp]
+    lib.tr_lbfgs_point.argtypes = [vp, vp, vp, dbl, vp, vp]
+    lib.tr_lbfgs_gtd.argtypes = [vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ('tr_last_error',):

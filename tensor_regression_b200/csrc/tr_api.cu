@@ -807,6 +807,50 @@ int tr_set_option(tr_handle* h, const char* name, int64_t value) {
     return fail(h, TR_ERR_INVALID, "unknown option '%s'", name);
 }
 
+int tr_lbfgs_direction(tr_handle* h, const void* g, void* prev_g, void* d, double t, int first, void* S, void* Y,
+                       double* lstate, int history, double* scal4, void* stream) {
+    if (!h) return TR_ERR_INVALID;
+    if (!g || !prev_g || !d || !S || !Y || !lstate || !scal4) return fail(h, TR_ERR_INVALID, "null pointer argument");
+    if (history < 1 || history > TR_LBFGS_MAX_HIST)
+        return fail(h, TR_ERR_UNSUPPORTED, "history_size %d (supported: 1..%d)", history, TR_LBFGS_MAX_HIST);
+    DeviceGuard dg(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long P = h->geo.pf + (h->geo.C == 0 ? 1 : 0);
+    if (h->dtype == TR_F32)
+        k_lbfgs_direction<float><<<1, 1024, 0, st>>>((const float*)g, (float*)prev_g, (float*)d, t, first, (float*)S,
+                                                     (float*)Y, lstate, history, P, scal4);
+    else
+        k_lbfgs_direction<double><<<1, 1024, 0, st>>>((const double*)g, (double*)prev_g, (double*)d, t, first,
+                                                      (double*)S, (double*)Y, lstate, history, P, scal4);
+    TR_LAUNCH_CHECK(h);
+    return TR_OK;
+}
+
+int tr_lbfgs_point(tr_handle* h, void* out, const void* x, double t, const void* d, void* stream) {
+    if (!h) return TR_ERR_INVALID;
+    if (!out || !x || !d) return fail(h, TR_ERR_INVALID, "null pointer argument");
+    DeviceGuard dg(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long P = h->geo.pf + (h->geo.C == 0 ? 1 : 0);
+    const int grid = (int)std::min<long long>((P + 255) / 256, 1024);
+    if (h->dtype == TR_F32) k_axpy_out<float><<<grid, 256, 0, st>>>((float*)out, (const float*)x, t, (const float*)d, P);
+    else k_axpy_out<double><<<grid, 256, 0, st>>>((double*)out, (const double*)x, t, (const double*)d, P);
+    TR_LAUNCH_CHECK(h);
+    return TR_OK;
+}
+
+int tr_lbfgs_gtd(tr_handle* h, const void* g, const void* d, double* scal2, void* stream) {
+    if (!h) return TR_ERR_INVALID;
+    if (!g || !scal2) return fail(h, TR_ERR_INVALID, "null pointer argument");
+    DeviceGuard dg(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long P = h->geo.pf + (h->geo.C == 0 ? 1 : 0);
+    if (h->dtype == TR_F32) k_lbfgs_gtd<float><<<1, 1024, 0, st>>>((const float*)g, (const float*)d, P, scal2);
+    else k_lbfgs_gtd<double><<<1, 1024, 0, st>>>((const double*)g, (const double*)d, P, scal2);
+    TR_LAUNCH_CHECK(h);
+    return TR_OK;
+}
+
 int tr_last_launch_info(tr_handle* h, int64_t* info8) {
     if (!h || !info8) return TR_ERR_INVALID;
     for (int i = 0; i < 8; ++i) info8[i] = h->info[i];

@@ -429,3 +429,144 @@ __global__ void k_adam(T* __restrict__ theta, const T* __restrict__ grad, T* __r
         theta[p] = th + (T)(-step_size) * (mm / dn);                  // addcdiv_(m, denom, value=-step_size)
     }
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// L-BFGS on the flat parameter vector (torch/optim/lbfgs.py:333-536, used by std:366,392 and
+// mn:355,381): history, two-loop recursion and every dot product stay on the device; only the few
+// scalars the strong-Wolfe control flow branches on are read back by the host.
+// lstate (double): [0]=H_diag, [1]=num_old, [2]=head (ring start), [3]=unused, [4 .. 4+hist)=ro
+// ---------------------------------------------------------------------------------------------
+#define TR_LBFGS_MAX_HIST 256
+
+__device__ __forceinline__ double block_sum_bcast(double v, double* sbuf, double* sb) {
+    v = block_sum(v, sbuf);
+    if (threadIdx.x == 0) *sb = v;
+    __syncthreads();
+    const double r = *sb;
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ double block_max_bcast(double v, double* sbuf, double* sb) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) sbuf[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        double r = lane < nw ? sbuf[lane] : 0.0;
+        r = warp_max(r);
+        if (lane == 0) *sb = r;
+    }
+    __syncthreads();
+    const double r = *sb;
+    __syncthreads();
+    return r;
+}
+
+// One "compute the search direction" step (lbfgs.py:395-440) in a single block.
+//   first != 0 : d = -g, history cleared, H_diag = 1
+//   otherwise  : y = g - prev_g, s = d*t; if y.s > 1e-10 push (y, s, 1/y.s) and H_diag = y.s / y.y;
+//                two-loop recursion -> d
+// then prev_g = g and scal = { g.d, sum|g|, max|g|, max|d| }.
+template <typename T>
+__global__ void __launch_bounds__(1024) k_lbfgs_direction(const T* __restrict__ g, T* __restrict__ prev_g,
+                                                          T* __restrict__ d, double t, int first, T* __restrict__ S,
+                                                          T* __restrict__ Y, double* __restrict__ ls, int hist,
+                                                          long long P, double* __restrict__ scal) {
+    __shared__ double sbuf[32];
+    __shared__ double sb;
+    __shared__ double s_al[TR_LBFGS_MAX_HIST];
+    double* ro = ls + 4;
+    int num_old = (int)ls[1], head = (int)ls[2];
+    double H_diag = ls[0];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    __syncthreads();                                   // every thread read the state before it is rewritten
+    if (first) {
+        for (long long p = tid; p < P; p += nt) d[p] = -g[p];
+        num_old = 0; head = 0; H_diag = 1.0;
+    } else {
+        double ys = 0.0, yy = 0.0;
+        for (long long p = tid; p < P; p += nt) {
+            const T y = g[p] - prev_g[p];
+            const T s = d[p] * (T)t;
+            ys += (double)y * (double)s;
+            yy += (double)y * (double)y;
+        }
+        ys = block_sum_bcast(ys, sbuf, &sb);
+        yy = block_sum_bcast(yy, sbuf, &sb);
+        if (ys > 1e-10) {
+            int slot;
+            if (num_old == hist) { slot = head; head = (head + 1) % hist; }
+            else { slot = (head + num_old) % hist; ++num_old; }
+            for (long long p = tid; p < P; p += nt) {
+                Y[(long long)slot * P + p] = g[p] - prev_g[p];
+                S[(long long)slot * P + p] = d[p] * (T)t;
+            }
+            if (tid == 0) ro[slot] = 1.0 / ys;
+            H_diag = ys / yy;
+            __syncthreads();
+        }
+        // two-loop recursion; q lives in d
+        for (long long p = tid; p < P; p += nt) d[p] = -g[p];
+        for (int i = num_old - 1; i >= 0; --i) {
+            const long long o = (long long)((head + i) % hist) * P;
+            double a = 0.0;
+            for (long long p = tid; p < P; p += nt) a += (double)S[o + p] * (double)d[p];
+            a = block_sum_bcast(a, sbuf, &sb) * ro[(head + i) % hist];
+            if (tid == 0) s_al[i] = a;
+            for (long long p = tid; p < P; p += nt) d[p] = d[p] - (T)a * Y[o + p];
+        }
+        for (long long p = tid; p < P; p += nt) d[p] = d[p] * (T)H_diag;
+        __syncthreads();
+        for (int i = 0; i < num_old; ++i) {
+            const long long o = (long long)((head + i) % hist) * P;
+            double be = 0.0;
+            for (long long p = tid; p < P; p += nt) be += (double)Y[o + p] * (double)d[p];
+            be = block_sum_bcast(be, sbuf, &sb) * ro[(head + i) % hist];
+            const double c = s_al[i] - be;
+            for (long long p = tid; p < P; p += nt) d[p] = d[p] + (T)c * S[o + p];
+        }
+    }
+    double gtd = 0.0, g1 = 0.0, gm = 0.0, dm = 0.0;
+    for (long long p = tid; p < P; p += nt) {
+        const double gv = (double)g[p], dv = (double)d[p];
+        prev_g[p] = g[p];
+        gtd += gv * dv;
+        g1 += fabs(gv);
+        gm = fmax(gm, fabs(gv));
+        dm = fmax(dm, fabs(dv));
+    }
+    gtd = block_sum_bcast(gtd, sbuf, &sb);
+    g1 = block_sum_bcast(g1, sbuf, &sb);
+    gm = block_max_bcast(gm, sbuf, &sb);
+    dm = block_max_bcast(dm, sbuf, &sb);
+    if (tid == 0) {
+        scal[0] = gtd; scal[1] = g1; scal[2] = gm; scal[3] = dm;
+        ls[0] = H_diag; ls[1] = (double)num_old; ls[2] = (double)head;
+    }
+}
+
+// out = x + t * d   (lbfgs.py:325-330 _directional_evaluate / _add_grad)
+template <typename T>
+__global__ void k_axpy_out(T* __restrict__ out, const T* __restrict__ x, double t, const T* __restrict__ d, long long P) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x)
+        out[p] = x[p] + (T)t * d[p];
+}
+
+// scal = { g.d, max|g| }  (line-search directional derivative, optimality condition)
+template <typename T>
+__global__ void __launch_bounds__(1024) k_lbfgs_gtd(const T* __restrict__ g, const T* __restrict__ d, long long P,
+                                                    double* __restrict__ scal) {
+    __shared__ double sbuf[32];
+    __shared__ double sb;
+    double gtd = 0.0, gm = 0.0;
+    for (long long p = threadIdx.x; p < P; p += blockDim.x) {
+        const double gv = (double)g[p];
+        gtd += gv * (d ? (double)d[p] : 0.0);
+        gm = fmax(gm, fabs(gv));
+    }
+    gtd = block_sum_bcast(gtd, sbuf, &sb);
+    gm = block_max_bcast(gm, sbuf, &sb);
+    if (threadIdx.x == 0) { scal[0] = gtd; scal[1] = gm; }
+}

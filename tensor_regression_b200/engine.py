@@ -224,6 +224,27 @@ class Engine:
         self.launches += 1
 
 
+    # -- L-BFGS vector kernels (see lbfgs.py) ------------------------------------------------
+    def lbfgs_direction(self, g, prev_g, d, t, first, S, Y, lstate, history, scal4):
+        with torch.cuda.device(self.device):
+            self._ck(_lib.lib.tr_lbfgs_direction(self._h, g.data_ptr(), prev_g.data_ptr(), d.data_ptr(), float(t),
+                                                 1 if first else 0, S.data_ptr(), Y.data_ptr(), lstate.data_ptr(),
+                                                 int(history), scal4.data_ptr(), self._stream()))
+        self.launches += 1
+
+    def lbfgs_point(self, out, x, t, d):
+        with torch.cuda.device(self.device):
+            self._ck(_lib.lib.tr_lbfgs_point(self._h, out.data_ptr(), x.data_ptr(), float(t), d.data_ptr(),
+                                             self._stream()))
+        self.launches += 1
+
+    def lbfgs_gtd(self, g, d, scal2):
+        with torch.cuda.device(self.device):
+            self._ck(_lib.lib.tr_lbfgs_gtd(self._h, g.data_ptr(), d.data_ptr() if d is not None else None,
+                                           scal2.data_ptr(), self._stream()))
+        self.launches += 1
+
+
 class ShardedSum:
     """Sums the packed ``gradsum`` vector over the ranks that each hold a slice of the sample
     axis: one all-reduce of P+2 doubles per closure evaluation.  With

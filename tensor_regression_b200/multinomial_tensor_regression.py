@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import engine as _engine
+from . import lbfgs as _lbfgs
 from .engine import nn_mask_of
 from .standard_tensor_regression import (_adam_hyper, _engine_for, _flatten, _predict_streamed)
 
@@ -232,15 +233,14 @@ class CP_logistic_regression():
         sharder = self._sharder()
         W = sharder.total(cw[self.y].sum().item(), self.X.device)
 
-        param = self.theta
-        optimizer = torch.optim.LBFGS([param], **LBFGS_kwargs)
+        optimizer = _lbfgs.LBFGS(eng, self.theta, **LBFGS_kwargs)    # torch.optim.LBFGS's algorithm, device-resident
+        gs = torch.empty(eng.n_gradsum, dtype=torch.float64, device=self.theta.device)
 
-        def closure():
-            gs = eng.fwd_grad_mn(self.X, self.y, cw, self.theta, self.weights, self._mask(), beta, thr)
+        def closure(grad_out, loss_out):
+            eng.fwd_grad_mn(self.X, self.y, cw, self.theta, self.weights, self._mask(), beta, thr, gradsum=gs)
             sharder.sum_(gs)
-            grad, loss = eng.finish(gs, 1.0 / W, 1.0 / W, self.theta, lambda_L2, self._mask(), beta, thr)
-            param.grad = grad
-            return loss[1].to(torch.float32)
+            eng.finish(gs, 1.0 / W, 1.0 / W, self.theta, lambda_L2, self._mask(), beta, thr, grad=grad_out,
+                       loss=loss_out)
 
         def logged_loss():
             # extra forward, CE without the penalty (mn:371-372): one pass over X, then the
@@ -262,7 +262,6 @@ class CP_logistic_regression():
                     break
 
             optimizer.step(closure)
-        param.grad = None
         if (verbose == True) or (verbose >= 1):  # noqa: E712
             if convergence_reached:
                 print('Convergence reached')

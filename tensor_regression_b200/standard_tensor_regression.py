@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from . import engine as _engine
+from . import lbfgs as _lbfgs
 from .engine import nn_mask_of
 
 _DEFAULT_SOFTPLUS = {'beta': 50, 'threshold': 1}
@@ -260,8 +261,9 @@ class CP_linear_regression():
             verbose=False,
             running_loss_logging_interval=10,
             LBFGS_kwargs=None):
-        """std:305-398 — L-BFGS (torch.optim.LBFGS drives the line search on the flat parameter
-        vector; every closure evaluation is the two-pass CUDA path)."""
+        """std:305-398 — L-BFGS with torch.optim.LBFGS's algorithm and keyword arguments; history,
+        two-loop recursion and vector algebra are device-resident (lbfgs.py), every closure
+        evaluation is one tr_fwd_grad_std + tr_finish_grad."""
         if LBFGS_kwargs is None:
             # the reference's "default" dict (std:353-362) is a bare expression: None raises there too
             raise TypeError('LBFGS_kwargs must be a dict of torch.optim.LBFGS keyword arguments (got None)')
@@ -271,13 +273,16 @@ class CP_linear_regression():
         eng = self._engine()
         beta, thr = self._sp()
 
-        param = self.theta            # one flat leaf == the reference's Bcp + [bias] list, same order
-        optimizer = torch.optim.LBFGS([param], **LBFGS_kwargs)
+        # one flat vector == the reference's Bcp + [bias] parameter list in the same order; the optimizer
+        # is torch.optim.LBFGS's algorithm with device-resident history / two-loop recursion (lbfgs.py)
+        optimizer = _lbfgs.LBFGS(eng, self.theta, **LBFGS_kwargs)
+        gs = torch.empty(eng.n_gradsum, dtype=torch.float64, device=self.theta.device)
 
-        def closure():
-            grad, loss = self._closure_eval(X, y, lambda_L2, sharder, n_total)
-            param.grad = grad
-            return loss[1].to(self.dtype)
+        def closure(grad_out, loss_out):
+            eng.fwd_grad_std(X, y, self.theta, self.weights, self._mask(), beta, thr, gradsum=gs)
+            sharder.sum_(gs)
+            eng.finish(gs, 2.0 / n_total, 1.0 / n_total, self.theta, lambda_L2, self._mask(), beta, thr,
+                       grad=grad_out, loss=loss_out)
 
         def logged_loss():
             # extra forward without the penalty (std:380-382): one pass over X
@@ -299,7 +304,6 @@ class CP_linear_regression():
                     break
 
             optimizer.step(closure)
-        param.grad = None
         if (verbose == True) or (verbose >= 1):  # noqa: E712
             if convergence_reached:
                 print('Convergence reached')

@@ -433,3 +433,21 @@ def test_fused_not_eligible_falls_back_loudly():
     eng.set_option('fused', -1)
     eng.fwd_grad_std(dev(X), dev(y).reshape(-1), theta, dev(torch.ones(R)), 0, 50.0, 1.0)
     assert eng.launch_info()['path'] == 'two-pass'
+
+
+def test_mn_lbfgs_fit_tracks_reference_algorithm():
+    """fit (L-BFGS) of the multinomial class in fp32: strong-Wolfe branches may flip on fp32 noise
+    (SURVEY H3), so the check is on the logged losses, not the factors."""
+    from tensor_regression_b200 import multinomial_tensor_regression as MTR
+    X, y, _ = O.synth_mn(160, (6, 5, 4), 3, 4, 77)
+    nn = [False] * 4
+    B0 = O.init_mn([6, 5, 4, 4], 3, nn, scale=0.5)
+    cw = np.ones(4, dtype=np.float32)
+    ref = O.fit_lbfgs_mn(X, y, B0, torch.ones(3), nn, cw, 0.01, 4, 1e-50, 10, LBFGS)
+    m = MTR.CP_logistic_regression(X, y, rank=3, Bcp_init=[b.clone() for b in B0], device=DEV)
+    m.fit(lambda_L2=0.01, max_iter=4, tol=1e-50, patience=10, weights=cw, running_loss_logging_interval=1,
+          LBFGS_kwargs=LBFGS)
+    assert len(m.loss_running) == len(ref['loss_running']) == 4
+    assert rel(m.loss_running[:2], ref['loss_running'][:2]) < 1e-4
+    assert m.loss_running[-1] < m.loss_running[0]
+    assert abs(m.loss_running[-1] - ref['loss_running'][-1]) < 2e-2 * abs(ref['loss_running'][-1])
