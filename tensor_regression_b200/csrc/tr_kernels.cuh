@@ -195,9 +195,9 @@ __global__ void __launch_bounds__(TR_TPB, TR_MINB) k_fwd(const FwdArgs<T> a) {
 
     constexpr int TILE = 32 * E * VEC;
     constexpr int RKR = tr_next_pow2(RK);
-    constexpr int M = U * RKR;
+    constexpr int M = tr_next_pow2(U * RKR);          // padded with zeros when U is not a power of two
     constexpr int LGM = tr_log2(M);
-    static_assert(M <= 32, "U * next_pow2(RK) must be <= 32");
+    static_assert(M <= 32, "next_pow2(U * next_pow2(RK)) must be <= 32");
 
     const int lane = threadIdx.x & 31;
     const long long warp_global = (long long)blockIdx.x * TR_WPB + (threadIdx.x >> 5);
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(TR_TPB, TR_MINB) k_fwd(const FwdArgs<T> a) {
                 const int q = lane >> (5 - LGM);
                 const int u = q / RKR, c = q % RKR;
                 const long long n = n0 + (long long)u * a.Gn;
-                if (c < RK && n < a.N) a.partial[(n * a.WT + t) * RK + c] = vals[0];
+                if (u < U && c < RK && n < a.N) a.partial[(n * a.WT + t) * RK + c] = vals[0];
             }
         }
     }

@@ -44,7 +44,7 @@
 #define TR_UF6 4
 #endif
 #ifndef TR_UG6
-#define TR_UG6 2
+#define TR_UG6 3
 #endif
 
 #if TR_PART == 0
