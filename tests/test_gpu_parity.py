@@ -451,3 +451,135 @@ def test_mn_lbfgs_fit_tracks_reference_algorithm():
     assert rel(m.loss_running[:2], ref['loss_running'][:2]) < 1e-4
     assert m.loss_running[-1] < m.loss_running[0]
     assert abs(m.loss_running[-1] - ref['loss_running'][-1]) < 2e-2 * abs(ref['loss_running'][-1])
+
+
+# ------------------------------------------------------------------------------------------
+# out-of-bounds detection without compute-sanitizer (closed on this pool): NaN poison around every
+# input the kernels read, sentinels around every output they write
+# ------------------------------------------------------------------------------------------
+def _guarded(t, pad=4096, poison=float('nan')):
+    """Return (view, whole): `view` has t's contents and sits in the middle of a poisoned buffer."""
+    flat = torch.full((t.numel() + 2 * pad,), poison, dtype=t.dtype, device=DEV) if t.is_floating_point() else \
+        torch.full((t.numel() + 2 * pad,), -1, dtype=t.dtype, device=DEV)
+    flat[pad:pad + t.numel()] = t.reshape(-1).to(DEV)
+    return flat[pad:pad + t.numel()].view(t.shape), flat
+
+
+@pytest.mark.parametrize('fused', [0, 1], ids=['two_pass', 'single_pass'])
+@pytest.mark.parametrize('N,dims', [(37, (8, 4, 8)), (19, (5, 7, 3)), (3, (64, 64, 32))], ids=['small', 'odd_D', 'cfg2_shape'])
+def test_std_kernels_do_not_touch_memory_outside_their_buffers(fused, N, dims):
+    from tensor_regression_b200 import engine
+    R = 3
+    D = int(np.prod(dims))
+    if fused and D % 4:
+        pytest.skip('single-pass kernel needs 16-byte rows')
+    X, y, _ = O.synth_std(N, dims, R, 5)
+    y = y.reshape(-1)
+    B0 = O.init_std(dims, R, [False] * (len(dims) + 1))
+    eng = engine_for(dims, R, 0, torch.float32)
+    eng.set_option('fused', fused)
+    pad = 4096
+    Xg, Xw = _guarded(X, pad)
+    yg, _ = _guarded(y, pad)
+    thg, _ = _guarded(O.pack(B0, torch.tensor([0.1])), pad)
+    wg, _ = _guarded(torch.ones(R), pad)
+    SENT = -777.0
+    gs_w = torch.full((eng.n_gradsum + 2 * pad,), SENT, dtype=torch.float64, device=DEV)
+    yh_w = torch.full((N + 2 * pad,), SENT, dtype=torch.float32, device=DEV)
+    gs, yh = gs_w[pad:pad + eng.n_gradsum], yh_w[pad:pad + N]
+    eng.fwd_grad_std(Xg, yg, thg, wg, 0, 50.0, 1.0, gradsum=gs, yhat=yh)
+    torch.cuda.synchronize()
+    cf = O.closed_form_std(X.double(), y.double(), [b.double() for b in B0], torch.tensor([0.1], dtype=torch.float64),
+                           torch.ones(R, dtype=torch.float64), [False] * (len(dims) + 1))
+    assert torch.isfinite(gs).all() and torch.isfinite(yh).all()          # a poisoned read would show up as NaN
+    assert rel(gs, cf['gradsum']) < 1e-5 and rel(yh, cf['y_hat']) < 1e-5
+    for w in (gs_w, yh_w):                                                # sentinels around the outputs intact
+        assert bool((w[:pad] == SENT).all()) and bool((w[-pad:] == SENT).all())
+    assert bool(torch.isnan(Xw[:pad]).all()) and bool(torch.isnan(Xw[-pad:]).all())
+    eng.set_option('fused', -1)
+
+
+def test_mn_kernels_do_not_touch_memory_outside_their_buffers():
+    from tensor_regression_b200 import engine
+    N, dims, C, R = 29, (6, 5, 4), 3, 5
+    X, y, _ = O.synth_mn(N, dims, R, C, 6)
+    B0 = O.init_mn(list(dims) + [C], R, [False] * 4, scale=0.5)
+    eng = engine_for(dims, R, C, torch.float32)
+    pad = 4096
+    Xg, _ = _guarded(X, pad)
+    yg, _ = _guarded(y, pad)
+    thg, _ = _guarded(O.pack(B0), pad)
+    wg, _ = _guarded(torch.ones(R), pad)
+    cwg, _ = _guarded(torch.ones(C), pad)
+    SENT = -777.0
+    gs_w = torch.full((eng.n_gradsum + 2 * pad,), SENT, dtype=torch.float64, device=DEV)
+    P_w = torch.full((N * C + 2 * pad,), SENT, dtype=torch.float32, device=DEV)
+    gs, P = gs_w[pad:pad + eng.n_gradsum], P_w[pad:pad + N * C].view(N, C)
+    eng.fwd_grad_mn(Xg, yg, cwg, thg, wg, 0, 50.0, 1.0, gradsum=gs, P=P)
+    torch.cuda.synchronize()
+    cf = O.closed_form_mn(X.double(), y, [b.double() for b in B0], torch.ones(R, dtype=torch.float64), [False] * 4,
+                          torch.ones(C, dtype=torch.float64))
+    assert torch.isfinite(gs).all() and torch.isfinite(P).all()
+    assert rel(gs, cf['gradsum']) < 1e-5 and rel(P, cf['P']) < 1e-5
+    for w in (gs_w, P_w):
+        assert bool((w[:pad] == SENT).all()) and bool((w[-pad:] == SENT).all())
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json configs[1] at FULL size (N=200000, 64x64x32, rank 8, fp32: 104.9 GB resident in HBM),
+# through size-independent properties (the CPU oracle cannot finish this size in seconds)
+# ------------------------------------------------------------------------------------------
+def test_cfg2_full_size_properties():
+    from tensor_regression_b200 import engine
+    free, _ = torch.cuda.mem_get_info()
+    N, dims, R = 200000, (64, 64, 32), 8
+    D = int(np.prod(dims))
+    if free < N * D * 4 + (8 << 30):
+        pytest.skip('needs ~113 GB of free HBM')
+    g = torch.Generator(device=DEV).manual_seed(2024)
+    X = torch.empty((N, *dims), dtype=torch.float32, device=DEV)
+    for lo in range(0, N, 2048):
+        X[lo:lo + 2048].normal_(generator=g)
+    nn = [False] * 4
+    B0 = O.init_std(dims, R, nn)
+    Fs = [0.3 * torch.randn(d, R, generator=torch.Generator().manual_seed(7)) for d in dims]
+    eng = engine_for(dims, R, 0, torch.float32)
+    w = dev(torch.ones(R))
+    theta_star = dev(O.pack(Fs, torch.tensor([0.1])))
+    theta = dev(O.pack(B0, torch.tensor([0.0])))
+    y = eng.forward_std(X, theta_star, w, 0, 50.0, 1.0)
+    # (1) forward at full size == oracle on a regenerated-by-copy sub-range (first / last 300 samples)
+    for sl in (slice(0, 300), slice(N - 300, N)):
+        Xs = X[sl].cpu()
+        want = O.lin_model(Xs.double(), [f.double() for f in Fs], torch.ones(R, dtype=torch.float64), nn,
+                           torch.tensor([0.1], dtype=torch.float64))
+        assert rel(y[sl], want) < 1e-5
+    # (2) single-pass == two-pass at full size, and both deterministic
+    eng.set_option('fused', 1)
+    yh1 = torch.empty_like(y)
+    one = eng.fwd_grad_std(X, y, theta, w, 0, 50.0, 1.0, yhat=yh1).clone()
+    assert eng.launch_info()['path'].startswith('single-pass')
+    eng.set_option('fused', 0)
+    yh2 = torch.empty_like(y)
+    two = eng.fwd_grad_std(X, y, theta, w, 0, 50.0, 1.0, yhat=yh2).clone()
+    assert rel(one, two) < 1e-5 and rel(yh1, yh2) < 1e-5
+    # (3) the packed sums of disjoint shards add up to the whole (what the all-reduce relies on)
+    parts = torch.zeros_like(two)
+    for r in range(3):
+        lo, hi = engine.shard_bounds(N, r, 3)
+        eng.set_option('fused', r % 2)
+        parts += eng.fwd_grad_std(X[lo:hi], y[lo:hi], theta, w, 0, 50.0, 1.0)
+    assert rel(parts, two) < 1e-5
+    # (4) linearity of the gradient pass in the residual: backward(a*r1 + r2) == a*backward(r1) + backward(r2)
+    r1 = torch.randn(N, device=DEV, generator=g)
+    r2 = torch.randn(N, device=DEV, generator=g)
+    b1 = eng.backward_std(X, r1, theta, w, 0, 50.0, 1.0).clone()
+    b2 = eng.backward_std(X, r2, theta, w, 0, 50.0, 1.0).clone()
+    b12 = eng.backward_std(X, (0.5 * r1 + r2).contiguous(), theta, w, 0, 50.0, 1.0)
+    assert rel(b12, 0.5 * b1 + b2) < 1e-5
+    # (5) the gradient at the generating factors is (numerically) zero relative to the gradient at the init
+    g_star = eng.fwd_grad_std(X, y, theta_star, w, 0, 50.0, 1.0)
+    assert float(g_star[:-1].abs().max()) < 1e-4 * float(two[:-1].abs().max())
+    eng.set_option('fused', -1)
+    del X
+    torch.cuda.empty_cache()
