@@ -106,6 +106,12 @@ int tr_backward_std(tr_handle* h, const void* X, const void* dyhat, int64_t N, c
                     const void* w, uint32_t nn_mask, double sp_beta, double sp_thr,
                     double* gradsum, void* stream);
 
+/* Vector-Jacobian product of model (mn:148-187) for an arbitrary upstream gradient dP (N,C) wrt the
+ * softmax probabilities: recomputes the forward pass, dZ = P*(dP - sum_c dP*P), then all factor
+ * gradients incl. the class factor.  gradsum = [ dFt | 0 ]. */
+int tr_backward_mn(tr_handle* h, const void* X, const void* dP, int64_t N, const void* theta, const void* w,
+                   uint32_t nn_mask, double sp_beta, double sp_thr, double* gradsum, void* stream);
+
 /* gradsum (after the cross-GPU sum, if any) -> gradient wrt the RAW parameters and the losses:
  *   grad[F_m] = grad_scale * dFt_m * softplus'(F_m) + lambda_L2 * F_m / ||F_m||_F   (L2_penalty, std:180-196)
  *   grad[bias] = grad_scale * gradsum[Pf]            (standard only)

@@ -11,7 +11,7 @@ TR_F32, TR_F64 = 0, 1
 SYMBOLS = [
     'tr_version', 'tr_create', 'tr_destroy', 'tr_last_error', 'tr_param_count', 'tr_gradsum_count',
     'tr_reserve', 'tr_forward_std', 'tr_forward_mn', 'tr_fwd_grad_std', 'tr_fwd_grad_mn',
-    'tr_backward_std', 'tr_finish_grad', 'tr_adam_step', 'tr_last_launch_info', 'tr_profile_enable',
+    'tr_backward_std', 'tr_backward_mn', 'tr_finish_grad', 'tr_adam_step', 'tr_last_launch_info', 'tr_profile_enable',
     'tr_profile_read', 'tr_set_option', 'tr_lbfgs_direction', 'tr_lbfgs_point', 'tr_lbfgs_gtd',
 ]
 
@@ -41,6 +41,7 @@ def _load():
     lib.tr_fwd_grad_std.argtypes = [vp, vp, vp, i64, vp, vp, u32, dbl, dbl, vp, vp, vp]
     lib.tr_fwd_grad_mn.argtypes = [vp, vp, vp, vp, i64, vp, vp, u32, dbl, dbl, vp, vp, vp]
     lib.tr_backward_std.argtypes = [vp, vp, vp, i64, vp, vp, u32, dbl, dbl, vp, vp]
+    lib.tr_backward_mn.argtypes = [vp, vp, vp, i64, vp, vp, u32, dbl, dbl, vp, vp]
     lib.tr_finish_grad.argtypes = [vp, vp, dbl, dbl, vp, dbl, u32, dbl, dbl, vp, vp, vp]
     lib.tr_adam_step.argtypes = [vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, dbl, dbl, vp]
     lib.tr_last_launch_info.argtypes = [vp, ctypes.POINTER(i64)]

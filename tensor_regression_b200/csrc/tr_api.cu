@@ -510,17 +510,18 @@ int fwd_grad_std_t(tr_handle* h, const void* X, const void* y, long long N, cons
 template <typename T>
 int mn_t(tr_handle* h, const void* X, const long long* y, const void* class_w, long long N, const void* theta,
          const void* w, uint32_t nn_mask, double beta, double thr, double* gradsum, void* P, long long* pred,
-         cudaStream_t st) {
+         cudaStream_t st, const void* dP_in = nullptr) {
     Plan pl; const KEntry<T>* e; int rc;
     const Geo& g = h->geo;
     if ((rc = make_plan<T>(h, N, g.R, vec_ok(X, g.D, sizeof(T)), &pl, &e))) return rc;
     if ((rc = reserve_for<T>(h, N, pl))) return rc;
     h->launches = 0;
     if ((rc = run_forward<T>(h, (const T*)X, N, (const T*)theta, (const T*)w, nn_mask, beta, thr, pl, e, st))) return rc;
-    const bool train = (y != nullptr);
+    const bool train = (y != nullptr) || (dP_in != nullptr);
     EpiMnArgs<T> ea;
     ea.partial = (const T*)h->partial.p; ea.WT = pl.WT; ea.RKs = pl.RKs; ea.N = N; ea.R = g.R; ea.C = g.C;
     ea.FC = (const double*)h->Ft64.p + g.pfeat; ea.w = (const T*)w; ea.y = y; ea.class_w = (const T*)class_w;
+    ea.dP_in = (const T*)dP_in;
     ea.P = (T*)P; ea.pred = pred;
     ea.V = train ? (T*)h->V.p : nullptr; ea.u_ws = train ? (T*)h->u_ws.p : nullptr;
     ea.dZ_ws = train ? (T*)h->dZ_ws.p : nullptr; ea.part = train ? (double*)h->epi_part.p : nullptr;
@@ -728,6 +729,20 @@ int tr_fwd_grad_mn(tr_handle* h, const void* X, const int64_t* y, const void* cl
     return h->dtype == TR_F32
                ? mn_t<float>(h, X, (const long long*)y, class_w, N, theta, w, nn_mask, sp_beta, sp_thr, gradsum, P, nullptr, st)
                : mn_t<double>(h, X, (const long long*)y, class_w, N, theta, w, nn_mask, sp_beta, sp_thr, gradsum, P, nullptr, st);
+}
+
+int tr_backward_mn(tr_handle* h, const void* X, const void* dP, int64_t N, const void* theta, const void* w,
+                   uint32_t nn_mask, double sp_beta, double sp_thr, double* gradsum, void* stream) {
+    int rc = check_common(h, X, N, theta, w);
+    if (rc) return rc;
+    if (h->geo.C == 0) return fail(h, TR_ERR_INVALID, "tr_backward_mn on a standard handle");
+    if (!gradsum || (N > 0 && !dP)) return fail(h, TR_ERR_INVALID, "null dP / gradsum pointer");
+    DeviceGuard dg(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) return zero_gradsum(h, gradsum, st);
+    return h->dtype == TR_F32
+               ? mn_t<float>(h, X, nullptr, nullptr, N, theta, w, nn_mask, sp_beta, sp_thr, gradsum, nullptr, nullptr, st, dP)
+               : mn_t<double>(h, X, nullptr, nullptr, N, theta, w, nn_mask, sp_beta, sp_thr, gradsum, nullptr, nullptr, st, dP);
 }
 
 int tr_finish_grad(tr_handle* h, const double* gradsum, double grad_scale, double loss_scale, const void* theta,

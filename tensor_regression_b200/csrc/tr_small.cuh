@@ -86,7 +86,8 @@ struct EpiMnArgs {
     int R, C;
     const double* FC;   // class factor (C,R), softplus-ed, double
     const T* w;         // rank weights
-    const long long* y; // may be null (forward only)
+    const long long* y; // may be null (forward only, or backward with dP_in)
+    const T* dP_in;     // (N,C) upstream gradient wrt P (tr_backward_mn) or null
     const T* class_w;   // (C) or null
     T* P;               // (N,C) or null
     long long* pred;    // (N) or null
@@ -178,30 +179,40 @@ __global__ void __launch_bounds__(TR_TPB) k_epi_mn(const EpiMnArgs<T> a) {
             for (int off = 16; off >= 1; off >>= 1) best = min(best, __shfl_xor_sync(TR_FULL, best, off));
             if (lane == 0) a.pred[n] = best;
         }
-        if (a.y == nullptr) continue;
+        if (a.y == nullptr && a.dP_in == nullptr) continue;
 
-        // second softmax (CrossEntropyLoss applied to probabilities, mn:364-366 / 448-450)
-        double Q[TR_JC];
-        double qs = 0.0;
-#pragma unroll
-        for (int jc = 0; jc < TR_JC; ++jc) {
-            const int c = lane + 32 * jc;
-            Q[jc] = c < C ? exp(P[jc] - pmax) : 0.0;
-            qs += Q[jc];
-        }
-        qs = warp_sum(qs);
-        const int yn = (int)a.y[n];
-        const double omega = a.class_w ? (double)a.class_w[yn] : 1.0;
         double dP[TR_JC], dot = 0.0;
+        if (a.dP_in) {
+            // vector-Jacobian product for an arbitrary upstream gradient wrt P (autograd of model, mn:180-187)
 #pragma unroll
-        for (int jc = 0; jc < TR_JC; ++jc) {
-            const int c = lane + 32 * jc;
-            dP[jc] = 0.0;
-            if (c < C) {
-                const double q = Q[jc] / qs;
-                if (c == yn) loss += -omega * ((P[jc] - pmax) - log(qs));
-                dP[jc] = omega * (q - (c == yn ? 1.0 : 0.0));
+            for (int jc = 0; jc < TR_JC; ++jc) {
+                const int c = lane + 32 * jc;
+                dP[jc] = c < C ? (double)a.dP_in[n * C + c] : 0.0;
                 dot += dP[jc] * P[jc];
+            }
+        } else {
+            // second softmax (CrossEntropyLoss applied to probabilities, mn:364-366 / 448-450)
+            double Q[TR_JC];
+            double qs = 0.0;
+#pragma unroll
+            for (int jc = 0; jc < TR_JC; ++jc) {
+                const int c = lane + 32 * jc;
+                Q[jc] = c < C ? exp(P[jc] - pmax) : 0.0;
+                qs += Q[jc];
+            }
+            qs = warp_sum(qs);
+            const int yn = (int)a.y[n];
+            const double omega = a.class_w ? (double)a.class_w[yn] : 1.0;
+#pragma unroll
+            for (int jc = 0; jc < TR_JC; ++jc) {
+                const int c = lane + 32 * jc;
+                dP[jc] = 0.0;
+                if (c < C) {
+                    const double q = Q[jc] / qs;
+                    if (c == yn) loss += -omega * ((P[jc] - pmax) - log(qs));
+                    dP[jc] = omega * (q - (c == yn ? 1.0 : 0.0));
+                    dot += dP[jc] * P[jc];
+                }
             }
         }
         dot = warp_sum(dot);

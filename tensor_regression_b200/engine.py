@@ -188,6 +188,19 @@ class Engine:
         self._count()
         return gradsum
 
+    def backward_mn(self, X, dP, theta, w, nn_mask, beta, thr, gradsum=None):
+        X = self._x(X)
+        N = X.shape[0]
+        if gradsum is None:
+            gradsum = torch.empty(self.n_gradsum, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(_lib.lib.tr_backward_mn(self._h, X.data_ptr(), self._vec(dP, N * self.n_classes, 'dP').data_ptr(), N,
+                                             self._vec(theta, self.P, 'theta').data_ptr(),
+                                             self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
+                                             gradsum.data_ptr(), self._stream()))
+        self._count()
+        return gradsum
+
     def fwd_grad_mn(self, X, y, class_w, theta, w, nn_mask, beta, thr, gradsum=None, P=None):
         X = self._x(X)
         N = X.shape[0]

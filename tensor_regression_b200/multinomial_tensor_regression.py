@@ -70,22 +70,45 @@ def non_neg_fn(B_cp, non_negative, softplus_kwargs=None):
             yield B_cp[ii]
 
 
+class _ModelFn(torch.autograd.Function):
+    """model with the reference's differentiability (gradients wrt the factors, not X):
+    forward = tr_forward_mn, backward = tr_backward_mn + tr_finish_grad (mn:180-187, 361)."""
+
+    @staticmethod
+    def forward(ctx, X, weights, nn_mask, beta, thr, eng, *Bcp):
+        theta = _flatten(Bcp, None, eng.dtype, eng.device)
+        ctx.save_for_backward(X, theta, weights)
+        ctx.meta = (nn_mask, beta, thr, eng, [tuple(b.shape) for b in Bcp])
+        P, _ = eng.forward_mn(X, theta, weights, nn_mask, beta, thr, want_pred=False)
+        return P
+
+    @staticmethod
+    def backward(ctx, dP):
+        X, theta, weights = ctx.saved_tensors
+        nn_mask, beta, thr, eng, shapes = ctx.meta
+        gs = eng.backward_mn(X, dP.contiguous().to(eng.dtype), theta, weights, nn_mask, beta, thr)
+        grad, _ = eng.finish(gs, 1.0, 0.0, theta, 0.0, nn_mask, beta, thr)
+        outs, off = [], 0
+        for shp in shapes:
+            n = shp[0] * shp[1]
+            outs.append(grad[off:off + n].reshape(shp))
+            off += n
+        return (None, None, None, None, None, None, *outs)
+
+
 def model(X, Bcp, weights, non_negative, softplus_kwargs=None):
     """mn:148-187 — softmax(inner(X, outer(softplus(Bcp)), n_modes=len(Bcp)-1), dim=1): (N, C)
-    probabilities.  Forward only (the fit loops use the fused forward+gradient entry point)."""
+    probabilities; the LAST factor is the (C, rank) class factor.  Differentiable with respect to the
+    factors like the reference's expression (through the CUDA backward kernels)."""
     if softplus_kwargs is None:
         softplus_kwargs = _DEFAULT_SOFTPLUS
     if not isinstance(X, torch.Tensor):
         raise TypeError('X must be a torch.Tensor')
-    if any(isinstance(b, torch.Tensor) and b.requires_grad for b in Bcp) and torch.is_grad_enabled():
-        Bcp = [b.detach() if isinstance(b, torch.Tensor) else b for b in Bcp]
     rank, C = Bcp[0].shape[1], Bcp[-1].shape[0]
     eng = _engine_for(X.shape[1:], rank, C, X.dtype, X.device)
     w = torch.as_tensor(weights).detach().to(device=X.device, dtype=X.dtype).contiguous()
-    theta = _flatten(Bcp, None, X.dtype, X.device)
-    P, _ = eng.forward_mn(X, theta, w, nn_mask_of(non_negative, len(Bcp)), float(softplus_kwargs['beta']),
-                          float(softplus_kwargs['threshold']), want_pred=False)
-    return P
+    return _ModelFn.apply(X, w, nn_mask_of(non_negative, len(Bcp)), float(softplus_kwargs['beta']),
+                          float(softplus_kwargs['threshold']), eng, *Bcp)
 
 
 def L2_penalty(B_cp):
@@ -102,13 +125,22 @@ def L2_penalty(B_cp):
 
 class CP_logistic_regression():
     def __init__(self, X, y, rank=5, non_negative=False, weights=None, Bcp_init=None, Bcp_init_scale=1,
-                 device='cuda', softplus_kwargs=None, *, shard_group=None, n_classes=None):
+                 device='cuda', softplus_kwargs=None, *, shard_group=None, n_classes=None, out_of_core=False,
+                 chunk_samples=None):
         """mn:212-286.  X is stored as float32, y as int64 (mn:255-256).  With ``shard_group`` X / y
         are this rank's slice of the sample axis; ``n_classes`` may then be given explicitly
-        (otherwise the number of distinct labels is all-reduced as a max of label+1)."""
+        (otherwise the number of distinct labels is all-reduced as a max of label+1).
+        ``out_of_core=True`` (keyword-only extension): X stays in host memory (numpy / memmap / CPU
+        tensor / anything with ``.shape`` and ``[lo:hi]``) and is streamed to the device in chunks of
+        ``chunk_samples`` on every pass; gradients are exact full-batch sums."""
         self.device = device
         dev = self._torch_device()
-        self.X = torch.as_tensor(X, dtype=torch.float32).to(dev)
+        self._out_of_core = bool(out_of_core)
+        self._chunk_samples = chunk_samples
+        if self._out_of_core:
+            self.X = X
+        else:
+            self.X = torch.as_tensor(X, dtype=torch.float32).to(dev)
         self.y = torch.as_tensor(y, dtype=torch.long).to(dev)
         self._shard_group = shard_group
         self._eng = None
@@ -125,10 +157,11 @@ class CP_logistic_regression():
 
         self.rank = rank
 
+        ndim = len(self.X.shape)
         if non_negative == True:  # noqa: E712  (mn:271-276)
-            self.non_negative = [True] * (self.X.ndim)
+            self.non_negative = [True] * ndim
         elif non_negative == False:  # noqa: E712
-            self.non_negative = [False] * (self.X.ndim)
+            self.non_negative = [False] * ndim
         else:
             self.non_negative = non_negative
 
@@ -194,8 +227,10 @@ class CP_logistic_regression():
         st = dict(self.__dict__)
         st['_eng'] = None
         st['_shard_group'] = None
-        for k in ('theta', 'weights', 'X', 'y'):
+        for k in ('theta', 'weights', 'y'):
             st[k] = st[k].detach().cpu()
+        if isinstance(st['X'], torch.Tensor):
+            st['X'] = st['X'].detach().cpu()
         st.pop('Bcp')
         return st
 
@@ -203,13 +238,30 @@ class CP_logistic_regression():
         theta = st.pop('theta')
         self.__dict__.update(st)
         dev = self._torch_device()
-        self.weights, self.X, self.y = self.weights.to(dev), self.X.to(dev), self.y.to(dev)
+        self.weights, self.y = self.weights.to(dev), self.y.to(dev)
+        if not self.__dict__.get('_out_of_core', False):
+            self.X = self.X.to(dev)
         want = self._dims + [self.n_classes]
         sizes, offs = _engine.factor_offsets(self._dims, self.rank, self.n_classes)
         self._set_theta([theta[offs[m]:offs[m + 1]].view(want[m], self.rank) for m in range(len(want))])
 
     def return_self(self):
         return self.Bcp
+
+    def _fwd_grad(self, eng, cw, beta, thr, gs, gs_chunk=None, streamer=None):
+        """Unnormalised local sums of one closure evaluation over all of this rank's samples."""
+        if streamer is None:
+            return eng.fwd_grad_mn(self.X, self.y, cw, self.theta, self.weights, self._mask(), beta, thr, gradsum=gs)
+        gs.zero_()
+        for lo, hi, xd in streamer.chunks():
+            eng.fwd_grad_mn(xd, self.y[lo:hi], cw, self.theta, self.weights, self._mask(), beta, thr, gradsum=gs_chunk)
+            gs.add_(gs_chunk)
+        return gs
+
+    def _streamer(self):
+        if not self._out_of_core:
+            return None
+        return _engine.HostStreamer(self.X, torch.float32, self._torch_device(), chunk_samples=self._chunk_samples)
 
     def _class_weights(self, weights):
         # same call as the reference (mn:365,449): None raises
@@ -231,13 +283,15 @@ class CP_logistic_regression():
         eng = self._engine()
         beta, thr = self._sp()
         sharder = self._sharder()
-        W = sharder.total(cw[self.y].sum().item(), self.X.device)
+        W = sharder.total(cw[self.y].sum().item(), self.theta.device)
 
         optimizer = _lbfgs.LBFGS(eng, self.theta, **LBFGS_kwargs)    # torch.optim.LBFGS's algorithm, device-resident
         gs = torch.empty(eng.n_gradsum, dtype=torch.float64, device=self.theta.device)
+        gs_chunk = torch.empty_like(gs)
+        streamer = self._streamer()
 
         def closure(grad_out, loss_out):
-            eng.fwd_grad_mn(self.X, self.y, cw, self.theta, self.weights, self._mask(), beta, thr, gradsum=gs)
+            self._fwd_grad(eng, cw, beta, thr, gs, gs_chunk, streamer)
             sharder.sum_(gs)
             eng.finish(gs, 1.0 / W, 1.0 / W, self.theta, lambda_L2, self._mask(), beta, thr, grad=grad_out,
                        loss=loss_out)
@@ -245,8 +299,11 @@ class CP_logistic_regression():
         def logged_loss():
             # extra forward, CE without the penalty (mn:371-372): one pass over X, then the
             # reference's own loss expression on the (N, C) probabilities
-            P, _ = eng.forward_mn(self.X, self.theta, self.weights, self._mask(), beta, thr, want_pred=False)
-            s = torch.nn.functional.cross_entropy(P.double(), self.y, weight=cw.double(), reduction='sum').reshape(1)
+            if streamer is not None:
+                s = self._fwd_grad(eng, cw, beta, thr, gs, gs_chunk, streamer)[-1].reshape(1).clone()
+            else:
+                P, _ = eng.forward_mn(self.X, self.theta, self.weights, self._mask(), beta, thr, want_pred=False)
+                s = torch.nn.functional.cross_entropy(P.double(), self.y, weight=cw.double(), reduction='sum').reshape(1)
             return (sharder.sum_(s) / W).item()
 
         convergence_reached = False
@@ -285,17 +342,19 @@ class CP_logistic_regression():
         eng = self._engine()
         beta, thr = self._sp()
         sharder = self._sharder()
-        W = sharder.total(cw[self.y].sum().item(), self.X.device)
+        W = sharder.total(cw[self.y].sum().item(), self.theta.device)
         m = torch.zeros_like(self.theta)
         v = torch.zeros_like(self.theta)
         vmax = torch.zeros_like(self.theta) if hyper['amsgrad'] else None
         gs = torch.empty(eng.n_gradsum, dtype=torch.float64, device=self.theta.device)
         grad = torch.empty_like(self.theta)
         loss = torch.empty(2, dtype=torch.float64, device=self.theta.device)
+        gs_chunk = torch.empty_like(gs)
+        streamer = self._streamer()
 
         convergence_reached = False
         for ii in range(max_iter):
-            eng.fwd_grad_mn(self.X, self.y, cw, self.theta, self.weights, self._mask(), beta, thr, gradsum=gs)
+            self._fwd_grad(eng, cw, beta, thr, gs, gs_chunk, streamer)
             sharder.sum_(gs)
             eng.finish(gs, 1.0 / W, 1.0 / W, self.theta, lambda_L2, self._mask(), beta, thr, grad=grad, loss=loss)
             eng.adam_step(self.theta, grad, m, v, vmax, ii + 1, lr=hyper['lr'], betas=hyper['betas'],
@@ -361,7 +420,7 @@ class CP_logistic_regression():
     def get_params(self):
         """mn:610-624 (the reference reads a ``self.bias`` that the multinomial model never
         creates, mn:619; the key is kept with value None so the dict round-trips)."""
-        return {'X': self.X.detach().cpu().numpy(),
+        return {'X': self.X.detach().cpu().numpy() if isinstance(self.X, torch.Tensor) else np.asarray(self.X),
                 'y': self.y.detach().cpu().numpy(),
                 'weights': self.weights.detach().cpu().numpy(),
                 'Bcp': self.detach_Bcp(),

@@ -583,3 +583,58 @@ def test_cfg2_full_size_properties():
     eng.set_option('fused', -1)
     del X
     torch.cuda.empty_cache()
+
+
+def test_mn_model_autograd_matches_reference_autograd():
+    from tensor_regression_b200 import multinomial_tensor_regression as MTR
+    N, dims, C, R = 48, (5, 4, 6), 4, 3
+    X, y, _ = O.synth_mn(N, dims, R, C, 31)
+    X = X.double()
+    nn = [False, True, False, False]
+    B0 = [b.double() for b in O.init_mn(list(dims) + [C], R, nn, scale=0.6)]
+    w = torch.tensor([0.5, 1.0, 2.0], dtype=torch.float64)
+    cw = torch.tensor([1.0, 0.5, 2.0, 1.5], dtype=torch.float64)
+    Bd = [dev(b).requires_grad_(True) for b in B0]
+    P = MTR.model(dev(X), Bd, dev(w), nn)
+    loss = torch.nn.CrossEntropyLoss(weight=dev(cw))(P, dev(y)) + 0.01 * MTR.L2_penalty(Bd)
+    loss.backward()
+    ref = O.mn_loss_grad(X, y, B0, w, nn, cw.numpy(), 0.01)
+    assert rel(P, ref['P']) < 1e-12
+    assert abs(loss.item() - ref['loss'].item()) < 1e-12
+    for i in range(4):
+        assert rel(Bd[i].grad, ref['grads'][i]) < 1e-10
+
+
+def test_mn_out_of_core_equals_resident():
+    from tensor_regression_b200 import multinomial_tensor_regression as MTR
+    N, dims, C, R = 333, (6, 5, 8), 3, 4
+    X, y, _ = O.synth_mn(N, dims, R, C, 32)
+    B0 = O.init_mn(list(dims) + [C], R, [False] * 4, scale=0.5)
+    cw = np.array([1.0, 2.0, 0.5], dtype=np.float32)
+    a = MTR.CP_logistic_regression(X, y, rank=R, Bcp_init=[b.clone() for b in B0], device=DEV)
+    a.fit_Adam(lambda_L2=0.01, max_iter=8, tol=1e-50, patience=100, weights=cw, Adam_kwargs=ADAM)
+    b = MTR.CP_logistic_regression(X.numpy(), y.numpy(), rank=R, Bcp_init=[b.clone() for b in B0], device=DEV,
+                                   out_of_core=True, chunk_samples=50)
+    assert not isinstance(b.X, torch.Tensor)
+    b.fit_Adam(lambda_L2=0.01, max_iter=8, tol=1e-50, patience=100, weights=cw, Adam_kwargs=ADAM)
+    assert rel(b.loss_running, a.loss_running) < 1e-6
+    for i in range(4):
+        assert rel(b.Bcp[i], a.Bcp[i]) < 1e-5
+    pa, _ = a.predict()
+    pb, _ = b.predict()
+    assert rel(pb, pa) < 1e-5
+    c = STR_out_of_core_check()
+    assert c < 1e-6
+
+
+def STR_out_of_core_check():
+    """standard model: out_of_core fit_Adam (streamed from a numpy array) == resident fit_Adam."""
+    from tensor_regression_b200 import standard_tensor_regression as STR
+    X, y, _ = O.synth_std(257, (8, 6, 4), 3, 33)
+    B0 = O.init_std((8, 6, 4), 3, [False] * 4)
+    a = STR.CP_linear_regression(X.shape, rank=3, Bcp_init=[b.clone() for b in B0], device=DEV)
+    a.fit_Adam(X.to(DEV), y.to(DEV), max_iter=6, tol=1e-50, patience=100, Adam_kwargs=ADAM)
+    b = STR.CP_linear_regression(X.shape, rank=3, Bcp_init=[b.clone() for b in B0], device=DEV)
+    b.fit_Adam(X.numpy(), y.numpy(), max_iter=6, tol=1e-50, patience=100, Adam_kwargs=ADAM, out_of_core=True,
+               chunk_samples=40)
+    return rel(b.loss_running, a.loss_running)
