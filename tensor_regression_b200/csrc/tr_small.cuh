@@ -327,13 +327,16 @@ __global__ void __launch_bounds__(TR_TPB) k_mttkrp(const MtArgs a) {
         double acc[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[q] = 0.0;
-        for (long long s = threadIdx.x; s < S; s += TR_TPB) {
-            long long rem = s, lin = (long long)im * stride[m];
+        for (unsigned s = threadIdx.x; s < (unsigned)S; s += TR_TPB) {     // D < 2^31: 32-bit index arithmetic
+            unsigned rem = s;
+            long long lin = (long long)im * stride[m];
             int idx[TR_MAX_MODES];
             for (int j = k - 1; j >= 0; --j) {
                 if (j == m) continue;
-                idx[j] = (int)(rem % a.geo.dims[j]);
-                rem /= a.geo.dims[j];
+                const unsigned dj = (unsigned)a.geo.dims[j];
+                const unsigned q = rem / dj;
+                idx[j] = (int)(rem - q * dj);
+                rem = q;
                 lin += idx[j] * stride[j];
             }
             const double g0 = a.per_rank ? 0.0 : a.G[lin];

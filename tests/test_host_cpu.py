@@ -172,3 +172,24 @@ def test_sharded_sum_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_create_rejects_unsupported_geometry_loudly():
+    """Limits of the kernels are explicit errors with a message, never a silent fallback."""
+    from tensor_regression_b200 import _lib
+    h = ctypes.c_void_p()
+
+    def create(dtype, dims, R, C):
+        arr = (ctypes.c_int64 * len(dims))(*dims)
+        rc = _lib.lib.tr_create(ctypes.byref(h), dtype, len(dims), arr, R, C, 0)
+        return rc, _lib.lib.tr_last_error(None).decode()
+
+    rc, msg = create(0, [2] * 9, 2, 0)
+    assert rc == 3 and 'feature modes' in msg
+    rc, msg = create(0, [4, 4], 2, 129)
+    assert rc == 3 and 'n_classes' in msg
+    rc, msg = create(0, [4, 4], 17, 3)
+    assert rc == 3 and 'multinomial rank' in msg
+    rc, msg = create(7, [4, 4], 2, 0)
+    assert rc == 1 and 'dtype' in msg
+    assert _lib.lib.tr_set_option(None, b'fused', 0) != 0
