@@ -152,14 +152,19 @@ int tr_profile_read(tr_handle* h, double* out6);
 
 /* Options.  "fused": -1 = auto (default; env TR_B200_FUSED overrides), 0 = always the two-pass
  * kernels, 1 = always the single-pass cluster kernel of tr_fwd_grad_std (error if the geometry
- * does not fit a cluster's shared memory). */
+ * does not fit a cluster's shared memory).
+ * "flow": 0 = never (default), 1 = run tr_fwd_grad_std / tr_fwd_grad_mn as ONE cooperative
+ * dataflow kernel whose gradient warps re-read X from L2 a bounded window behind the forward warps
+ * (experimental: correct, but measured slower than the two-pass kernels; error if the
+ * geometry / alignment is not eligible); "flow_window_mb": size of that window in MiB (default 32). */
 int tr_set_option(tr_handle* h, const char* name, int64_t value);
 
 /* How the last tr_fwd_grad_* / tr_forward_* call was executed (host ints):
  * info[0]=kernel launches, [1]=forward grid, [2]=gradient grid, [3]=tiles per sample,
  * [4]=sample groups (forward), [5]=sample groups (gradient), [6]=channels RK, [7]=vector width.
  * After a single-pass launch: [1]=grid, [2]=cluster size, [3]=stages, [4]=clusters, [5]=chunks,
- * [7]= -(vector width). */
+ * [7]= -(vector width).  After a dataflow launch: [1]=grid, [2]=0, [3]=window in samples per group,
+ * [4]=sample groups, [5]=chunks, [6]=channels, [7]= -(vector width). */
 int tr_last_launch_info(tr_handle* h, int64_t* info8);
 
 #ifdef __cplusplus

@@ -95,6 +95,11 @@ struct tr_handle {
     int fused_piece = 32768;            // bytes per bulk-copy instruction (option "fused_piece")
     int last_fused = 0;
     std::map<const void*, int> occ_clusters;
+    int flow_mode = 0;                  // dataflow kernel (tr_flow.cuh), experimental: 0 never (default), 1 always (error when
+                                        // not eligible); -1 is accepted and currently means 0 (it measured slower)
+    long long flow_window_mb = 32;      // bytes of X the forward warps may lead the gradient warps by (option "flow_window_mb")
+    Buf flow_ring, flow_sync;
+    int flow_debug = 0;
 };
 
 namespace {
@@ -432,6 +437,152 @@ int run_fused_std(tr_handle* h, const T* X, const T* y, long long N, const T* th
     return TR_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// single-launch dataflow path (tr_flow.cuh): plan + launch
+// ---------------------------------------------------------------------------------------------
+struct FlowPlan {
+    int ok;             // 1 when the geometry is eligible
+    int RKs, tile, WT, Gn, grid, lag, ring, nchunk;
+    long long Dpad, spc;
+    size_t smem;
+};
+
+template <typename T>
+int plan_flow(tr_handle* h, long long N, int rk_needed, const void* X, FlowPlan* fp, const KEntry<T>** ent) {
+    fp->ok = 0;
+    const Geo& g = h->geo;
+    if (!vec_ok(X, g.D, sizeof(T)) || N < 1) return TR_OK;
+    const KEntry<T>* e = pick_entry<T>(rk_needed);
+    if (!e || !e->flow_vec) return TR_OK;
+    *ent = e;
+    fp->RKs = e->RK;
+    fp->tile = 32 * e->E * VN<T>::v;
+    fp->WT = (int)((g.D + fp->tile - 1) / fp->tile);
+    fp->Dpad = (long long)fp->WT * fp->tile;
+    // factor rows (T) | class factor + rank weights (double) | accumulator parking area of the gradient warps
+    fp->smem = (((size_t)(g.pfeat + g.R) * sizeof(T) + 15) / 16) * 16 +
+               (((size_t)(g.C * g.R + g.R) * sizeof(double) + 15) / 16) * 16 +
+               (size_t)TR_FLOW_PAIRS * e->E * VN<T>::v * e->RK * 32 * sizeof(T);
+    if (fp->smem > 200 * 1024) return TR_OK;
+    int occ = 0, rc;
+    if ((rc = occupancy(h, e->flow_vec, fp->smem, &occ))) return rc;
+    const long long pairs = (long long)h->sms * occ * TR_FLOW_PAIRS;
+    if (fp->WT > pairs) return TR_OK;                       // every item needs its own resident warp pair
+    long long Gn = pairs / fp->WT;
+    if (Gn > N) Gn = N;
+    fp->Gn = (int)Gn;
+    fp->grid = (int)(((long long)fp->WT * Gn + TR_FLOW_PAIRS - 1) / TR_FLOW_PAIRS);
+    const long long Sg = (N + Gn - 1) / Gn;
+    if (Sg >= (1LL << 30)) return TR_OK;
+    const int umin = 2 * (e->Uf + e->Ug);
+    const double per = (double)Gn * (double)g.D * sizeof(T);
+    long long lag = (long long)((double)h->flow_window_mb * 1048576.0 / per);
+    lag = std::min<long long>(lag, Sg);                      // no point in a window longer than the sample list
+    lag = std::max<long long>(lag, umin);
+    fp->lag = (int)lag;
+    fp->ring = (int)(((lag + e->Uf + e->Uf - 1) / e->Uf) * e->Uf);
+    const long long target = sizeof(T) == 4 ? 2048 : (1LL << 40);
+    long long nchunk = std::max<long long>(1, (Sg + target - 1) / target);
+    const size_t slot_bytes = (size_t)fp->RKs * (size_t)fp->Dpad * sizeof(T);
+    while (nchunk > 1 && (size_t)nchunk * Gn * slot_bytes > ((size_t)1 << 30)) --nchunk;
+    fp->nchunk = (int)nchunk;
+    fp->spc = std::max<long long>(1, (Sg + nchunk - 1) / nchunk);
+    fp->ok = 1;
+    return TR_OK;
+}
+
+// forward + epilogue + gradient in one launch, then the shared tail (loss sums, class-factor gradient,
+// split-N reduction, all-mode MTTKRP).  Fills gradsum completely.
+template <typename T>
+int run_flow(tr_handle* h, const T* X, const void* y, const T* class_w, long long N, const T* theta, const T* w,
+             uint32_t nn_mask, double beta, double thr, const FlowPlan& fp, const KEntry<T>* e, double* gradsum,
+             T* out /* yhat (N) or P (N,C), may be null */, cudaStream_t st) {
+    const Geo& g = h->geo;
+    int rc;
+    const bool mn = g.C > 0;
+    if ((rc = ensure(h, h->FtT, (size_t)g.pf * sizeof(T)))) return rc;
+    if ((rc = ensure(h, h->Ft64, (size_t)g.pf * sizeof(double)))) return rc;
+    const size_t ring_bytes = (size_t)fp.Gn * fp.ring * fp.WT * fp.RKs * (sizeof(T) / 4) * sizeof(unsigned long long);
+    if ((rc = ensure(h, h->flow_ring, ring_bytes))) return rc;
+    if ((rc = ensure(h, h->flow_sync, (size_t)N * sizeof(unsigned)))) return rc;
+    if ((rc = ensure(h, h->V, (size_t)N * fp.RKs * sizeof(T)))) return rc;
+    if (mn) {
+        if ((rc = ensure(h, h->u_ws, (size_t)N * g.R * sizeof(T)))) return rc;
+        if ((rc = ensure(h, h->dZ_ws, (size_t)N * g.C * sizeof(T)))) return rc;
+        if ((rc = ensure(h, h->dfc_part, (size_t)h->sms * 2 * g.C * g.R * sizeof(double)))) return rc;
+    }
+    if ((rc = ensure(h, h->Gpart, (size_t)fp.nchunk * fp.Gn * fp.RKs * fp.Dpad * sizeof(T)))) return rc;
+    if ((rc = ensure(h, h->Gred, (size_t)fp.RKs * g.D * sizeof(double)))) return rc;
+    const int nwarps = fp.grid * TR_WPB;
+    if ((rc = ensure(h, h->epi_part, std::max((size_t)nwarps, (size_t)h->sms * 8) * 2 * sizeof(double)))) return rc;
+
+    k_prep<T><<<std::max(1, std::min(64, (g.pf + 255) / 256)), 256, 0, st>>>(theta, g, nn_mask, beta, thr,
+                                                                           (T*)h->FtT.p, (double*)h->Ft64.p);
+    TR_LAUNCH_CHECK(h);
+    TR_CUDA(h, cudaMemsetAsync(h->flow_sync.p, 0, (size_t)N * sizeof(unsigned), st));
+    TR_CUDA(h, cudaMemsetAsync(h->flow_ring.p, 0, ring_bytes, st));                     // tag 0 = never written
+    TR_CUDA(h, cudaMemsetAsync(h->V.p, 0xff, (size_t)N * fp.RKs * sizeof(T), st));      // "not written yet" pattern
+
+    FlowArgs<T> fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.X = X; fa.N = N; fa.FtT = (const T*)h->FtT.p; fa.w = w; fa.geo = g; fa.mode = mn ? 1 : 0;
+    fa.WT = fp.WT; fa.Gn = fp.Gn; fa.partial = (unsigned long long*)h->flow_ring.p; fa.ring = fp.ring;
+    fa.cnt = (unsigned*)h->flow_sync.p; fa.lag = fp.lag;
+    fa.V = (T*)h->V.p; fa.Gpart = (T*)h->Gpart.p; fa.Dpad = fp.Dpad; fa.nchunk = fp.nchunk; fa.spc = fp.spc;
+    fa.losspart = (double*)h->epi_part.p;
+    fa.dbg = h->flow_debug;
+    if (!mn) {
+        fa.es.partial = nullptr; fa.es.WT = fp.WT; fa.es.N = N; fa.es.theta = theta; fa.es.bias_off = g.pf;
+        fa.es.y = (const T*)y; fa.es.yhat = out; fa.es.V = (T*)h->V.p; fa.es.part = nullptr;
+    } else {
+        fa.em.partial = nullptr; fa.em.WT = fp.WT; fa.em.RKs = fp.RKs; fa.em.N = N; fa.em.R = g.R; fa.em.C = g.C;
+        fa.em.w = w; fa.em.y = (const long long*)y; fa.em.dP_in = nullptr; fa.em.class_w = class_w;
+        fa.em.P = out; fa.em.pred = nullptr; fa.em.V = (T*)h->V.p; fa.em.u_ws = (T*)h->u_ws.p;
+        fa.em.dZ_ws = (T*)h->dZ_ws.p; fa.em.part = nullptr;
+    }
+    fa.em.FC = (const double*)h->Ft64.p + g.pfeat;           // read by the kernel prologue only when C > 0
+    if (h->prof) { rc = prof_fold(h, false); if (rc) return rc; TR_CUDA(h, cudaEventRecord(h->ev[4], st)); }
+    {
+        // blocks wait on one another: a cooperative launch guarantees that the whole grid is resident
+        void* kargs[] = {(void*)&fa};
+        TR_CUDA(h, cudaLaunchCooperativeKernel((const void*)e->flow_vec, dim3((unsigned)fp.grid), dim3(TR_TPB), kargs,
+                                               fp.smem, st));
+    }
+    TR_LAUNCH_CHECK(h);
+    if (h->prof) { TR_CUDA(h, cudaEventRecord(h->ev[5], st)); h->ev_set[2] = true; }
+
+    if (!mn) {
+        k_colsum<<<2, 128, 0, st>>>((const double*)h->epi_part.p, nwarps, 2, gradsum + g.pf);
+        TR_LAUNCH_CHECK(h);
+    } else {
+        k_colsum<<<1, 128, 0, st>>>((const double*)h->epi_part.p, nwarps, 2, gradsum + g.pf);
+        TR_LAUNCH_CHECK(h);
+        const int dgrid = (int)std::min<long long>((N + 63) / 64, (long long)h->sms * 2);
+        k_dfc<T><<<dgrid, TR_TPB, 0, st>>>((const T*)h->dZ_ws.p, (const T*)h->u_ws.p, w, N, g.C, g.R,
+                                           (double*)h->dfc_part.p);
+        TR_LAUNCH_CHECK(h);
+        k_colsum<<<g.C * g.R, 128, 0, st>>>((const double*)h->dfc_part.p, dgrid, g.C * g.R, gradsum + g.pfeat);
+        TR_LAUNCH_CHECK(h);
+    }
+    const long long tot = (long long)fp.RKs * g.D;
+    const int rgrid = (int)std::min<long long>((tot + 255) / 256, (long long)h->sms * 8);
+    k_reduce_G<T><<<rgrid, 256, 0, st>>>((const T*)h->Gpart.p, fp.nchunk * fp.Gn, fp.RKs, g.D, fp.Dpad,
+                                         (double*)h->Gred.p);
+    TR_LAUNCH_CHECK(h);
+    MtArgs ma;
+    ma.G = (const double*)h->Gred.p; ma.Ft64 = (const double*)h->Ft64.p; ma.w = w;
+    ma.w_is_f64 = sizeof(T) == 8; ma.per_rank = mn ? 1 : 0; ma.geo = g; ma.gradsum = gradsum;
+    int rows = 0;
+    for (int m = 0; m < g.k; ++m) rows += g.dims[m];
+    k_mttkrp<<<rows, TR_TPB, 0, st>>>(ma);
+    TR_LAUNCH_CHECK(h);
+    h->info[0] = h->launches; h->info[1] = fp.grid; h->info[2] = 0; h->info[3] = fp.lag;
+    h->info[4] = fp.Gn; h->info[5] = fp.nchunk; h->info[6] = fp.RKs; h->info[7] = -(16 / (int)sizeof(T));
+    h->last_fused = 2;
+    return TR_OK;
+}
+
 void set_info(tr_handle* h, const Plan& pl) {
     h->info[0] = h->launches; h->info[1] = pl.grid_f; h->info[2] = pl.grid_g; h->info[3] = pl.WT;
     h->info[4] = pl.Gn_f; h->info[5] = pl.Gn_g; h->info[6] = pl.RKs; h->info[7] = pl.vec ? (int)(16 / h->elt) : 1;
@@ -476,6 +627,17 @@ int fwd_grad_std_t(tr_handle* h, const void* X, const void* y, long long N, cons
                                     fp, gradsum, (T*)yhat, st);
         }
     }
+    if (!backward_only && h->flow_mode == 1) {
+        FlowPlan fl; const KEntry<T>* fe = nullptr;
+        if ((rc = plan_flow<T>(h, N, 1, X, &fl, &fe))) return rc;
+        if (h->flow_mode == 1 && !fl.ok)
+            return fail(h, TR_ERR_UNSUPPORTED, "flow=1 requested but this geometry / alignment is not eligible for the dataflow kernel");
+        if (fl.ok) {
+            h->launches = 0;
+            return run_flow<T>(h, (const T*)X, y, (const T*)nullptr, N, (const T*)theta, (const T*)w, nn_mask, beta, thr,
+                               fl, fe, gradsum, (T*)yhat, st);
+        }
+    }
     if ((rc = make_plan<T>(h, N, 1, vec_ok(X, g.D, sizeof(T)), &pl, &e))) return rc;
     if ((rc = reserve_for<T>(h, N, pl))) return rc;
     h->launches = 0;
@@ -513,6 +675,18 @@ int mn_t(tr_handle* h, const void* X, const long long* y, const void* class_w, l
          cudaStream_t st, const void* dP_in = nullptr) {
     Plan pl; const KEntry<T>* e; int rc;
     const Geo& g = h->geo;
+    h->last_fused = 0;
+    if (y != nullptr && dP_in == nullptr && pred == nullptr && h->flow_mode == 1) {
+        FlowPlan fl; const KEntry<T>* fe = nullptr;
+        if ((rc = plan_flow<T>(h, N, g.R, X, &fl, &fe))) return rc;
+        if (h->flow_mode == 1 && !fl.ok)
+            return fail(h, TR_ERR_UNSUPPORTED, "flow=1 requested but this geometry / alignment is not eligible for the dataflow kernel");
+        if (fl.ok) {
+            h->launches = 0;
+            return run_flow<T>(h, (const T*)X, y, (const T*)class_w, N, (const T*)theta, (const T*)w, nn_mask, beta, thr,
+                               fl, fe, gradsum, (T*)P, st);
+        }
+    }
     if ((rc = make_plan<T>(h, N, g.R, vec_ok(X, g.D, sizeof(T)), &pl, &e))) return rc;
     if ((rc = reserve_for<T>(h, N, pl))) return rc;
     h->launches = 0;
@@ -612,7 +786,8 @@ int tr_destroy(tr_handle* h) {
     if (!h) return TR_OK;
     DeviceGuard dg(h->device);
     cudaDeviceSynchronize();
-    Buf* bufs[] = {&h->FtT, &h->Ft64, &h->partial, &h->V, &h->u_ws, &h->dZ_ws, &h->Gpart, &h->Gred, &h->epi_part, &h->dfc_part};
+    Buf* bufs[] = {&h->FtT, &h->Ft64, &h->partial, &h->V, &h->u_ws, &h->dZ_ws, &h->Gpart, &h->Gred, &h->epi_part, &h->dfc_part,
+                   &h->flow_ring, &h->flow_sync};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
@@ -811,6 +986,17 @@ int tr_set_option(tr_handle* h, const char* name, int64_t value) {
     if (strcmp(name, "fused") == 0) {
         if (value < -1 || value > 1) return fail(h, TR_ERR_INVALID, "option fused: -1 (auto), 0 (two-pass), 1 (single-pass)");
         h->fused_mode = (int)value;
+        return TR_OK;
+    }
+    if (strcmp(name, "flow") == 0) {
+        if (value < -1 || value > 1) return fail(h, TR_ERR_INVALID, "option flow: 0 (never, default), 1 (always the experimental dataflow kernel), -1 (auto = 0 for now)");
+        h->flow_mode = (int)value;
+        return TR_OK;
+    }
+    if (strcmp(name, "flow_debug") == 0) { h->flow_debug = (int)value; return TR_OK; }
+    if (strcmp(name, "flow_window_mb") == 0) {
+        if (value < 1 || value > 4096) return fail(h, TR_ERR_INVALID, "flow_window_mb must be in 1..4096");
+        h->flow_window_mb = value;
         return TR_OK;
     }
     if (strcmp(name, "fused_pace") == 0) { h->fused_pace = (int)value; return TR_OK; }

@@ -1,6 +1,7 @@
 // tr_dispatch.h — table of streaming-kernel instantiations shared by tr_api.cu and tr_stream.cu.
 #pragma once
 #include "tr_kernels.cuh"
+#include "tr_flow.cuh"
 
 template <typename T> struct VN;
 template <> struct VN<float> { static constexpr int v = 4; };
@@ -13,11 +14,13 @@ struct KEntry {
     void (*fwd_sc)(FwdArgs<T>);
     void (*grad_vec)(GradArgs<T>);
     void (*grad_sc)(GradArgs<T>);
+    void (*flow_vec)(FlowArgs<T>);        // single-launch dataflow kernel (tr_flow.cuh), 16-byte loads only
 };
 
 #define TR_ENTRY(T, RK, E, UF, UG)                                                                  \
     { RK, E, UF, UG, k_fwd<T, RK, E, UF, VN<T>::v>, k_fwd<T, RK, E * VN<T>::v, UF, 1>,              \
-      k_grad<T, RK, E, UG, VN<T>::v>, k_grad<T, RK, E * VN<T>::v, UG, 1> }
+      k_grad<T, RK, E, UG, VN<T>::v>, k_grad<T, RK, E * VN<T>::v, UG, 1>,                           \
+      k_flow<T, RK, E, UF, UG, VN<T>::v> }
 
 const KEntry<float>* tr_entries_f32_0(int* n);
 const KEntry<float>* tr_entries_f32_1(int* n);

@@ -37,214 +37,7 @@ __global__ void k_reduce_G(const T* __restrict__ Gpart, int slots, int RK, long 
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Per-sample epilogues (one warp per sample)
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-struct EpiStdArgs {
-    const T* partial; int WT; long long N;
-    const T* theta; int bias_off;
-    const T* y;        // may be null (forward only)
-    T* yhat;           // may be null
-    T* V;              // residual out (N) or null
-    double* part;      // (gridDim.x, 2): sum res, sum res^2
-};
-
-template <typename T>
-__global__ void __launch_bounds__(TR_TPB) k_epi_std(const EpiStdArgs<T> a) {
-    __shared__ double sbuf[32];
-    const int lane = threadIdx.x & 31;
-    const long long warp_global = (long long)blockIdx.x * TR_WPB + (threadIdx.x >> 5);
-    const long long wtot = (long long)gridDim.x * TR_WPB;
-    const double bias = (double)a.theta[a.bias_off];
-    double l2 = 0.0, l1 = 0.0;
-    for (long long n = warp_global; n < a.N; n += wtot) {
-        const T* p = a.partial + n * a.WT;
-        double s = 0.0;
-#pragma unroll 4
-        for (int t = lane; t < a.WT; t += 32) s += (double)__ldg(p + t);
-        s = warp_sum(s);
-        if (lane == 0) {
-            const T yh = (T)(s + bias);                // yhat in the model dtype, as the reference returns it
-            if (a.yhat) a.yhat[n] = yh;
-            if (a.y) {
-                const double res = (double)yh - (double)a.y[n];
-                if (a.V) a.V[n] = (T)res;
-                l2 += res * res;
-                l1 += res;
-            }
-        }
-    }
-    const double t2 = block_sum(l2, sbuf);
-    const double t1 = block_sum(l1, sbuf);
-    if (threadIdx.x == 0 && a.part) { a.part[blockIdx.x * 2 + 0] = t1; a.part[blockIdx.x * 2 + 1] = t2; }
-}
-
-template <typename T>
-struct EpiMnArgs {
-    const T* partial; int WT; int RKs; long long N;
-    int R, C;
-    const double* FC;   // class factor (C,R), softplus-ed, double
-    const T* w;         // rank weights
-    const long long* y; // may be null (forward only, or backward with dP_in)
-    const T* dP_in;     // (N,C) upstream gradient wrt P (tr_backward_mn) or null
-    const T* class_w;   // (C) or null
-    T* P;               // (N,C) or null
-    long long* pred;    // (N) or null
-    T* V;               // (N,RKs) or null
-    T* u_ws;            // (N,R) or null
-    T* dZ_ws;           // (N,C) or null
-    double* part;       // (gridDim.x): sum -omega log Q
-};
-
-#define TR_JC (TR_MAX_CLASSES / 32)
-#define TR_MAX_RANK_MN 16
-
-template <typename T>
-__global__ void __launch_bounds__(TR_TPB) k_epi_mn(const EpiMnArgs<T> a) {
-    extern __shared__ __align__(16) unsigned char tr_smem[];
-    double* sFC = reinterpret_cast<double*>(tr_smem);      // C*R
-    double* sW = sFC + a.C * a.R;                            // R
-    __shared__ double sbuf[32];
-    for (int i = threadIdx.x; i < a.C * a.R + a.R; i += TR_TPB)
-        sFC[i] = i < a.C * a.R ? a.FC[i] : (double)a.w[i - a.C * a.R];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const long long warp_global = (long long)blockIdx.x * TR_WPB + (threadIdx.x >> 5);
-    const long long wtot = (long long)gridDim.x * TR_WPB;
-    const int R = a.R, C = a.C;
-    double loss = 0.0;
-    for (long long n = warp_global; n < a.N; n += wtot) {
-        // u[r] = sum over warp tiles: lane t-strided, all channels of a tile are contiguous, so every
-        // lane keeps RKs independent accumulators and several tiles' loads in flight
-        double u[TR_MAX_RANK_MN];
-        const T* p = a.partial + n * a.WT * a.RKs;
-#pragma unroll
-        for (int r = 0; r < TR_MAX_RANK_MN; ++r) u[r] = 0.0;
-#pragma unroll 2
-        for (int t = lane; t < a.WT; t += 32) {
-            const T* pt = p + (long long)t * a.RKs;
-#pragma unroll
-            for (int r = 0; r < TR_MAX_RANK_MN; ++r)
-                if (r < R) u[r] += (double)__ldg(pt + r);
-        }
-#pragma unroll
-        for (int r = 0; r < TR_MAX_RANK_MN; ++r)
-            if (r < R) u[r] = warp_sum(u[r]);
-        // logits of this lane's classes, softmax
-        double z[TR_JC], P[TR_JC];
-        double zmax = -INFINITY;
-#pragma unroll
-        for (int jc = 0; jc < TR_JC; ++jc) {
-            const int c = lane + 32 * jc;
-            z[jc] = -INFINITY;
-            if (c < C) {
-                double s = 0.0;
-#pragma unroll
-                for (int r = 0; r < TR_MAX_RANK_MN; ++r)
-                    if (r < R) s += sW[r] * u[r] * sFC[c * R + r];
-                z[jc] = s;
-                zmax = fmax(zmax, s);
-            }
-        }
-        zmax = warp_max(zmax);
-        double zs = 0.0;
-#pragma unroll
-        for (int jc = 0; jc < TR_JC; ++jc) {
-            const int c = lane + 32 * jc;
-            P[jc] = c < C ? exp(z[jc] - zmax) : 0.0;
-            zs += P[jc];
-        }
-        zs = warp_sum(zs);
-        double pmax = -INFINITY;
-#pragma unroll
-        for (int jc = 0; jc < TR_JC; ++jc) {
-            const int c = lane + 32 * jc;
-            P[jc] = P[jc] / zs;
-            if (c < C) {
-                P[jc] = (double)(T)P[jc];          // probabilities in the model dtype, as the reference holds them
-                pmax = fmax(pmax, P[jc]);
-                if (a.P) a.P[n * C + c] = (T)P[jc];
-            }
-        }
-        pmax = warp_max(pmax);
-        if (a.pred) {                                // first index of the maximum (np.argmax, mn:527)
-            int best = 1 << 30;
-#pragma unroll
-            for (int jc = 0; jc < TR_JC; ++jc) {
-                const int c = lane + 32 * jc;
-                if (c < C && P[jc] == pmax && c < best) best = c;
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) best = min(best, __shfl_xor_sync(TR_FULL, best, off));
-            if (lane == 0) a.pred[n] = best;
-        }
-        if (a.y == nullptr && a.dP_in == nullptr) continue;
-
-        double dP[TR_JC], dot = 0.0;
-        if (a.dP_in) {
-            // vector-Jacobian product for an arbitrary upstream gradient wrt P (autograd of model, mn:180-187)
-#pragma unroll
-            for (int jc = 0; jc < TR_JC; ++jc) {
-                const int c = lane + 32 * jc;
-                dP[jc] = c < C ? (double)a.dP_in[n * C + c] : 0.0;
-                dot += dP[jc] * P[jc];
-            }
-        } else {
-            // second softmax (CrossEntropyLoss applied to probabilities, mn:364-366 / 448-450)
-            double Q[TR_JC];
-            double qs = 0.0;
-#pragma unroll
-            for (int jc = 0; jc < TR_JC; ++jc) {
-                const int c = lane + 32 * jc;
-                Q[jc] = c < C ? exp(P[jc] - pmax) : 0.0;
-                qs += Q[jc];
-            }
-            qs = warp_sum(qs);
-            const int yn = (int)a.y[n];
-            const double omega = a.class_w ? (double)a.class_w[yn] : 1.0;
-#pragma unroll
-            for (int jc = 0; jc < TR_JC; ++jc) {
-                const int c = lane + 32 * jc;
-                dP[jc] = 0.0;
-                if (c < C) {
-                    const double q = Q[jc] / qs;
-                    if (c == yn) loss += -omega * ((P[jc] - pmax) - log(qs));
-                    dP[jc] = omega * (q - (c == yn ? 1.0 : 0.0));
-                    dot += dP[jc] * P[jc];
-                }
-            }
-        }
-        dot = warp_sum(dot);
-        double dZ[TR_JC];
-#pragma unroll
-        for (int jc = 0; jc < TR_JC; ++jc) {
-            const int c = lane + 32 * jc;
-            dZ[jc] = c < C ? P[jc] * (dP[jc] - dot) : 0.0;
-            if (c < C && a.dZ_ws) a.dZ_ws[n * C + c] = (T)dZ[jc];
-        }
-        // v[r] = w_r sum_c dZ[c] FC[c,r]
-#pragma unroll
-        for (int r = 0; r < TR_MAX_RANK_MN; ++r) {
-            if (r < R) {
-                double s = 0.0;
-#pragma unroll
-                for (int jc = 0; jc < TR_JC; ++jc) {
-                    const int c = lane + 32 * jc;
-                    if (c < C) s += dZ[jc] * sFC[c * R + r];
-                }
-                s = warp_sum(s) * sW[r];
-                if (lane == 0) {
-                    if (a.V) a.V[n * a.RKs + r] = (T)s;
-                    if (a.u_ws) a.u_ws[n * R + r] = (T)u[r];
-                }
-            }
-        }
-        if (a.V && lane >= R && lane < a.RKs) a.V[n * a.RKs + lane] = (T)0;   // padding channels
-    }
-    const double tl = block_sum(loss, sbuf);
-    if (threadIdx.x == 0 && a.part) a.part[blockIdx.x] = tl;
-}
+#include "tr_epi.cuh"
 
 // dFC_part[b, c*R + r] = w_r * sum_{n in block b's range} dZ[n,c] * u[n,r]   (class-factor gradient)
 template <typename T>

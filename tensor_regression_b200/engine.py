@@ -111,6 +111,12 @@ class Engine:
     def launch_info(self):
         info = (ctypes.c_int64 * 8)()
         _lib.lib.tr_last_launch_info(self._h, info)
+        if int(info[7]) < 0 and int(info[2]) == 0:
+            keys = ['launches', 'grid', '_', 'lag_samples', 'groups', 'chunks', 'channels', 'vector_width']
+            d = {k: int(v) for k, v in zip(keys, info) if k != '_'}
+            d['vector_width'] = -d['vector_width']
+            d['path'] = 'single-launch dataflow (second read of X from L2)'
+            return d
         if int(info[7]) < 0:
             keys = ['launches', 'grid', 'cluster_size', 'stages', 'clusters', 'chunks', 'channels', 'vector_width']
             d = dict(zip(keys, [int(v) for v in info]))
@@ -134,7 +140,9 @@ class Engine:
                 'fused_ms': out[4], 'fused_launches': int(out[5])}
 
     def set_option(self, name, value):
-        """'fused': -1 auto, 0 two-pass kernels only, 1 single-pass cluster kernel only."""
+        """'fused': -1 auto, 0 never, 1 always the single-pass cluster kernel (standard model);
+        'flow': -1 auto, 0 never, 1 always the single-launch dataflow kernel; 'flow_window_mb': bytes of X
+        the forward warps may lead the gradient warps by (the part of X that must stay in L2)."""
         self._ck(_lib.lib.tr_set_option(self._h, name.encode(), int(value)))
 
     # -- the hot path --------------------------------------------------------------------------

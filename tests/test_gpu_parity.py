@@ -421,6 +421,106 @@ def test_fused_single_pass_matches_two_pass_and_oracle(name, N, dims, R, dt):
     eng.set_option('fused', -1)
 
 
+# ------------------------------------------------------------------------------------------
+# single-launch dataflow kernel (option flow=1: forward, epilogue and gradient in one persistent
+# kernel, second read of X from L2) vs two-pass vs oracle
+# ------------------------------------------------------------------------------------------
+FLOW_STD = [
+    ('cfg2_shape', 300, (64, 64, 32), 8, torch.float32),
+    ('cfg1', 2000, (20, 30, 40), 5, torch.float32),
+    ('cfg4_shape_f64', 40, (16, 16, 16, 32), 12, torch.float64),
+    ('tiny', 257, (8, 6, 16), 3, torch.float32),
+    ('single_sample', 1, (64, 64, 32), 2, torch.float32),
+    ('long_sums_chunked', 40000, (16, 16), 3, torch.float32),
+    ('ragged_tiles', 333, (10, 10, 12), 4, torch.float32),
+]
+
+
+@pytest.mark.parametrize('name,N,dims,R,dt', FLOW_STD, ids=[c[0] for c in FLOW_STD])
+@pytest.mark.parametrize('window', [32, 1], ids=['win32', 'win1'])
+def test_flow_std_matches_two_pass_and_oracle(name, N, dims, R, dt, window):
+    X, y, _ = O.synth_std(N, dims, R, 1234 + 7, dtype=dt)
+    y = y.reshape(-1)
+    nn = [True] + [False] * len(dims)
+    B0 = O.init_std(dims, R, nn, dtype=dt)
+    bias = torch.tensor([0.07], dtype=dt)
+    w = torch.linspace(0.5, 1.5, R, dtype=dt)
+    eng = engine_for(dims, R, 0, dt)
+    theta = dev(O.pack(B0, bias))
+    Xd, yd, wd = dev(X), dev(y), dev(w)
+    eng.set_option('fused', 0)
+    eng.set_option('flow', 0)
+    yh2 = torch.empty_like(yd)
+    two = eng.fwd_grad_std(Xd, yd, theta, wd, 1, 50.0, 1.0, yhat=yh2).clone()
+    assert eng.launch_info()['path'] == 'two-pass'
+    eng.set_option('flow', 1)
+    eng.set_option('flow_window_mb', window)
+    yh1 = torch.empty_like(yd)
+    one = eng.fwd_grad_std(Xd, yd, theta, wd, 1, 50.0, 1.0, yhat=yh1).clone()
+    info = eng.launch_info()
+    assert info['path'].startswith('single-launch dataflow'), info
+    cf = O.closed_form_std(X.double(), y.double(), [b.double() for b in B0], bias.double(), w.double(), nn)
+    tol = TOL[dt]
+    assert rel(yh1, cf['y_hat']) < tol
+    assert rel(one, cf['gradsum']) < tol, (rel(one, cf['gradsum']), info)
+    assert rel(one, two) < tol
+    again = eng.fwd_grad_std(Xd, yd, theta, wd, 1, 50.0, 1.0)          # deterministic: same bits
+    assert torch.equal(again, one)
+
+
+FLOW_MN = [
+    ('cfg3_shape', 256, (100, 50, 20), 10, 6, torch.float32),
+    ('cfg5_shape', 200, (100, 50, 20), 4, 4, torch.float32),
+    ('rank16', 64, (12, 10), 3, 16, torch.float32),
+    ('many_classes', 150, (8, 6, 4), 40, 5, torch.float32),
+    ('padded_channels_f64', 90, (12, 8, 4), 7, 5, torch.float64),
+    ('long', 30000, (10, 8), 3, 2, torch.float32),
+]
+
+
+@pytest.mark.parametrize('name,N,dims,C,R,dt', FLOW_MN, ids=[c[0] for c in FLOW_MN])
+def test_flow_mn_matches_two_pass_and_oracle(name, N, dims, C, R, dt):
+    X, y, _ = O.synth_mn(N, dims, R, C, 1234 + 3)
+    X = X.to(dt)
+    nn = [False, True] + [False] * (len(dims) - 1)
+    B0 = [b.to(dt) for b in O.init_mn(list(dims) + [C], R, nn, scale=0.2)]
+    w = torch.linspace(0.7, 1.2, R, dtype=dt)
+    counts = np.bincount(y.numpy(), minlength=C).astype(np.float64)
+    cw = torch.tensor(N / (C * np.maximum(counts, 1)), dtype=dt)
+    eng = engine_for(dims, R, C, dt)
+    theta = dev(O.pack(B0))
+    Xd, yd, cwd, wd = dev(X), dev(y), dev(cw), dev(w)
+    eng.set_option('flow', 0)
+    P2 = torch.empty((N, C), dtype=dt, device=DEV)
+    two = eng.fwd_grad_mn(Xd, yd, cwd, theta, wd, 2, 50.0, 1.0, P=P2).clone()
+    assert eng.launch_info()['path'] == 'two-pass'
+    eng.set_option('flow', 1)
+    P1 = torch.empty((N, C), dtype=dt, device=DEV)
+    one = eng.fwd_grad_mn(Xd, yd, cwd, theta, wd, 2, 50.0, 1.0, P=P1).clone()
+    info = eng.launch_info()
+    assert info['path'].startswith('single-launch dataflow'), info
+    cf = O.closed_form_mn(X.double(), y, [b.double() for b in B0], w.double(), nn, cw.double().numpy())
+    tol = TOL[dt]
+    assert rel(P1, cf['P']) < tol
+    assert rel(one, cf['gradsum']) < tol, (rel(one, cf['gradsum']), info)
+    assert rel(one, two) < tol
+    assert torch.equal(P1, P2)                                            # same epilogue arithmetic
+    again = eng.fwd_grad_mn(Xd, yd, cwd, theta, wd, 2, 50.0, 1.0)
+    assert torch.equal(again, one)
+
+
+def test_flow_not_eligible_fails_loudly():
+    from tensor_regression_b200 import engine
+    dims, R = (5, 7, 3), 2                       # D = 105: rows are not 16-byte multiples
+    X, y, _ = O.synth_std(64, dims, R, 3)
+    eng = engine_for(dims, R, 0, torch.float32)
+    theta = dev(O.pack(O.init_std(dims, R, [False] * 4), torch.tensor([0.0])))
+    eng.set_option('fused', 0)
+    eng.set_option('flow', 1)
+    with pytest.raises(engine.TRError):
+        eng.fwd_grad_std(dev(X), dev(y).reshape(-1), theta, dev(torch.ones(R)), 0, 50.0, 1.0)
+
+
 def test_fused_not_eligible_falls_back_loudly():
     from tensor_regression_b200 import engine
     dims, R = (5, 7, 3), 2                       # D = 105: rows are not 16-byte multiples
