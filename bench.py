@@ -60,17 +60,37 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML in a thread (a sample every
+    few ms; the timed region of the default run is ~0.2 s), nvidia-smi -lms as the fallback."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self._stop = index, [], None, None, False
+
+    def _phys_index(self):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            ids = [v.strip() for v in vis.split(',') if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.hdl = pynvml.nvmlDeviceGetHandleByIndex(self._phys_index())
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.hdl, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self._phys_index()}', f'--query-gpu={self.Q}',
                                           '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -78,11 +98,33 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        bits = {'hw_slowdown': nv.nvmlClocksThrottleReasonHwSlowdown,
+                'hw_thermal_slowdown': nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.hdl, nv.NVML_CLOCK_SM))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.hdl))
+                self.rows.append((sm, [k for k, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(',')])
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop = True
+            self.t.join(timeout=2)
+            sm = [r[0] for r in self.rows]
+            reasons = sorted({k for r in self.rows for k in r[1]})
+            return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.mx, 'reasons': reasons,
+                    'samples': len(sm), 'source': 'nvml'}
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -102,7 +144,7 @@ class ClockSampler:
             except Exception:
                 continue
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+                'samples': len(sm), 'source': 'nvidia-smi'}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -461,8 +503,34 @@ def main():
                'host_buffer': f'{pool_n}-sample pinned pool cycled to N={n_local} (synthetic data)'}
         del pool, m2
     elif not args.no_e2e:
-        e2e = {'value': None, 'unit': 'samples/s', 'h2d_bytes_per_step': None, 'd2h_bytes_per_step': None,
-               'note': 'out-of-core streaming is implemented for the standard model only'}
+        pool_n = int(min(n_local, max(256, (2 << 30) // (D * elt))))
+        pool = torch.empty((pool_n, *dims), dtype=dt, pin_memory=True)
+        pool.copy_(X[:pool_n])
+        Xh = CycledHostArray(pool, n_local)
+        reps = (n_local + pool_n - 1) // pool_n
+        yh = torch.cat([y[:pool_n].cpu()] * reps)[:n_local].contiguous()
+        chunk = int(max(1, min(pool_n, (1 << 30) // (D * elt))))
+        m2 = MTR.CP_logistic_regression(Xh, yh, rank=R, non_negative=False, Bcp_init=[b.clone() for b in B0],
+                                        device=device, shard_group='world' if world > 1 else None, n_classes=C,
+                                        out_of_core=True, chunk_samples=chunk)
+        cwh = np.ones(C, dtype=np.float32)
+        m2.fit_Adam(lambda_L2=LAMBDA, max_iter=1, tol=0.0, patience=10 ** 9, weights=cwh, Adam_kwargs=ADAM)   # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        m2.fit_Adam(lambda_L2=LAMBDA, max_iter=args.e2e_steps, tol=0.0, patience=10 ** 9, weights=cwh, Adam_kwargs=ADAM)
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+        e2e = {'value': n_total / e2e_s, 'unit': 'samples/s', 'h2d_bytes_per_step': int(x_bytes),
+               'd2h_bytes_per_step': 8, 'steps': args.e2e_steps, 'ms_per_step': e2e_s * 1e3,
+               'api': 'CP_logistic_regression(X_host, y, out_of_core=True).fit_Adam(...): every iteration streams X '
+                      'from pinned host memory (PCIe-bound); host y uploaded once (N x 8 B)',
+               'h2d_gbs_per_gpu': x_bytes / e2e_s / 1e9,
+               'host_buffer': f'{pool_n}-sample pinned pool cycled to N={n_local} (synthetic data)'}
+        del pool, m2
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

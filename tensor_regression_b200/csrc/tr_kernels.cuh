@@ -71,23 +71,44 @@ template <> __device__ __forceinline__ double tr_fma<double>(double a, double b,
 // Sum M values (M a power of two <= 32) across the 32 lanes with M-1+(5-log2 M) shuffles instead
 // of 5*M: each halving step trades half of the values with the xor-partner.  On return v[0] in
 // lane l is the total of value index (l >> (5 - log2 M)).  Deterministic.
-template <typename T, int M>
+//
+// NOSEL: the first NOSEL halving steps need no per-lane selects because the caller stored its values
+// PERMUTED: a lane whose bit (16 >> s) is set, s < NOSEL, keeps logical value i at physical index
+// i ^ (M >> (s+1)) (all such bits xor-ed together, see warp_perm_mask).  Then every lane sends its
+// physical upper half and keeps its lower half; the pairing of lanes, and therefore the summation
+// order and the bits of the result, are the same as with NOSEL = 0.
+template <typename T, int M, int NOSEL = 0>
 __device__ __forceinline__ void warp_reduce_transpose(T (&v)[M], int lane) {
     constexpr int LG = tr_log2(M);
 #pragma unroll
     for (int s = 0; s < LG; ++s) {
         const int half = (M >> s) >> 1;
         const int off = 16 >> s;
-        const bool up = (lane & off) != 0;
+        if (s < NOSEL) {
 #pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const T send = up ? v[i] : v[i + half];
-            const T keep = up ? v[i + half] : v[i];
-            v[i] = keep + __shfl_xor_sync(TR_FULL, send, off);
+            for (int i = 0; i < half; ++i) v[i] = v[i] + __shfl_xor_sync(TR_FULL, v[i + half], off);
+        } else {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const T send = up ? v[i] : v[i + half];
+                const T keep = up ? v[i + half] : v[i];
+                v[i] = keep + __shfl_xor_sync(TR_FULL, send, off);
+            }
         }
     }
 #pragma unroll
     for (int off = (16 >> LG); off >= 1; off >>= 1) v[0] += __shfl_xor_sync(TR_FULL, v[0], off);
+}
+
+// index permutation of a lane for the NOSEL leading steps of warp_reduce_transpose<T, M, NOSEL>
+template <int M, int NOSEL>
+__device__ __forceinline__ int warp_perm_mask(int lane) {
+    int m = 0;
+#pragma unroll
+    for (int s = 0; s < NOSEL; ++s)
+        if (lane & (16 >> s)) m |= (M >> s) >> 1;
+    return m;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -198,8 +219,13 @@ __global__ void __launch_bounds__(TR_TPB, TR_MINB) k_fwd(const FwdArgs<T> a) {
     constexpr int M = tr_next_pow2(U * RKR);          // padded with zeros when U is not a power of two
     constexpr int LGM = tr_log2(M);
     static_assert(M <= 32, "next_pow2(U * next_pow2(RK)) must be <= 32");
+    // With several channels the shuffle reduction is a large share of the instructions.  Its steps that
+    // halve the SAMPLE index run without selects when each lane loads sample (u ^ mu) into slot u
+    // (U a power of two): same lanes paired in the same order, same bits.
+    constexpr int NOSEL = (RK > 1 && (U & (U - 1)) == 0) ? tr_log2(U) : 0;
 
     const int lane = threadIdx.x & 31;
+    const int mu = warp_perm_mask<M, NOSEL>(lane) / RKR;     // sample-slot permutation of this lane
     const long long warp_global = (long long)blockIdx.x * TR_WPB + (threadIdx.x >> 5);
     const long long wtot = (long long)gridDim.x * TR_WPB;
     const long long D = a.geo.D;
@@ -236,7 +262,7 @@ __global__ void __launch_bounds__(TR_TPB, TR_MINB) k_fwd(const FwdArgs<T> a) {
             T x[U][E][VEC];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const long long n = n0 + (long long)u * a.Gn;
+                const long long n = n0 + (long long)(u ^ mu) * a.Gn;
                 const T* xp = xbase + n * D;
 #pragma unroll
                 for (int j = 0; j < E; ++j) {
@@ -260,7 +286,7 @@ __global__ void __launch_bounds__(TR_TPB, TR_MINB) k_fwd(const FwdArgs<T> a) {
 #pragma unroll
                         for (int c = 0; c < RK; ++c)
                             vals[u * RKR + c] = tr_fma<T>(x[u][j][v], coef[j][v][c], vals[u * RKR + c]);
-            warp_reduce_transpose<T, M>(vals, lane);
+            warp_reduce_transpose<T, M, NOSEL>(vals, lane);
             if ((lane & ((1 << (5 - LGM)) - 1)) == 0) {
                 const int q = lane >> (5 - LGM);
                 const int u = q / RKR, c = q % RKR;
