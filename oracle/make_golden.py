@@ -128,13 +128,42 @@ def gen_mn(MTR):
         print('wrote', name, 'loss', out['loss'])
 
 
+def gen_hier(HTR):
+    """multinomial_tensor_regression_hierarchical.py: unweighted CE, three Adam parameter groups (3-D X)."""
+    name, N, dims, C, R, lam, seed = 'hier_2mode', 96, (10, 8), 3, 3, 0.01, 21
+    X, y, _ = O.synth_mn(N, dims, R, C, 1234 + seed)
+    nn = [False, True, False]
+    init = O.init_mn(list(dims) + [C], R, nn, scale=1.0, seed=321)
+    out = {'X': X.numpy(), 'y': y.numpy(), 'non_negative': np.array(nn), 'lambda_L2': lam, 'R': R, 'C': C}
+    for i, b in enumerate(init):
+        out[f'Bcp_init_{i}'] = b.numpy()
+    m = HTR.CP_logistic_regression(X, y, rank=R, non_negative=nn,
+                                   Bcp_init=[b.clone().requires_grad_(True) for b in init], device='cpu')
+    m.fit_Adam(lambda_L2=lam, max_iter=20, tol=1e-50, patience=100, verbose=False, Adam_kwargs=ADAM)
+    out['adam_loss_running'] = np.array(m.loss_running)
+    for i, b in enumerate(m.Bcp):
+        out[f'adam_Bcp_{i}'] = b.detach().numpy()
+    prob, pred = m.predict()
+    out['adam_prob'] = prob
+    out['adam_pred'] = pred
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('wrote', name, 'final loss', out['adam_loss_running'][-1])
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'hier':        # only the hierarchical fixture (the others stay as committed)
+        if not ref_loader.available():
+            sys.exit('reference not found at ' + ref_loader.REFERENCE_DIR)
+        torch.set_num_threads(1)
+        gen_hier(ref_loader.hierarchical())
+        return
     if not ref_loader.available():
         sys.exit('reference not found at ' + ref_loader.REFERENCE_DIR)
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)            # fixed summation order for the fixtures
     gen_std(ref_loader.standard())
     gen_mn(ref_loader.multinomial())
+    gen_hier(ref_loader.hierarchical())
 
 
 if __name__ == '__main__':

@@ -38,3 +38,9 @@ def multinomial():
     if 'mn' not in _cache:
         _cache['mn'] = _load('multinomial_tensor_regression')
     return _cache['mn']
+
+
+def hierarchical():
+    if 'hier' not in _cache:
+        _cache['hier'] = _load('multinomial_tensor_regression_hierarchical')
+    return _cache['hier']

@@ -1,5 +1,6 @@
 """B200-native CP (Kruskal) tensor regression — drop-in for the fit / predict path of
-kimerein/tensor_regression's ``standard_tensor_regression`` and ``multinomial_tensor_regression``.
+kimerein/tensor_regression's ``standard_tensor_regression``, ``multinomial_tensor_regression`` and
+``multinomial_tensor_regression_hierarchical``.
 
     from tensor_regression_b200 import standard_tensor_regression as STR
     from tensor_regression_b200 import multinomial_tensor_regression as MTR
@@ -12,5 +13,7 @@ from . import _lib  # noqa: F401  (fails loudly if the extension is missing)
 from . import engine  # noqa: F401
 from . import standard_tensor_regression  # noqa: F401
 from . import multinomial_tensor_regression  # noqa: F401
+from . import multinomial_tensor_regression_hierarchical  # noqa: F401
 
-__all__ = ['standard_tensor_regression', 'multinomial_tensor_regression', 'engine']
+__all__ = ['standard_tensor_regression', 'multinomial_tensor_regression',
+           'multinomial_tensor_regression_hierarchical', 'engine']

@@ -181,6 +181,28 @@ def test_mn_api_fit_vs_reference_golden(path):
         m.fit_Adam(Adam_kwargs=ADAM)                    # class weights None raises like mn:449
 
 
+def test_hierarchical_api_fit_vs_reference_golden():
+    """Drop-in for multinomial_tensor_regression_hierarchical.py: no class weights in the
+    signatures, unweighted CE, fitted factors / probabilities equal to the reference's."""
+    from tensor_regression_b200 import multinomial_tensor_regression_hierarchical as HTR
+    z, k = load(os.path.join(GOLDEN, 'hier_2mode.npz'))
+    nn = [bool(v) for v in z['non_negative']]
+    B0 = [torch.from_numpy(z[f'Bcp_init_{i}']) for i in range(k)]
+    m = HTR.CP_logistic_regression(z['X'], z['y'], rank=int(z['R']), non_negative=nn,
+                                   Bcp_init=[b.clone() for b in B0], device=DEV)
+    m.fit_Adam(lambda_L2=float(z['lambda_L2']), max_iter=20, tol=1e-50, patience=100, verbose=False, Adam_kwargs=ADAM)
+    assert rel(m.loss_running, z['adam_loss_running']) < 1e-4
+    for i in range(k):
+        assert rel(m.Bcp[i], z[f'adam_Bcp_{i}']) < 1e-4
+    prob, pred = m.predict(plot_pref=False)
+    assert rel(prob, z['adam_prob']) < 1e-4 and np.mean(pred == z['adam_pred']) > 0.98
+    with pytest.raises(TypeError):
+        m.fit_Adam(weights=np.ones(3), Adam_kwargs=ADAM)      # the hierarchical signatures have no `weights`
+    m4 = HTR.CP_logistic_regression(np.zeros((8, 4, 3, 2), dtype=np.float32), np.arange(8) % 2, rank=2, device=DEV)
+    with pytest.raises(IndexError):
+        m4.fit_Adam(Adam_kwargs=ADAM)                           # three parameter groups only (hier:436-440)
+
+
 # ------------------------------------------------------------------------------------------
 # (b) oracle on BASELINE.json shapes at sizes the CPU finishes in seconds
 # ------------------------------------------------------------------------------------------

@@ -81,6 +81,17 @@ def test_signatures_match_reference():
     for name in ['squeeze_integers', 'confusion_matrix', 'idx_to_oneHot', 'make_BcpInit', 'non_neg_fn', 'model',
                  'L2_penalty', 'CP_logistic_regression']:
         assert hasattr(MTR, name)
+    # multinomial_tensor_regression_hierarchical.py: no class weights, predict(plot_pref) (hier:291-299, 385-392, 473)
+    from tensor_regression_b200 import multinomial_tensor_regression_hierarchical as HTR
+    assert names(HTR.CP_logistic_regression.fit)[1:] == ['lambda_L2', 'max_iter', 'tol', 'patience', 'verbose',
+                                                         'running_loss_logging_interval', 'LBFGS_kwargs']
+    assert names(HTR.CP_logistic_regression.fit_Adam)[1:] == ['lambda_L2', 'max_iter', 'tol', 'patience', 'verbose',
+                                                              'Adam_kwargs']
+    assert names(HTR.CP_logistic_regression.predict)[1:] == ['X', 'y_true', 'Bcp', 'device', 'plot_pref']
+    assert names(HTR.CP_logistic_regression.__init__)[1:] == names(MTR.CP_logistic_regression.__init__)[1:]
+    for name in ['squeeze_integers', 'confusion_matrix', 'idx_to_oneHot', 'make_BcpInit', 'non_neg_fn', 'model',
+                 'L2_penalty']:
+        assert hasattr(HTR, name)
 
 
 def test_masks_offsets_shards():

@@ -85,6 +85,20 @@ def test_port_matches_reference_mn(path):
         assert rel(f['Bcp'][i], z[f'adam_Bcp_{i}']) < 2e-5
 
 
+def test_port_matches_reference_hierarchical():
+    """multinomial_tensor_regression_hierarchical.py (unweighted CE, three Adam parameter groups with one
+    learning rate) == the multinomial port with class weights of one."""
+    z, k = load(os.path.join(GOLDEN, 'hier_2mode.npz'))
+    X, y = torch.from_numpy(z['X']), torch.from_numpy(z['y'])
+    B0 = [torch.from_numpy(z[f'Bcp_init_{i}']) for i in range(k)]
+    nn = [bool(v) for v in z['non_negative']]
+    R, C = int(z['R']), int(z['C'])
+    f = O.fit_adam_mn(X, y, B0, torch.ones(R), nn, np.ones(C, dtype=np.float32), float(z['lambda_L2']), 20, ADAM)
+    assert rel(f['loss_running'], z['adam_loss_running']) < 2e-5
+    for i in range(k):
+        assert rel(f['Bcp'][i], z[f'adam_Bcp_{i}']) < 2e-5
+
+
 @pytest.mark.parametrize('path', STD, ids=[os.path.basename(p)[:-4] for p in STD])
 def test_closed_form_vs_autograd_std(path):
     z, k = load(path)
