@@ -438,6 +438,17 @@ int run_fused_std(tr_handle* h, const T* X, const T* y, long long N, const T* th
 }
 
 
+// class-factor gradient partial sums (dZ_ws, u_ws -> dfc_part)
+template <typename T>
+int launch_dfc(tr_handle* h, int dgrid, const T* w, long long N, cudaStream_t st) {
+    const Geo& g = h->geo;
+    const size_t smem = (size_t)4 * g.C * g.R * sizeof(double);
+    if (smem > 48 * 1024) TR_CUDA(h, cudaFuncSetAttribute(k_dfc<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dfc<T><<<dgrid, TR_TPB, smem, st>>>((const T*)h->dZ_ws.p, (const T*)h->u_ws.p, w, N, g.C, g.R, (double*)h->dfc_part.p);
+    TR_LAUNCH_CHECK(h);
+    return TR_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // single-launch dataflow path (tr_flow.cuh): plan + launch
 // ---------------------------------------------------------------------------------------------
@@ -559,9 +570,7 @@ int run_flow(tr_handle* h, const T* X, const void* y, const T* class_w, long lon
         k_colsum<<<1, 128, 0, st>>>((const double*)h->epi_part.p, nwarps, 2, gradsum + g.pf);
         TR_LAUNCH_CHECK(h);
         const int dgrid = (int)std::min<long long>((N + 63) / 64, (long long)h->sms * 2);
-        k_dfc<T><<<dgrid, TR_TPB, 0, st>>>((const T*)h->dZ_ws.p, (const T*)h->u_ws.p, w, N, g.C, g.R,
-                                           (double*)h->dfc_part.p);
-        TR_LAUNCH_CHECK(h);
+        if ((rc = launch_dfc<T>(h, dgrid, w, N, st))) return rc;
         k_colsum<<<g.C * g.R, 128, 0, st>>>((const double*)h->dfc_part.p, dgrid, g.C * g.R, gradsum + g.pfeat);
         TR_LAUNCH_CHECK(h);
     }
@@ -707,9 +716,7 @@ int mn_t(tr_handle* h, const void* X, const long long* y, const void* class_w, l
         k_colsum<<<1, 128, 0, st>>>((const double*)h->epi_part.p, egrid, 1, gradsum + g.pf);
         TR_LAUNCH_CHECK(h);
         const int dgrid = (int)std::min<long long>((N + 63) / 64, (long long)h->sms * 2);
-        k_dfc<T><<<dgrid, TR_TPB, 0, st>>>((const T*)h->dZ_ws.p, (const T*)h->u_ws.p, (const T*)w, N, g.C, g.R,
-                                           (double*)h->dfc_part.p);
-        TR_LAUNCH_CHECK(h);
+        if ((rc = launch_dfc<T>(h, dgrid, (const T*)w, N, st))) return rc;
         k_colsum<<<g.C * g.R, 128, 0, st>>>((const double*)h->dfc_part.p, dgrid, g.C * g.R,
                                                           gradsum + g.pfeat);
         TR_LAUNCH_CHECK(h);

@@ -21,10 +21,10 @@ __device__ __forceinline__ double tr_canon(double v) { return v != v ? __longlon
 // (fully batched) read of the sample — a loop that waited inside get() would serialise ~80 L2 round trips.
 template <typename T>
 struct PlainPartials {
-    const T* p;
+    const T* p;       // this sample's (WT, RKs) block
     int RKs;
     __device__ __forceinline__ bool get(int t, int r, T& out) const {
-        out = __ldcg(p + (long long)t * RKs + r);
+        out = __ldg(p + (long long)t * RKs + r);       // the RKs loads of a tile share sectors: keep them in L1
         return true;
     }
 };
@@ -103,7 +103,7 @@ struct EpiMnArgs {
 };
 
 // model()'s softmax (mn:180-187), CrossEntropyLoss on the probabilities (second softmax, mn:364-366 /
-// 448-450) and its backward down to v[n,r], for sample n.  p = the sample's (WT, RKs) partials;
+// 448-450) and its backward down to v[n,r], for sample n.  rd = reader of the sample's tile partials;
 // sFC (C,R) / sW (R) in shared memory (double).
 template <typename T, typename Reader>
 __device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n, const Reader& rd, int lane,
@@ -244,7 +244,7 @@ __device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n
 }
 
 template <typename T>
-__global__ void __launch_bounds__(TR_TPB) k_epi_mn(const EpiMnArgs<T> a) {
+__global__ void __launch_bounds__(TR_TPB, 3) k_epi_mn(const EpiMnArgs<T> a) {
     extern __shared__ __align__(16) unsigned char tr_smem[];
     double* sFC = reinterpret_cast<double*>(tr_smem);      // C*R
     double* sW = sFC + a.C * a.R;                            // R

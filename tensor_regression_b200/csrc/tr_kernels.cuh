@@ -3,7 +3,8 @@
 // Data layout in HBM:
 //   X        (N, I_1..I_k) row-major, sample stride D = prod I_m; streamed, never copied
 //   theta    flat parameter vector [F_0 | .. | F_{k-1} | F_C | bias], (I_m, R) row-major blocks
-//   partial  (N, WT, RK)   per-sample, per-warp-tile, per-channel partial inner products
+//   partial  (N, WT, RK)   per-sample, per-warp-tile, per-channel partial inner products (channels of a
+//                          tile contiguous: one warp store of pass 1 touches U lines, not U*RK)
 //   V        (N, RK)       per-sample weights of the gradient pass (residual / v[n,r])
 //   Gpart    (slots, RK, Dpad) split-N partial sums of  sum_n V[n,c] * X[n,:]
 //   Gred     (RK, D) double   = sum over slots

@@ -39,20 +39,29 @@ __global__ void k_reduce_G(const T* __restrict__ Gpart, int slots, int RK, long 
 
 #include "tr_epi.cuh"
 
-// dFC_part[b, c*R + r] = w_r * sum_{n in block b's range} dZ[n,c] * u[n,r]   (class-factor gradient)
+// dFC_part[b, c*R + r] = w_r * sum_{n in block b's range} dZ[n,c] * u[n,r]   (class-factor gradient).
+// Thread (q, j): sample lane q = tid / 64 of 4, (c,r) pair j = tid % 64 (+64, ...); the four sample lanes
+// are combined in a fixed order through shared memory (4 * C * R doubles of dynamic shared memory).
 template <typename T>
 __global__ void __launch_bounds__(TR_TPB) k_dfc(const T* __restrict__ dZ, const T* __restrict__ u,
                                                 const T* __restrict__ w, long long N, int C, int R,
                                                 double* __restrict__ part) {
+    extern __shared__ __align__(16) unsigned char tr_smem[];
+    double* sq = reinterpret_cast<double*>(tr_smem);                // [4][C*R]
     const long long per = (N + gridDim.x - 1) / gridDim.x;
     const long long n0 = (long long)blockIdx.x * per;
     const long long n1 = n0 + per < N ? n0 + per : N;
-    for (int j = threadIdx.x; j < C * R; j += TR_TPB) {
+    const int q = threadIdx.x >> 6, CR = C * R;
+    for (int j = threadIdx.x & 63; j < CR; j += 64) {
         const int c = j / R, r = j % R;
         double s = 0.0;
-        for (long long n = n0; n < n1; ++n) s += (double)dZ[n * C + c] * (double)u[n * R + r];
-        part[(long long)blockIdx.x * C * R + j] = s * (double)w[r];
+#pragma unroll 4
+        for (long long n = n0 + q; n < n1; n += 4) s += (double)__ldg(dZ + n * C + c) * (double)__ldg(u + n * R + r);
+        sq[q * CR + j] = s;
     }
+    __syncthreads();
+    for (int j = threadIdx.x; j < CR; j += TR_TPB)
+        part[(long long)blockIdx.x * CR + j] = (((sq[j] + sq[CR + j]) + sq[2 * CR + j]) + sq[3 * CR + j]) * (double)w[j % R];
 }
 
 // out[j] = sum_b part[b, j] for a (rows, cols) double matrix; one block per column (deterministic)
