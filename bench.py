@@ -421,6 +421,8 @@ def main():
     prof = eng.profile_read()
     eng.profile(False)
     launches = eng.launches - launches0
+    launch_info = eng.launch_info()
+    n_gradsum = eng.n_gradsum
     final_loss = loss.cpu().tolist()
     t = torch.tensor([ms], dtype=torch.float64, device=device)
     if world > 1:
@@ -442,7 +444,7 @@ def main():
     if prof['fused_launches'] > 0:
         # single-pass kernel: does the work of both passes (algorithmic bytes = 2 x bytes(X))
         # while reading X from HBM once -> "achieved" exceeds the HBM peak by design; traffic shows the real bytes
-        is_flow = eng.launch_info()['path'].startswith('single-launch dataflow')
+        is_flow = launch_info['path'].startswith('single-launch dataflow')
         dom, dom_ms, alg = ('k_flow' if is_flow else 'k_fused_std'), fused_ms, 2 * x_bytes
         extra = {'k_single_ms': fused_ms, 'hbm_gbs_if_x_read_once': x_bytes / (fused_ms * 1e-3) / 1e9,
                  'hbm_frac_if_x_read_once': x_bytes / (fused_ms * 1e-3) / 1e9 / peak,
@@ -532,6 +534,47 @@ def main():
                'host_buffer': f'{pool_n}-sample pinned pool cycled to N={n_local} (synthetic data)'}
         del pool, m2
 
+    # ---- the call a user makes: one fit_Adam(X_host, ...) of K iterations, X uploaded ONCE inside the
+    # timed region (pinned, double-buffered) and then resident.  Reported next to the strict e2e number
+    # above (which re-streams X over PCIe on every iteration); the original X is freed first.
+    if e2e is not None and e2e.get('value') is not None:
+        pool_n = int(min(n_local, max(256, (2 << 30) // (D * elt))))
+        pool = torch.empty((pool_n, *dims), dtype=dt, pin_memory=True)
+        pool.copy_(X[:pool_n])
+        reps = (n_local + pool_n - 1) // pool_n
+        yh = torch.cat([y[:pool_n].cpu()] * reps)[:n_local].contiguous()
+        Xh = CycledHostArray(pool, n_local)
+        X = None
+        model = None
+        eng = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        K = max(1, args.steps)
+        barrier()
+        t0 = time.perf_counter()
+        if kind == 'std':
+            m3 = STR.CP_linear_regression((n_local, *dims), dtype=dt, rank=R, non_negative=False,
+                                          Bcp_init=[b.clone() for b in B0], device=device,
+                                          shard_group='world' if world > 1 else None)
+            m3.fit_Adam(Xh, yh, lambda_L2=LAMBDA, max_iter=K, tol=0.0, patience=10 ** 9, Adam_kwargs=ADAM)
+        else:
+            m3 = MTR.CP_logistic_regression(Xh, yh, rank=R, non_negative=False, Bcp_init=[b.clone() for b in B0],
+                                            device=device, shard_group='world' if world > 1 else None, n_classes=C)
+            m3.fit_Adam(lambda_L2=LAMBDA, max_iter=K, tol=0.0, patience=10 ** 9, weights=np.ones(C, dtype=np.float32),
+                        Adam_kwargs=ADAM)
+        barrier()
+        call_s = time.perf_counter() - t0
+        tc = torch.tensor([call_s], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        call_s = float(tc.item())
+        e2e['fit_call'] = {'value': n_total * K / call_s, 'unit': 'samples/s', 'iterations': K, 'seconds': call_s,
+                           'h2d_bytes_total': int(x_bytes), 'final_loss': float(m3.loss_running[-1]),
+                           'api': 'one fit_Adam(X_host, y, max_iter=K) call: construction, ONE pinned double-buffered '
+                                  'upload of X, K resident iterations, one loss read per iteration'}
+        del pool, m3
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(wl)
@@ -545,8 +588,8 @@ def main():
                           'x_bytes_per_gpu': int(x_bytes), 'optimizer': 'Adam lr=0.01 amsgrad', 'lambda_L2': LAMBDA,
                           'l2_flush': 'not needed: X per GPU (%.1f GB) >> 126 MB L2' % (x_bytes / 1e9)
                           if x_bytes > (1 << 30) else 'X smaller than L2+: numbers are cache-assisted',
-                          'parallelism': f'sample-sharded x{world}, one all-reduce of {eng.n_gradsum} doubles/iter',
-                          'launch': eng.launch_info()},
+                          'parallelism': f'sample-sharded x{world}, one all-reduce of {n_gradsum} doubles/iter',
+                          'launch': launch_info},
                'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches),
                'clocks': clocks, 'final_loss': final_loss}
         emit(out)

@@ -346,3 +346,40 @@ class HostStreamer:
             yield lo, hi, self._dev[s][:hi - lo]
             self._done[s].record(main)
             self._used[s] = True
+
+
+def upload_resident(X, dtype, device, chunk_bytes=256 << 20):
+    """Host array (numpy / memmap / CPU tensor / anything with ``.shape`` and ``[lo:hi]``) -> ONE resident
+    device tensor.  Chunks are copied on a side stream straight into their place; chunks that are not
+    already pinned go through two pinned staging buffers, so the host-side staging copy of chunk i+1
+    overlaps the DMA of chunk i.  (``torch.as_tensor(X).to(device)`` does one synchronous pageable copy
+    and needs X materialised as a single host tensor first.)"""
+    device = torch.device(device)
+    N = int(X.shape[0])
+    shape = tuple(int(d) for d in X.shape[1:])
+    row = max(1, int(np.prod(shape))) * torch.empty((), dtype=dtype).element_size()
+    step = int(max(1, min(N, chunk_bytes // row)))
+    out = torch.empty((N, *shape), dtype=dtype, device=device)
+    main = torch.cuda.current_stream(device)
+    copy = torch.cuda.Stream(device=device)
+    copy.wait_stream(main)
+    pin, busy = [None, None], [None, None]
+    for i, lo in enumerate(range(0, N, step)):
+        hi = min(N, lo + step)
+        s = i % 2
+        c = X[lo:hi]
+        if not isinstance(c, torch.Tensor):
+            c = torch.as_tensor(np.ascontiguousarray(c))
+        if not (c.dtype == dtype and c.is_contiguous() and c.is_pinned()):
+            if busy[s] is not None:
+                busy[s].synchronize()                      # the DMA that read this staging buffer is done
+            if pin[s] is None:
+                pin[s] = torch.empty((step, *shape), dtype=dtype, pin_memory=True)
+            pin[s][:hi - lo].copy_(c)
+            c = pin[s][:hi - lo]
+        with torch.cuda.stream(copy):
+            out[lo:hi].copy_(c, non_blocking=True)
+            busy[s] = torch.cuda.Event()
+            busy[s].record(copy)
+    main.wait_stream(copy)
+    return out

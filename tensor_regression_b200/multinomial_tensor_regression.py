@@ -139,6 +139,10 @@ class CP_logistic_regression():
         self._chunk_samples = chunk_samples
         if self._out_of_core:
             self.X = X
+        elif isinstance(X, torch.Tensor) and X.is_cuda:
+            self.X = X.to(device=dev, dtype=torch.float32)
+        elif hasattr(X, 'shape') and len(X.shape) >= 1 and int(X.shape[0]) > 0:
+            self.X = _engine.upload_resident(X, torch.float32, dev)   # host data: pinned, double-buffered upload
         else:
             self.X = torch.as_tensor(X, dtype=torch.float32).to(dev)
         self.y = torch.as_tensor(y, dtype=torch.long).to(dev)

@@ -209,11 +209,14 @@ class CP_linear_regression():
 
     def _prep_xy(self, X, y):
         dev = self._torch_device()
-        if not isinstance(X, torch.Tensor):
-            X = torch.as_tensor(X)
         if not isinstance(y, torch.Tensor):
             y = torch.as_tensor(y)
-        X = X.to(device=dev, dtype=self.dtype)
+        if isinstance(X, torch.Tensor) and X.is_cuda:
+            X = X.to(device=dev, dtype=self.dtype)
+        elif hasattr(X, 'shape') and len(X.shape) >= 1 and int(X.shape[0]) > 0:
+            X = _engine.upload_resident(X, self.dtype, dev)        # host data: pinned, double-buffered upload
+        else:
+            X = torch.as_tensor(np.asarray(X)).to(device=dev, dtype=self.dtype)
         y = y.to(device=dev, dtype=self.dtype).reshape(-1).contiguous()
         if X.shape[0] != y.shape[0]:
             raise ValueError('X.shape[0] must match len(y)')

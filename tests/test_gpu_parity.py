@@ -727,6 +727,25 @@ def test_mn_model_autograd_matches_reference_autograd():
         assert rel(Bd[i].grad, ref['grads'][i]) < 1e-10
 
 
+def test_upload_resident_places_every_chunk():
+    """Host data of a resident fit goes up through pinned staging in chunks: float64 numpy (converted), a pinned
+    fp32 tensor (copied in place), a chunk size that does not divide N, an array-like that is neither."""
+    from tensor_regression_b200 import engine
+    g = np.random.default_rng(5)
+    A = g.standard_normal((37, 6, 10))
+    d = engine.upload_resident(A, torch.float32, DEV, chunk_bytes=5 * 6 * 10 * 4)
+    assert torch.equal(d.cpu(), torch.from_numpy(A).float())
+    B = torch.from_numpy(A).float().pin_memory()
+    assert torch.equal(engine.upload_resident(B, torch.float32, DEV, chunk_bytes=1 << 12).cpu(), B)
+
+    class View:                       # anything with .shape and [lo:hi]
+        shape = A.shape
+
+        def __getitem__(self, sl):
+            return A[sl]
+    assert torch.equal(engine.upload_resident(View(), torch.float64, DEV, chunk_bytes=999).cpu(), torch.from_numpy(A))
+
+
 def test_mn_out_of_core_equals_resident():
     from tensor_regression_b200 import multinomial_tensor_regression as MTR
     N, dims, C, R = 333, (6, 5, 8), 3, 4
