@@ -31,8 +31,17 @@ __global__ void k_reduce_G(const T* __restrict__ Gpart, int slots, int RK, long 
          e += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(e / D);
         const long long i = e % D;
+        // slots in order (deterministic); four loads in flight per thread
         double s = 0.0;
-        for (int sl = 0; sl < slots; ++sl) s += (double)Gpart[((long long)sl * RK + c) * Dpad + i];
+        const T* gp = Gpart + (long long)c * Dpad + i;
+        const long long sstr = (long long)RK * Dpad;
+        int sl = 0;
+        for (; sl + 4 <= slots; sl += 4) {
+            const T v0 = __ldcg(gp + (long long)sl * sstr), v1 = __ldcg(gp + (long long)(sl + 1) * sstr);
+            const T v2 = __ldcg(gp + (long long)(sl + 2) * sstr), v3 = __ldcg(gp + (long long)(sl + 3) * sstr);
+            s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+        }
+        for (; sl < slots; ++sl) s += (double)__ldcg(gp + (long long)sl * sstr);
         Gred[e] = s;
     }
 }
