@@ -462,7 +462,7 @@ def main():
                  'k_grad_gbs': x_bytes / (grad_ms * 1e-3) / 1e9 if grad_ms else None,
                  'share_of_step': {'k_fwd': fwd_ms / ms_per_step, 'k_grad': grad_ms / ms_per_step}}
     achieved = alg / (dom_ms * 1e-3) / 1e9
-    tr = ratios.get(dom)
+    tr = ratios.get(f'{dom}_{kind}') or ratios.get(dom)
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak,
                 'traffic': (tr['dram_bytes_per_algorithmic_byte'] * alg) if tr else None,

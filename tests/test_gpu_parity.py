@@ -779,3 +779,39 @@ def STR_out_of_core_check():
     b.fit_Adam(X.numpy(), y.numpy(), max_iter=6, tol=1e-50, patience=100, Adam_kwargs=ADAM, out_of_core=True,
                chunk_samples=40)
     return rel(b.loss_running, a.loss_running)
+
+
+def test_notebook_known_answer_through_the_cuda_path():
+    """The reference's only known-answer vector (demo_TensorRegression.ipynb cells 5 + 8: fp64, seeds 321,
+    rank 10, L-BFGS strong-Wolfe, saved log 560125.5196947237, 1699.8925874402807, 0.041904340578888165 x 11,
+    'Convergence reached'), reproduced with the notebook's own calls on the CUDA path at the notebook's full
+    size (X is 2000 x 500 x 500 float64 = 4 GB)."""
+    import scipy.signal
+    from oracle.tensorly_standin import cp_to_tensor, inner
+    from tensor_regression_b200 import standard_tensor_regression as STR
+    torch.manual_seed(321)
+    np.random.seed(321)
+    dims = [2000, 500, 500]
+    Xcp = [torch.rand(dims[0], 4) - 0.5,
+           torch.vstack([torch.sin(torch.linspace(0, 140, dims[1])),
+                         torch.cos(torch.linspace(2, 19, dims[1])),
+                         torch.linspace(0, 1, dims[1]),
+                         torch.cos(torch.linspace(0, 17, dims[1])) > 0]).T,
+           torch.tensor(scipy.signal.savgol_filter(np.random.rand(dims[2], 4), 15, 3, axis=0)) - 0.5]
+    X_fake = cp_to_tensor((np.ones(4), Xcp))
+    y = inner(X_fake + torch.rand(dims) / 100, cp_to_tensor((np.ones(4), Xcp[1:])), n_modes=2)
+    X = X_fake - X_fake.mean(0)
+    del X_fake
+    assert X.dtype == torch.float64
+    # cell 8, verbatim apart from the device
+    cpmlr = STR.CP_linear_regression(X.shape, dtype=X.dtype, rank=10, non_negative=[False, False], weights=None,
+                                     Bcp_init=None, Bcp_init_scale=0.005, device=DEV, softplus_kwargs={'beta': 50, 'threshold': 1})
+    conv = cpmlr.fit(X, y, lambda_L2=1e-5, max_iter=200, tol=1e-50, patience=10, verbose=0,
+                     running_loss_logging_interval=1, LBFGS_kwargs=LBFGS)
+    L = cpmlr.loss_running
+    assert conv is True and len(L) == 13, (conv, len(L), L)
+    assert abs(L[0] - 560125.5196947237) / 560125.5196947237 < 1e-3      # (the noise term of y is not seeded identically)
+    assert abs(L[-1] - 0.041904340578888165) / 0.041904340578888165 < 1e-5
+    assert max(abs(v - L[2]) for v in L[2:]) < 1e-9 * L[2]
+    y_hat = cpmlr.predict(X[:64])
+    assert y_hat.shape == (64,) and np.all(np.isfinite(y_hat))
