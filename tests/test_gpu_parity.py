@@ -707,6 +707,65 @@ def test_cfg2_full_size_properties():
     torch.cuda.empty_cache()
 
 
+def test_cfg3_full_size_properties():
+    """One GPU's shard of configs[2] (62 500 x (100, 50, 20) fp32 = 25 GB, 10 classes, rank 6): what can be
+    checked at a size the oracle cannot run."""
+    from tensor_regression_b200 import engine
+    free, _ = torch.cuda.mem_get_info()
+    N, dims, C, R = 62500, (100, 50, 20), 10, 6
+    D = int(np.prod(dims))
+    if free < N * D * 4 + (8 << 30):
+        pytest.skip('needs ~33 GB of free HBM')
+    g = torch.Generator(device=DEV).manual_seed(2025)
+    X = torch.empty((N, *dims), dtype=torch.float32, device=DEV)
+    for lo in range(0, N, 2048):
+        X[lo:lo + 2048].normal_(generator=g)
+    nn = [False] * 4
+    gc = torch.Generator().manual_seed(11)
+    Fs = [0.3 * torch.randn(d, R, generator=gc) for d in list(dims) + [C]]
+    B0 = O.init_mn(list(dims) + [C], R, nn, scale=0.2)
+    eng = engine_for(dims, R, C, torch.float32)
+    w = dev(torch.ones(R))
+    theta_star, theta = dev(O.pack(Fs)), dev(O.pack(B0))
+    P, y = eng.forward_mn(X, theta_star, w, 0, 50.0, 1.0)
+    # (1) probabilities at full size == oracle on the first / last 200 samples; rows sum to one; argmax == labels
+    for sl in (slice(0, 200), slice(N - 200, N)):
+        want = O.mn_model(X[sl].cpu().double(), [f.double() for f in Fs], torch.ones(R, dtype=torch.float64), nn)
+        assert rel(P[sl], want) < 1e-5
+    assert float((P.sum(1) - 1).abs().max()) < 1e-5 and torch.equal(P.argmax(1), y)
+    counts = torch.bincount(y, minlength=C).double()
+    cw = dev((N / (C * counts.clamp(min=1))).float())
+    # (2) deterministic: same bits on a second launch
+    full = eng.fwd_grad_mn(X, y, cw, theta, w, 0, 50.0, 1.0).clone()
+    assert torch.equal(eng.fwd_grad_mn(X, y, cw, theta, w, 0, 50.0, 1.0), full)
+    # (3) the packed sums of disjoint shards add up to the whole (what the all-reduce relies on)
+    parts = torch.zeros_like(full)
+    for r in range(3):
+        lo, hi = engine.shard_bounds(N, r, 3)
+        parts += eng.fwd_grad_mn(X[lo:hi], y[lo:hi], cw, theta, w, 0, 50.0, 1.0)
+    assert rel(parts, full) < 1e-5
+    # (4) the vector-Jacobian product is linear in the upstream gradient
+    d1 = torch.randn((N, C), device=DEV, generator=g)
+    d2 = torch.randn((N, C), device=DEV, generator=g)
+    b1 = eng.backward_mn(X, d1, theta, w, 0, 50.0, 1.0).clone()
+    b2 = eng.backward_mn(X, d2, theta, w, 0, 50.0, 1.0).clone()
+    b12 = eng.backward_mn(X, (0.5 * d1 + d2).contiguous(), theta, w, 0, 50.0, 1.0)
+    assert rel(b12[:-1], 0.5 * b1[:-1] + b2[:-1]) < 1e-5
+    # (5) loss bounds of the double softmax (SURVEY Appendix A): log(1 + (C-1)/e) <= CE <= log C at unit class weights
+    ones = dev(torch.ones(C))
+    for th in (theta, theta_star):
+        gs = eng.fwd_grad_mn(X, y, ones, th, w, 0, 50.0, 1.0)
+        ce = float(gs[-1]) / N
+        assert np.log(1 + (C - 1) / np.e) - 1e-6 <= ce <= np.log(C) + 1e-6, ce
+    # (6) with a zero class factor every logit is zero: P uniform, CE == log C, feature-factor gradients vanish
+    B_zero = [b.clone() for b in B0]
+    B_zero[-1].zero_()
+    gz = eng.fwd_grad_mn(X, y, ones, dev(O.pack(B_zero)), w, 0, 50.0, 1.0)
+    assert abs(float(gz[-1]) / N - np.log(C)) < 1e-9 and float(gz[:eng.P - C * R].abs().max()) == 0.0
+    del X
+    torch.cuda.empty_cache()
+
+
 def test_mn_model_autograd_matches_reference_autograd():
     from tensor_regression_b200 import multinomial_tensor_regression as MTR
     N, dims, C, R = 48, (5, 4, 6), 4, 3
