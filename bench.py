@@ -37,6 +37,8 @@ WORKLOADS = {
     'cfg3': ('mn', 62500, (100, 50, 20), 6, 10, torch.float32),
     'cfg4': ('std', 100000, (16, 16, 16, 32), 12, 0, torch.float64),
     'cfg5': ('mn', 312500, (100, 50, 20), 4, 4, torch.float32),
+    # diagnostic only (not a BASELINE config): the standard model on the cfg3 sample shape
+    'dbg3': ('std', 62500, (100, 50, 20), 6, 0, torch.float32),
 }
 DESCR = {
     'cfg1': 'standard CP regression, X (N=2000, 20,30,40), rank 5, fp32',
@@ -44,6 +46,7 @@ DESCR = {
     'cfg3': 'multinomial CP regression, X (N=62500 per GPU, 100,50,20), n_classes=10, rank 6, fp32',
     'cfg4': '5-mode standard CP regression, X (N=100000, 16,16,16,32), rank 12, fp64',
     'cfg5': 'multinomial CP regression, X (N=312500 per GPU, 100,50,20), n_classes=4, rank 4, fp32',
+    'dbg3': 'diagnostic: standard CP regression on the cfg3 sample shape, X (N=62500, 100,50,20), rank 6, fp32',
 }
 ADAM = {'lr': 0.01, 'amsgrad': True}
 LAMBDA = 0.01
@@ -152,7 +155,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 def make_device_data(wl, n_local, rank, device):
     kind, _, dims, R, C, dt = WORKLOADS[wl]
-    g = torch.Generator(device=device).manual_seed(1234 + int(wl[-1]) + 1000 * rank)
+    g = torch.Generator(device=device).manual_seed(1234 + int(wl[-1]) + 1000 * rank)   # (last character: config number)
     X = torch.empty((n_local, *dims), dtype=dt, device=device)
     step = max(1, (1 << 28) // int(np.prod(dims)))
     for lo in range(0, n_local, step):

@@ -117,14 +117,19 @@ __device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n
         ok = true;
 #pragma unroll
         for (int r = 0; r < TR_MAX_RANK_MN; ++r) u[r] = 0.0;
-#pragma unroll 4
-        for (int t = lane; t < a.WT; t += 32) {
+        // four tiles per step: their partials are pre-summed in T in a fixed order, ((a+b)+(c+d)), and only
+        // the sum is widened — the T -> double conversions (XU pipe) were 36 % of this kernel's issue slots
+        for (int t0 = lane; t0 < a.WT; t0 += 128) {
 #pragma unroll
             for (int r = 0; r < TR_MAX_RANK_MN; ++r)
                 if (r < R) {
-                    T v;
-                    ok &= rd.get(t, r, v);
-                    u[r] += (double)v;
+                    T v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        v[q] = (T)0;
+                        if (t0 + 32 * q < a.WT) ok &= rd.get(t0 + 32 * q, r, v[q]);
+                    }
+                    u[r] += (double)((v[0] + v[1]) + (v[2] + v[3]));
                 }
         }
     } while (!__all_sync(TR_FULL, ok));
