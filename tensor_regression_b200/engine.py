@@ -67,6 +67,8 @@ class Engine:
         self.launches = 0            # kernels launched through this engine (bench: gpu_launches)
 
     # -- plumbing -----------------------------------------------------------------------------
+    # (no torch.cuda.device(...) context around the calls: every entry point of the library selects its
+    # handle's device itself, and the context manager costs more host time than a whole small-problem launch)
     def _ck(self, rc):
         if rc != 0:
             raise TRError(f'libtrb200 error {rc}: {_lib.lib.tr_last_error(self._h).decode()}')
@@ -150,10 +152,9 @@ class Engine:
         X = self._x(X)
         N = X.shape[0]
         yhat = torch.empty(N, dtype=self.dtype, device=self.device)
-        with torch.cuda.device(self.device):
-            self._ck(_lib.lib.tr_forward_std(self._h, X.data_ptr(), N, self._vec(theta, self.P, 'theta').data_ptr(),
-                                             self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
-                                             yhat.data_ptr(), self._stream()))
+        self._ck(_lib.lib.tr_forward_std(self._h, X.data_ptr(), N, self._vec(theta, self.P, 'theta').data_ptr(),
+                                         self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
+                                         yhat.data_ptr(), self._stream()))
         self._count()
         return yhat
 
@@ -162,10 +163,9 @@ class Engine:
         N = X.shape[0]
         P = torch.empty((N, self.n_classes), dtype=self.dtype, device=self.device)
         pred = torch.empty(N, dtype=torch.int64, device=self.device) if want_pred else None
-        with torch.cuda.device(self.device):
-            self._ck(_lib.lib.tr_forward_mn(self._h, X.data_ptr(), N, self._vec(theta, self.P, 'theta').data_ptr(),
-                                            self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
-                                            P.data_ptr(), pred.data_ptr() if want_pred else None, self._stream()))
+        self._ck(_lib.lib.tr_forward_mn(self._h, X.data_ptr(), N, self._vec(theta, self.P, 'theta').data_ptr(),
+                                        self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
+                                        P.data_ptr(), pred.data_ptr() if want_pred else None, self._stream()))
         self._count()
         return P, pred
 
@@ -174,12 +174,11 @@ class Engine:
         N = X.shape[0]
         if gradsum is None:
             gradsum = torch.empty(self.n_gradsum, dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
-            self._ck(_lib.lib.tr_fwd_grad_std(self._h, X.data_ptr(), self._vec(y, N, 'y').data_ptr(), N,
-                                              self._vec(theta, self.P, 'theta').data_ptr(),
-                                              self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
-                                              self._vec(gradsum, self.n_gradsum, 'gradsum', torch.float64).data_ptr(),
-                                              yhat.data_ptr() if yhat is not None else None, self._stream()))
+        self._ck(_lib.lib.tr_fwd_grad_std(self._h, X.data_ptr(), self._vec(y, N, 'y').data_ptr(), N,
+                                          self._vec(theta, self.P, 'theta').data_ptr(),
+                                          self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
+                                          self._vec(gradsum, self.n_gradsum, 'gradsum', torch.float64).data_ptr(),
+                                          yhat.data_ptr() if yhat is not None else None, self._stream()))
         self._count()
         return gradsum
 
@@ -188,11 +187,10 @@ class Engine:
         N = X.shape[0]
         if gradsum is None:
             gradsum = torch.empty(self.n_gradsum, dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
-            self._ck(_lib.lib.tr_backward_std(self._h, X.data_ptr(), self._vec(dyhat, N, 'dyhat').data_ptr(), N,
-                                              self._vec(theta, self.P, 'theta').data_ptr(),
-                                              self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
-                                              gradsum.data_ptr(), self._stream()))
+        self._ck(_lib.lib.tr_backward_std(self._h, X.data_ptr(), self._vec(dyhat, N, 'dyhat').data_ptr(), N,
+                                          self._vec(theta, self.P, 'theta').data_ptr(),
+                                          self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
+                                          gradsum.data_ptr(), self._stream()))
         self._count()
         return gradsum
 
@@ -201,11 +199,10 @@ class Engine:
         N = X.shape[0]
         if gradsum is None:
             gradsum = torch.empty(self.n_gradsum, dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
-            self._ck(_lib.lib.tr_backward_mn(self._h, X.data_ptr(), self._vec(dP, N * self.n_classes, 'dP').data_ptr(), N,
-                                             self._vec(theta, self.P, 'theta').data_ptr(),
-                                             self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
-                                             gradsum.data_ptr(), self._stream()))
+        self._ck(_lib.lib.tr_backward_mn(self._h, X.data_ptr(), self._vec(dP, N * self.n_classes, 'dP').data_ptr(), N,
+                                         self._vec(theta, self.P, 'theta').data_ptr(),
+                                         self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
+                                         gradsum.data_ptr(), self._stream()))
         self._count()
         return gradsum
 
@@ -214,13 +211,12 @@ class Engine:
         N = X.shape[0]
         if gradsum is None:
             gradsum = torch.empty(self.n_gradsum, dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
-            self._ck(_lib.lib.tr_fwd_grad_mn(self._h, X.data_ptr(), self._vec(y, N, 'y', torch.int64).data_ptr(),
-                                             self._vec(class_w, self.n_classes, 'class weights').data_ptr(), N,
-                                             self._vec(theta, self.P, 'theta').data_ptr(),
-                                             self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
-                                             self._vec(gradsum, self.n_gradsum, 'gradsum', torch.float64).data_ptr(),
-                                             P.data_ptr() if P is not None else None, self._stream()))
+        self._ck(_lib.lib.tr_fwd_grad_mn(self._h, X.data_ptr(), self._vec(y, N, 'y', torch.int64).data_ptr(),
+                                         self._vec(class_w, self.n_classes, 'class weights').data_ptr(), N,
+                                         self._vec(theta, self.P, 'theta').data_ptr(),
+                                         self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
+                                         self._vec(gradsum, self.n_gradsum, 'gradsum', torch.float64).data_ptr(),
+                                         P.data_ptr() if P is not None else None, self._stream()))
         self._count()
         return gradsum
 
@@ -229,40 +225,35 @@ class Engine:
             grad = torch.empty(self.P, dtype=self.dtype, device=self.device)
         if loss is None:
             loss = torch.empty(2, dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
-            self._ck(_lib.lib.tr_finish_grad(self._h, gradsum.data_ptr(), float(grad_scale), float(loss_scale),
-                                             self._vec(theta, self.P, 'theta').data_ptr(), float(lambda_L2), nn_mask,
-                                             beta, thr, grad.data_ptr(), loss.data_ptr(), self._stream()))
+        self._ck(_lib.lib.tr_finish_grad(self._h, gradsum.data_ptr(), float(grad_scale), float(loss_scale),
+                                         self._vec(theta, self.P, 'theta').data_ptr(), float(lambda_L2), nn_mask,
+                                         beta, thr, grad.data_ptr(), loss.data_ptr(), self._stream()))
         self.launches += 1
         return grad, loss
 
     def adam_step(self, theta, grad, m, v, vmax, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
-        with torch.cuda.device(self.device):
-            self._ck(_lib.lib.tr_adam_step(self._h, theta.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(),
-                                           vmax.data_ptr() if vmax is not None else None, int(step), float(lr),
-                                           float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
-                                           self._stream()))
+        self._ck(_lib.lib.tr_adam_step(self._h, theta.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                       vmax.data_ptr() if vmax is not None else None, int(step), float(lr),
+                                       float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                       self._stream()))
         self.launches += 1
 
 
     # -- L-BFGS vector kernels (see lbfgs.py) ------------------------------------------------
     def lbfgs_direction(self, g, prev_g, d, t, first, S, Y, lstate, history, scal4):
-        with torch.cuda.device(self.device):
-            self._ck(_lib.lib.tr_lbfgs_direction(self._h, g.data_ptr(), prev_g.data_ptr(), d.data_ptr(), float(t),
-                                                 1 if first else 0, S.data_ptr(), Y.data_ptr(), lstate.data_ptr(),
-                                                 int(history), scal4.data_ptr(), self._stream()))
+        self._ck(_lib.lib.tr_lbfgs_direction(self._h, g.data_ptr(), prev_g.data_ptr(), d.data_ptr(), float(t),
+                                             1 if first else 0, S.data_ptr(), Y.data_ptr(), lstate.data_ptr(),
+                                             int(history), scal4.data_ptr(), self._stream()))
         self.launches += 1
 
     def lbfgs_point(self, out, x, t, d):
-        with torch.cuda.device(self.device):
-            self._ck(_lib.lib.tr_lbfgs_point(self._h, out.data_ptr(), x.data_ptr(), float(t), d.data_ptr(),
-                                             self._stream()))
+        self._ck(_lib.lib.tr_lbfgs_point(self._h, out.data_ptr(), x.data_ptr(), float(t), d.data_ptr(),
+                                         self._stream()))
         self.launches += 1
 
     def lbfgs_gtd(self, g, d, scal2):
-        with torch.cuda.device(self.device):
-            self._ck(_lib.lib.tr_lbfgs_gtd(self._h, g.data_ptr(), d.data_ptr() if d is not None else None,
-                                           scal2.data_ptr(), self._stream()))
+        self._ck(_lib.lib.tr_lbfgs_gtd(self._h, g.data_ptr(), d.data_ptr() if d is not None else None,
+                                       scal2.data_ptr(), self._stream()))
         self.launches += 1
 
 
