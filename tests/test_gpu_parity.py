@@ -874,3 +874,61 @@ def test_notebook_known_answer_through_the_cuda_path():
     assert max(abs(v - L[2]) for v in L[2:]) < 1e-9 * L[2]
     y_hat = cpmlr.predict(X[:64])
     assert y_hat.shape == (64,) and np.all(np.isfinite(y_hat))
+
+
+def test_randomised_geometry_sweep_vs_oracle():
+    """40 seeded random geometries per model (1-5 feature modes, odd sizes, ranks that need channel padding,
+    softplus masks, non-unit rank / class weights, N from 1 to a few hundred): packed sums through the C ABI
+    against the closed-form oracle in float64, and the fp32 kernels against the same at 1e-5."""
+    rng = np.random.default_rng(20261018)
+    for case in range(40):
+        k = int(rng.integers(1, 6))
+        dims = tuple(int(rng.integers(2, 9 if k > 2 else 24)) for _ in range(k))
+        R = int(rng.integers(1, 17))
+        N = int(rng.choice([1, 2, 3, 7, 33, 130, 257]))
+        dt = torch.float64 if case % 4 == 0 else torch.float32
+        tol = TOL[dt]
+        nn = [bool(rng.integers(0, 2)) for _ in range(k + 1)]
+        mask = sum(1 << i for i in range(k) if nn[i])
+        # ---- standard
+        X, y, _ = O.synth_std(N, dims, R, 9000 + case, dtype=dt)
+        y = y.reshape(-1)
+        B0 = O.init_std(dims, R, nn, dtype=dt)
+        bias = torch.tensor([float(rng.normal())], dtype=dt)
+        w = torch.tensor(rng.uniform(0.5, 1.5, R), dtype=dt)
+        eng = engine_for(dims, R, 0, dt)
+        gs = eng.fwd_grad_std(dev(X), dev(y), dev(O.pack(B0, bias)), dev(w), mask, 50.0, 1.0)
+        cf = O.closed_form_std(X.double(), y.double(), [b.double() for b in B0], bias.double(), w.double(), nn)
+        assert rel(gs, cf['gradsum']) < tol, ('std', case, dims, R, N, dt, rel(gs, cf['gradsum']))
+        # the single-pass cluster kernel and the dataflow kernel on the same geometry, where they are eligible
+        from tensor_regression_b200 import engine as _E
+        for opt in ('fused', 'flow'):
+            eng.set_option('fused', 0)
+            eng.set_option(opt, 1)
+            try:
+                alt = eng.fwd_grad_std(dev(X), dev(y), dev(O.pack(B0, bias)), dev(w), mask, 50.0, 1.0)
+            except _E.TRError:
+                alt = None                      # geometry / alignment not eligible: loud refusal, not a fallback
+            eng.set_option(opt, 0)
+            if alt is not None:
+                assert rel(alt, cf['gradsum']) < tol, (opt, case, dims, R, N, dt, rel(alt, cf['gradsum']))
+        # ---- multinomial (class factor last; its softplus flag is nn[k])
+        C = int(rng.integers(2, 12))
+        Xm, ym, _ = O.synth_mn(N, dims, R, C, 9500 + case)
+        Xm = Xm.to(dt)
+        Bm = [b.to(dt) for b in O.init_mn(list(dims) + [C], R, nn, scale=0.3)]
+        cw = torch.tensor(rng.uniform(0.5, 2.0, C), dtype=dt)
+        mask_mn = sum(1 << i for i in range(k + 1) if nn[i])
+        engm = engine_for(dims, R, C, dt)
+        P = torch.empty((N, C), dtype=dt, device=DEV)
+        gm = engm.fwd_grad_mn(dev(Xm), dev(ym), dev(cw), dev(O.pack(Bm)), dev(w), mask_mn, 50.0, 1.0, P=P)
+        cm = O.closed_form_mn(Xm.double(), ym, [b.double() for b in Bm], w.double(), nn, cw.double().numpy())
+        assert rel(P, cm['P']) < tol, ('mn P', case, dims, R, C, N, dt, rel(P, cm['P']))
+        assert rel(gm, cm['gradsum']) < tol, ('mn', case, dims, R, C, N, dt, rel(gm, cm['gradsum']))
+        engm.set_option('flow', 1)
+        try:
+            gf = engm.fwd_grad_mn(dev(Xm), dev(ym), dev(cw), dev(O.pack(Bm)), dev(w), mask_mn, 50.0, 1.0)
+        except _E.TRError:
+            gf = None
+        if gf is not None:
+            assert rel(gf, cm['gradsum']) < tol, ('mn flow', case, dims, R, C, N, dt, rel(gf, cm['gradsum']))
