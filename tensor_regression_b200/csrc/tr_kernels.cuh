@@ -69,6 +69,42 @@ template <typename T> __device__ __forceinline__ T tr_fma(T a, T b, T c);
 template <> __device__ __forceinline__ float tr_fma<float>(float a, float b, float c) { return fmaf(a, b, c); }
 template <> __device__ __forceinline__ double tr_fma<double>(double a, double b, double c) { return fma(a, b, c); }
 
+// Two independent fp32 FMAs in one instruction (sm_100 FFMA2, PTX fma.rn.f32x2): d.{x,y} = a.{x,y} * b.{x,y} +
+// d.{x,y}, each lane rounded like fmaf — same bits as two scalar FMAs, half the issue slots.  Used in the
+// forward contraction with several channels (issue-slot / latency limited); in the gradient pass it
+// measured slower (k_grad<6>: 4.71 ms vs 3.97 ms on cfg 3) and is not used there.
+__device__ __forceinline__ void tr_ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    unsigned long long d, a, b;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
+// vals[c] += x[v] * coef[v][c] for one 16-byte chunk: FFMA2 over the channel pairs (c, c+1) for float
+// (x[v] duplicated), scalar otherwise.  Every vals[c] sees the same sequence of FMAs either way.
+template <typename T, int VEC, int RK>
+struct ChunkDot {
+    static __device__ __forceinline__ void run(T* vals, const T (&x)[VEC], const T (&coef)[VEC][RK]) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+#pragma unroll
+            for (int c = 0; c < RK; ++c) vals[c] = tr_fma<T>(x[v], coef[v][c], vals[c]);
+    }
+};
+template <int RK>
+struct ChunkDot<float, 4, RK> {
+    static __device__ __forceinline__ void run(float* vals, const float (&x)[4], const float (&coef)[4][RK]) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+#pragma unroll
+            for (int c = 0; c + 1 < RK; c += 2) tr_ffma2(vals[c], vals[c + 1], x[v], x[v], coef[v][c], coef[v][c + 1]);
+            if (RK & 1) vals[RK - 1] = fmaf(x[v], coef[v][RK - 1], vals[RK - 1]);
+        }
+    }
+};
+
 // Sum M values (M a power of two <= 32) across the 32 lanes with M-1+(5-log2 M) shuffles instead
 // of 5*M: each halving step trades half of the values with the xor-partner.  On return v[0] in
 // lane l is the total of value index (l >> (5 - log2 M)).  Deterministic.
@@ -281,12 +317,7 @@ __global__ void __launch_bounds__(TR_TPB, TR_MINB) k_fwd(const FwdArgs<T> a) {
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
-                for (int j = 0; j < E; ++j)
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v)
-#pragma unroll
-                        for (int c = 0; c < RK; ++c)
-                            vals[u * RKR + c] = tr_fma<T>(x[u][j][v], coef[j][v][c], vals[u * RKR + c]);
+                for (int j = 0; j < E; ++j) ChunkDot<T, VEC, RK>::run(&vals[u * RKR], x[u][j], coef[j]);
             warp_reduce_transpose<T, M, NOSEL>(vals, lane);
             if ((lane & ((1 << (5 - LGM)) - 1)) == 0) {
                 const int q = lane >> (5 - LGM);
