@@ -295,8 +295,9 @@ __global__ void __launch_bounds__(TR_TPB, TR_MINB) k_fwd(const FwdArgs<T> a) {
 
         // ---- stream the group's samples ----
         const T* xbase = a.X + tile_base + (long long)lane * VEC;
-        for (long long n0 = g; n0 < a.N; n0 += (long long)U * a.Gn) {
-            T x[U][E][VEC];
+        T x[U][E][VEC];
+        // loads of the batch of U samples that starts at sample n0 (zeros past the end / past D)
+        auto issue = [&](long long n0) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const long long n = n0 + (long long)(u ^ mu) * a.Gn;
@@ -311,6 +312,10 @@ __global__ void __launch_bounds__(TR_TPB, TR_MINB) k_fwd(const FwdArgs<T> a) {
                     }
                 }
             }
+        };
+        const long long nstep = (long long)U * a.Gn;
+        if (g < a.N) issue(g);
+        for (long long n0 = g; n0 < a.N; n0 += nstep) {
             T vals[M];
 #pragma unroll
             for (int q = 0; q < M; ++q) vals[q] = (T)0;
@@ -318,6 +323,9 @@ __global__ void __launch_bounds__(TR_TPB, TR_MINB) k_fwd(const FwdArgs<T> a) {
             for (int u = 0; u < U; ++u)
 #pragma unroll
                 for (int j = 0; j < E; ++j) ChunkDot<T, VEC, RK>::run(&vals[u * RKR], x[u][j], coef[j]);
+            // the next batch's loads go out as soon as the FMAs have consumed x: they are in flight during
+            // the shuffle reduction and the partial stores below
+            if (n0 + nstep < a.N) issue(n0 + nstep);
             warp_reduce_transpose<T, M, NOSEL>(vals, lane);
             if ((lane & ((1 << (5 - LGM)) - 1)) == 0) {
                 const int q = lane >> (5 - LGM);
