@@ -932,3 +932,36 @@ def test_randomised_geometry_sweep_vs_oracle():
             gf = None
         if gf is not None:
             assert rel(gf, cm['gradsum']) < tol, ('mn flow', case, dims, R, C, N, dt, rel(gf, cm['gradsum']))
+
+
+def test_sample_larger_than_one_wave_of_warp_tiles():
+    """D so large that a sample has more warp tiles than the grid has warps (the persistent kernels then
+    loop over tiles): (1300, 1000) = 1.3 M elements per sample, both models, all eligible paths."""
+    from tensor_regression_b200 import engine as _E
+    dims, R, N = (1300, 1000), 2, 6
+    X, y, _ = O.synth_std(N, dims, R, 77)
+    y = y.reshape(-1)
+    nn = [False, False, False]
+    B0 = O.init_std(dims, R, nn)
+    bias, w = torch.tensor([0.3]), torch.ones(R)
+    eng = engine_for(dims, R, 0, torch.float32)
+    cf = O.closed_form_std(X.double(), y.double(), [b.double() for b in B0], bias.double(), w.double(), nn)
+    for opt in (None, 'fused', 'flow'):
+        eng.set_option('fused', 0)
+        eng.set_option('flow', 0)
+        try:
+            if opt:
+                eng.set_option(opt, 1)
+            yh = torch.empty(N, device=DEV)
+            gs = eng.fwd_grad_std(dev(X), dev(y), dev(O.pack(B0, bias)), dev(w), 0, 50.0, 1.0, yhat=yh)
+        except _E.TRError:
+            assert opt is not None           # the plain two-pass path must take any geometry
+            continue
+        assert rel(yh, cf['y_hat']) < 1e-5 and rel(gs, cf['gradsum']) < 1e-5, (opt, eng.launch_info())
+    C = 3
+    Xm, ym, _ = O.synth_mn(N, dims, R, C, 78)
+    Bm = O.init_mn(list(dims) + [C], R, nn + [False], scale=0.05)
+    engm = engine_for(dims, R, C, torch.float32)
+    cm = O.closed_form_mn(Xm.double(), ym, [b.double() for b in Bm], w.double(), nn + [False], np.ones(C))
+    gm = engm.fwd_grad_mn(dev(Xm), dev(ym), dev(torch.ones(C)), dev(O.pack(Bm)), dev(w), 0, 50.0, 1.0)
+    assert rel(gm, cm['gradsum']) < 1e-5, engm.launch_info()
