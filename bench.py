@@ -62,6 +62,32 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-rank runs: pin this process to the CPUs NVML reports as local to its GPU, so the pinned host
+    buffers of the e2e legs are first-touched on the GPU's own NUMA node (eight ranks streaming from the
+    wrong socket share one inter-socket link).  Returns the CPU count of the set, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = index
+        if vis:
+            ids = [v.strip() for v in vis.split(',') if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                phys = int(ids[index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w in range(words) for b in range(64) if (int(mask[w]) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region: NVML in a thread (a sample every
     few ms; the timed region of the default run is ~0.2 s), nvidia-smi -lms as the fallback."""
@@ -330,6 +356,7 @@ def main():
 
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU path)'
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     device = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
@@ -592,6 +619,7 @@ def main():
                           'l2_flush': 'not needed: X per GPU (%.1f GB) >> 126 MB L2' % (x_bytes / 1e9)
                           if x_bytes > (1 << 30) else 'X smaller than L2+: numbers are cache-assisted',
                           'parallelism': f'sample-sharded x{world}, one all-reduce of {n_gradsum} doubles/iter',
+                          'host_cpus_bound_to_gpu_numa_node': numa,
                           'launch': launch_info},
                'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches),
                'clocks': clocks, 'final_loss': final_loss}
