@@ -710,7 +710,10 @@ int mn_t(tr_handle* h, const void* X, const long long* y, const void* class_w, l
     ea.dZ_ws = train ? (T*)h->dZ_ws.p : nullptr; ea.part = train ? (double*)h->epi_part.p : nullptr;
     const int egrid = (int)std::min<long long>((N + TR_WPB - 1) / TR_WPB, (long long)h->sms * 8);
     const size_t esmem = (size_t)(g.C * g.R + g.R) * sizeof(double);
-    k_epi_mn<T><<<egrid, TR_TPB, esmem, st>>>(ea);
+    // loop bounds of the epilogue sized to the model (same arithmetic, fewer dead iterations and registers)
+    if (g.C <= 32 && g.R <= 8) k_epi_mn<T, 8, 1><<<egrid, TR_TPB, esmem, st>>>(ea);
+    else if (g.C <= 32) k_epi_mn<T, TR_MAX_RANK_MN, 1><<<egrid, TR_TPB, esmem, st>>>(ea);
+    else k_epi_mn<T, TR_MAX_RANK_MN, TR_JC><<<egrid, TR_TPB, esmem, st>>>(ea);
     TR_LAUNCH_CHECK(h);
     if (train) {
         k_colsum<<<1, 128, 0, st>>>((const double*)h->epi_part.p, egrid, 1, gradsum + g.pf);

@@ -105,23 +105,26 @@ struct EpiMnArgs {
 // model()'s softmax (mn:180-187), CrossEntropyLoss on the probabilities (second softmax, mn:364-366 /
 // 448-450) and its backward down to v[n,r], for sample n.  rd = reader of the sample's tile partials;
 // sFC (C,R) / sW (R) in shared memory (double).
-template <typename T, typename Reader>
+// RMAX >= R and 32*JC >= C are compile-time bounds of the unrolled loops (register arrays u[RMAX], z/P/dP/dZ[JC]):
+// the kernels are instantiated for (8,1), (16,1) and (TR_MAX_RANK_MN, TR_JC); the arithmetic on the live
+// entries — and therefore every bit of the result — does not depend on the bounds.
+template <typename T, typename Reader, int RMAX = TR_MAX_RANK_MN, int JC = TR_JC>
 __device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n, const Reader& rd, int lane,
                                               const double* sFC, const double* sW, double& loss) {
     const int R = a.R, C = a.C;
     // u[r] = sum over warp tiles: lane t-strided, all channels of a tile are contiguous, so every
     // lane keeps RKs independent accumulators and several tiles' loads in flight
-    double u[TR_MAX_RANK_MN];
+    double u[RMAX];
     bool ok;
     do {
         ok = true;
 #pragma unroll
-        for (int r = 0; r < TR_MAX_RANK_MN; ++r) u[r] = 0.0;
+        for (int r = 0; r < RMAX; ++r) u[r] = 0.0;
         // four tiles per step: their partials are pre-summed in T in a fixed order, ((a+b)+(c+d)), and only
         // the sum is widened — the T -> double conversions (XU pipe) were 36 % of this kernel's issue slots
         for (int t0 = lane; t0 < a.WT; t0 += 128) {
 #pragma unroll
-            for (int r = 0; r < TR_MAX_RANK_MN; ++r)
+            for (int r = 0; r < RMAX; ++r)
                 if (r < R) {
                     T v[4];
 #pragma unroll
@@ -134,19 +137,19 @@ __device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n
         }
     } while (!__all_sync(TR_FULL, ok));
 #pragma unroll
-    for (int r = 0; r < TR_MAX_RANK_MN; ++r)
+    for (int r = 0; r < RMAX; ++r)
         if (r < R) u[r] = warp_sum(u[r]);
     // logits of this lane's classes, softmax
-    double z[TR_JC], P[TR_JC];
+    double z[JC], P[JC];
     double zmax = -INFINITY;
 #pragma unroll
-    for (int jc = 0; jc < TR_JC; ++jc) {
+    for (int jc = 0; jc < JC; ++jc) {
         const int c = lane + 32 * jc;
         z[jc] = -INFINITY;
         if (c < C) {
             double s = 0.0;
 #pragma unroll
-            for (int r = 0; r < TR_MAX_RANK_MN; ++r)
+            for (int r = 0; r < RMAX; ++r)
                 if (r < R) s += sW[r] * u[r] * sFC[c * R + r];
             z[jc] = s;
             zmax = fmax(zmax, s);
@@ -155,7 +158,7 @@ __device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n
     zmax = warp_max(zmax);
     double zs = 0.0;
 #pragma unroll
-    for (int jc = 0; jc < TR_JC; ++jc) {
+    for (int jc = 0; jc < JC; ++jc) {
         const int c = lane + 32 * jc;
         P[jc] = c < C ? exp(z[jc] - zmax) : 0.0;
         zs += P[jc];
@@ -163,7 +166,7 @@ __device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n
     zs = warp_sum(zs);
     double pmax = -INFINITY;
 #pragma unroll
-    for (int jc = 0; jc < TR_JC; ++jc) {
+    for (int jc = 0; jc < JC; ++jc) {
         const int c = lane + 32 * jc;
         P[jc] = P[jc] / zs;
         if (c < C) {
@@ -176,7 +179,7 @@ __device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n
     if (a.pred) {                                // first index of the maximum (np.argmax, mn:527)
         int best = 1 << 30;
 #pragma unroll
-        for (int jc = 0; jc < TR_JC; ++jc) {
+        for (int jc = 0; jc < JC; ++jc) {
             const int c = lane + 32 * jc;
             if (c < C && P[jc] == pmax && c < best) best = c;
         }
@@ -186,21 +189,21 @@ __device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n
     }
     if (a.y == nullptr && a.dP_in == nullptr) return;
 
-    double dP[TR_JC], dot = 0.0;
+    double dP[JC], dot = 0.0;
     if (a.dP_in) {
         // vector-Jacobian product for an arbitrary upstream gradient wrt P (autograd of model, mn:180-187)
 #pragma unroll
-        for (int jc = 0; jc < TR_JC; ++jc) {
+        for (int jc = 0; jc < JC; ++jc) {
             const int c = lane + 32 * jc;
             dP[jc] = c < C ? (double)a.dP_in[n * C + c] : 0.0;
             dot += dP[jc] * P[jc];
         }
     } else {
         // second softmax (CrossEntropyLoss applied to probabilities, mn:364-366 / 448-450)
-        double Q[TR_JC];
+        double Q[JC];
         double qs = 0.0;
 #pragma unroll
-        for (int jc = 0; jc < TR_JC; ++jc) {
+        for (int jc = 0; jc < JC; ++jc) {
             const int c = lane + 32 * jc;
             Q[jc] = c < C ? exp(P[jc] - pmax) : 0.0;
             qs += Q[jc];
@@ -209,7 +212,7 @@ __device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n
         const int yn = (int)a.y[n];
         const double omega = a.class_w ? (double)a.class_w[yn] : 1.0;
 #pragma unroll
-        for (int jc = 0; jc < TR_JC; ++jc) {
+        for (int jc = 0; jc < JC; ++jc) {
             const int c = lane + 32 * jc;
             dP[jc] = 0.0;
             if (c < C) {
@@ -221,20 +224,20 @@ __device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n
         }
     }
     dot = warp_sum(dot);
-    double dZ[TR_JC];
+    double dZ[JC];
 #pragma unroll
-    for (int jc = 0; jc < TR_JC; ++jc) {
+    for (int jc = 0; jc < JC; ++jc) {
         const int c = lane + 32 * jc;
         dZ[jc] = c < C ? P[jc] * (dP[jc] - dot) : 0.0;
         if (c < C && a.dZ_ws) a.dZ_ws[n * C + c] = (T)dZ[jc];
     }
     // v[r] = w_r sum_c dZ[c] FC[c,r]
 #pragma unroll
-    for (int r = 0; r < TR_MAX_RANK_MN; ++r) {
+    for (int r = 0; r < RMAX; ++r) {
         if (r < R) {
             double s = 0.0;
 #pragma unroll
-            for (int jc = 0; jc < TR_JC; ++jc) {
+            for (int jc = 0; jc < JC; ++jc) {
                 const int c = lane + 32 * jc;
                 if (c < C) s += dZ[jc] * sFC[c * R + r];
             }
@@ -248,7 +251,7 @@ __device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n
     if (a.V && lane >= R && lane < a.RKs) a.V[n * a.RKs + lane] = (T)0;   // padding channels
 }
 
-template <typename T>
+template <typename T, int RMAX = TR_MAX_RANK_MN, int JC = TR_JC>
 __global__ void __launch_bounds__(TR_TPB, 3) k_epi_mn(const EpiMnArgs<T> a) {
     extern __shared__ __align__(16) unsigned char tr_smem[];
     double* sFC = reinterpret_cast<double*>(tr_smem);      // C*R
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(TR_TPB, 3) k_epi_mn(const EpiMnArgs<T> a) {
     double loss = 0.0;
     for (long long n = warp_global; n < a.N; n += wtot) {
         const PlainPartials<T> rd{a.partial + n * a.WT * a.RKs, a.RKs};
-        epi_mn_sample<T>(a, n, rd, lane, sFC, sW, loss);
+        epi_mn_sample<T, PlainPartials<T>, RMAX, JC>(a, n, rd, lane, sFC, sW, loss);
     }
     const double tl = block_sum(loss, sbuf);
     if (threadIdx.x == 0 && a.part) a.part[blockIdx.x] = tl;
