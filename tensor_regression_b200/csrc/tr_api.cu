@@ -77,6 +77,7 @@ struct Plan {
 
 struct tr_handle {
     int dtype = 0, device = 0, sms = 0;
+    size_t l2_bytes = 0;
     size_t elt = 4;
     Geo geo;
     std::string err;
@@ -625,8 +626,11 @@ int fwd_grad_std_t(tr_handle* h, const void* X, const void* y, long long N, cons
     if (!backward_only && h->fused_mode != 0) {
         FusedPlan fp;
         if ((rc = plan_fused<T>(h, N, X, &fp))) return rc;
-        // auto: the single-pass kernel pays once every cluster has a few samples to pipeline
-        const bool want = fp.CL > 0 && (h->fused_mode == 1 || N >= 8LL * fp.NC);
+        // auto: the single-pass kernel pays once every cluster has a few samples to pipeline AND X is well beyond
+        // L2: up to ~3 x L2 the second pass of the two-pass kernels is served largely from L2 and beats the cluster
+        // kernel's prologue (measured on (N, 20,30,40): crossover between 192 MB and 768 MB of X)
+        const bool big = (size_t)N * (size_t)g.D * sizeof(T) >= 3 * h->l2_bytes;
+        const bool want = fp.CL > 0 && (h->fused_mode == 1 || (N >= 8LL * fp.NC && big));
         if (h->fused_mode == 1 && fp.CL == 0)
             return fail(h, TR_ERR_UNSUPPORTED, "fused=1 requested but this geometry / alignment is not eligible for the single-pass kernel");
         if (want) {
@@ -785,6 +789,7 @@ int tr_create(tr_handle** out, int dtype, int k, const int64_t* dims, int R, int
     if (e != cudaSuccess) { delete h; return fail(nullptr, TR_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
     if (prop.major < 10) { delete h; return fail(nullptr, TR_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); }
     h->sms = prop.multiProcessorCount;
+    h->l2_bytes = (size_t)prop.l2CacheSize;
     if (const char* ev = getenv("TR_B200_FUSED")) h->fused_mode = atoi(ev) < 0 ? -1 : (atoi(ev) > 0 ? 1 : 0);
     if (const char* ev = getenv("TR_B200_FUSED_PACE")) h->fused_pace = atoi(ev);
     if (const char* ev = getenv("TR_B200_FUSED_PIECE")) { const int v = atoi(ev); if (v >= 16 && v % 16 == 0) h->fused_piece = v; }
