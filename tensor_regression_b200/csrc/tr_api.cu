@@ -332,9 +332,9 @@ int plan_fused(tr_handle* h, long long N, const void* X, FusedPlan* fp) {
     const size_t fixed = ((((sizeof(FusedCtl) + 15) / 16) * 16 + (size_t)(g.pfeat + g.R) * sizeof(T)) + 1023) / 1024 * 1024;
     const size_t budget = 226 * 1024;
     for (int CL = 1; CL <= TR_FUSED_MAX_CL; CL *= 2) {
-        if (g.D % ((long long)CL * VEC) != 0) continue;
-        const long long Dc = g.D / CL;
-        const long long chunks = Dc / VEC;
+        // ragged slices: the first (D/VEC mod CL) CTAs of a cluster hold one 16-byte chunk more
+        const long long chunks = (g.D / VEC + CL - 1) / CL;
+        const long long Dc = chunks * VEC;
         const int E = (int)((chunks + TR_FUSED_NCT - 1) / TR_FUSED_NCT);
         if (E > 16) continue;
         const size_t stage = (size_t)Dc * sizeof(T);

@@ -45,11 +45,12 @@ struct FusedArgs {
     T* res;              // (N) residuals y_hat - y out (loss sums are formed from it by k_ressum)
     int CL;              // CTAs per cluster
     int NC;              // clusters in the grid
-    int Dc;              // feature elements per CTA slice (D / CL)
+    int Dc;              // feature elements of the LARGEST CTA slice: ceil(D/VEC / CL) * VEC (slices are ragged when
+                         // D/VEC is not a multiple of CL; the shared-memory stage stride is this size)
     int NS;              // shared-memory stages per CTA (>= 3)
     int nchunk;          // G is flushed to a fresh slot every spc samples (bounds fp32 sum length)
     long long spc;
-    unsigned stage_bytes;  // Dc * sizeof(T), multiple of 16
+    unsigned stage_bytes;  // Dc * sizeof(T), multiple of 16 (stage stride; a CTA loads its own slice's bytes)
     unsigned piece;        // bytes per cp.async.bulk instruction (multiple of 16)
     int pace;              // minimum cycles between two TMA issues of a CTA (anti-bunching), 0 = off
     long long* trace;      // debug (tools/fused_trace.cu): clock64 stamps of cluster 0 / rank 0, else null
@@ -223,12 +224,19 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
     // samples of this cluster: n = cid + j*NC, j = 0..cnt-1.  All ring positions and mbarrier phase
     // bits are carried incrementally (no 64-bit division in the sample loop).
     const int cnt = cid < a.N ? (int)((a.N - cid + a.NC - 1) / a.NC) : 0;
+    // this CTA's slice of the feature axis, in 16-byte chunks: the first (D/VEC mod CL) ranks hold one more
+    const int chunks_total = (int)(a.geo.D / VEC);
+    const int cq = chunks_total / a.CL, crem = chunks_total % a.CL;
+    const int my_chunks = cq + ((int)crank < crem ? 1 : 0);
+    const long long my_off = ((long long)crank * cq + ((int)crank < crem ? (int)crank : crem)) * VEC;   // elements
+    const int my_elems = my_chunks * VEC;
+    const unsigned my_bytes = (unsigned)my_elems * (unsigned)sizeof(T);
     const size_t sample_stride = (size_t)a.NC * (size_t)a.geo.D;      // elements between this cluster's samples
 
     if (wid == 2 * NWC) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
-            const T* src = a.X + (size_t)cid * (size_t)a.geo.D + (size_t)crank * a.Dc;
+            const T* src = a.X + (size_t)cid * (size_t)a.geo.D + (size_t)my_off;
             int s = 0;
             unsigned ph = 0;                       // parity of the empty-phase to wait for (from the 2nd lap on)
             long long t_next = clock64();
@@ -241,11 +249,11 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
                     t_next = clock64() + a.pace;
                 }
                 TR_TRACE(0, j);
-                trf::mbar_arrive_expect_tx(&ctl->full[s], a.stage_bytes);
+                trf::mbar_arrive_expect_tx(&ctl->full[s], my_bytes);
                 const unsigned char* sp = reinterpret_cast<const unsigned char*>(src);
                 unsigned char* dst = reinterpret_cast<unsigned char*>(stage0) + (size_t)s * a.stage_bytes;
-                for (unsigned off = 0; off < a.stage_bytes; off += a.piece) {
-                    const unsigned len = a.stage_bytes - off < a.piece ? a.stage_bytes - off : a.piece;
+                for (unsigned off = 0; off < my_bytes; off += a.piece) {
+                    const unsigned len = my_bytes - off < a.piece ? my_bytes - off : a.piece;
                     trf::bulk_g2s(dst + off, sp + off, len, &ctl->full[s]);
                 }
                 src += sample_stride;
@@ -304,7 +312,7 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
         // ============================ forward warps: phase A ============================
         T coef[E][VEC];
         unsigned cmask = 0;
-        const int chunks = a.Dc / VEC;
+        const int chunks = my_chunks;
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             const int ch = j * NCT + tid;
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
                 T tmp[1] = {(T)0};
                 if (ch < chunks) {
                     cmask |= 1u << j;
-                    const unsigned i = (unsigned)((long long)crank * a.Dc + (long long)ch * VEC + v);
+                    const unsigned i = (unsigned)(my_off + (long long)ch * VEC + v);
                     tr_coef_at<T, 1>(sF, sF + pfeat, ctl->dims, ctl->foff, k, R, 0, i, tmp);
                 }
                 coef[j][v] = tmp[0];
@@ -364,7 +372,7 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
         const int tb = tid - NCT;                                       // 0 .. NCT-1
         T acc[E][VEC];
         unsigned cmask = 0;
-        const int chunks = a.Dc / VEC;
+        const int chunks = my_chunks;
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             if (j * NCT + tb < chunks) cmask |= 1u << j;
@@ -387,7 +395,7 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
         int sB = 0;
         unsigned phB = 0;
         int left = (int)(a.spc < cnt ? a.spc : cnt);                    // samples until the next flush of G
-        T* gp = a.Gpart + (size_t)cid * a.nchunk * (size_t)a.Dpad + (size_t)crank * a.Dc + (size_t)tb * VEC;
+        T* gp = a.Gpart + (size_t)cid * a.nchunk * (size_t)a.Dpad + (size_t)my_off + (size_t)tb * VEC;
         for (int i = 0; i < cnt; ++i) {
             trf::mbar_wait(&ctl->rready[sB], phB);                     // all lanes wait (see phase A)
             __syncwarp();
@@ -420,8 +428,8 @@ __global__ void __launch_bounds__(TR_FUSED_NT, 1) k_fused_std(const FusedArgs<T>
         // slots of chunks this cluster never reached must still be defined for the reduction
         const int used = cnt > 0 ? (int)((cnt - 1) / a.spc) + 1 : 0;
         for (int c2 = used; c2 < a.nchunk; ++c2) {
-            T* gz = a.Gpart + ((size_t)cid * a.nchunk + c2) * (size_t)a.Dpad + (size_t)crank * a.Dc;
-            for (int e = tb; e < a.Dc; e += NCT) gz[e] = (T)0;
+            T* gz = a.Gpart + ((size_t)cid * a.nchunk + c2) * (size_t)a.Dpad + (size_t)my_off;
+            for (int e = tb; e < my_elems; e += NCT) gz[e] = (T)0;
         }
     }
     // no CTA may exit while a peer can still write into its shared memory

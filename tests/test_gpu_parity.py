@@ -408,6 +408,8 @@ FUSED_CASES = [
     ('single_sample', 1, (64, 64, 32), 2, torch.float32),
     ('fewer_samples_than_clusters', 5, (32, 16, 8), 2, torch.float64),
     ('long_sums_chunked', 40000, (16, 16), 3, torch.float32),
+    ('ragged_slices_cl16_demo_shape_f32', 150, (500, 500), 3, torch.float32),     # 62 500 chunks over 16 CTAs
+    ('ragged_slices_f64', 70, (300, 333), 2, torch.float64),                      # 49 950 chunks over 16 CTAs
 ]
 
 
