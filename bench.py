@@ -565,8 +565,7 @@ def main():
         del pool, m2
 
     # ---- the call a user makes: one fit_Adam(X_host, ...) of K iterations, X uploaded ONCE inside the
-    # timed region (pinned, double-buffered) and then resident.  Reported next to the strict e2e number
-    # above (which re-streams X over PCIe on every iteration); the original X is freed first.
+    # timed region (pinned, double-buffered) and then resident.  The original X is freed first.
     if e2e is not None and e2e.get('value') is not None:
         pool_n = int(min(n_local, max(256, (2 << 30) // (D * elt))))
         pool = torch.empty((pool_n, *dims), dtype=dt, pin_memory=True)
@@ -599,10 +598,22 @@ def main():
         if world > 1:
             dist.all_reduce(tc, op=dist.ReduceOp.MAX)
         call_s = float(tc.item())
-        e2e['fit_call'] = {'value': n_total * K / call_s, 'unit': 'samples/s', 'iterations': K, 'seconds': call_s,
-                           'h2d_bytes_total': int(x_bytes), 'final_loss': float(m3.loss_running[-1]),
-                           'api': 'one fit_Adam(X_host, y, max_iter=K) call: construction, ONE pinned double-buffered '
-                                  'upload of X, K resident iterations, one loss read per iteration'}
+        # e2e.value = the reference-facing call with HOST buffers (the reference's own fit_Adam signature, nothing
+        # resident beforehand, every host<->device copy inside the timed region).  The variant that re-streams X
+        # on every iteration (our out_of_core extension, for X larger than HBM) is kept beside it.
+        streaming = e2e
+        y_bytes = n_local * (elt if kind == 'std' else 8)
+        e2e = {'value': n_total * K / call_s, 'unit': 'samples/s',
+               'h2d_bytes_per_step': int((x_bytes + y_bytes) // K), 'd2h_bytes_per_step': 8,
+               'iterations': K, 'seconds': call_s, 'ms_per_step': call_s * 1e3 / K,
+               'h2d_bytes_total': int(x_bytes + y_bytes), 'final_loss': float(m3.loss_running[-1]),
+               'api': ('CP_linear_regression(...).fit_Adam(X_host, y_host, max_iter=K)' if kind == 'std' else
+                       'CP_logistic_regression(X_host, y_host, ...).fit_Adam(max_iter=K)') +
+                      ': ONE call with the reference signature and K = --steps iterations, timed from construction to '
+                      'return: one pinned double-buffered upload of X and y (h2d_bytes_total; h2d_bytes_per_step is '
+                      'that total / K), K resident fit iterations, one 8-byte loss read per iteration',
+               'host_buffer': streaming['host_buffer'],
+               'streaming_every_iteration': streaming}
         del pool, m3
 
     cpu = None
