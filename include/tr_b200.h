@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define TR_B200_VERSION 100
+#define TR_B200_VERSION 200
 
 enum { TR_F32 = 0, TR_F64 = 1 };
 enum { TR_OK = 0, TR_ERR_INVALID = 1, TR_ERR_CUDA = 2, TR_ERR_UNSUPPORTED = 3, TR_ERR_NOMEM = 4 };
@@ -126,6 +126,29 @@ int tr_finish_grad(tr_handle* h, const double* gradsum, double grad_scale, doubl
 int tr_adam_step(tr_handle* h, void* theta, const void* grad, void* m, void* v, void* vmax,
                  int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
                  void* stream);
+
+/* Same step with one learning rate per parameter group, the groups being the factors of theta in order
+ * (feature factors, class factor) plus, for the standard model, the bias: the three Adam parameter groups of
+ * multinomial_tensor_regression_hierarchical.py (hier:436-440) are lr_groups = {lr, lr, lr}.  lr_groups is a
+ * HOST array of n_groups doubles; n_groups must equal k + 1 (multinomial: k feature factors + class factor;
+ * standard: k factors + bias). */
+int tr_adam_step_groups(tr_handle* h, void* theta, const void* grad, void* m, void* v, void* vmax, int64_t step,
+                        const double* lr_groups, int n_groups, double beta1, double beta2, double eps,
+                        double weight_decay, void* stream);
+
+/* Cross-GPU sum of `count` doubles in place (the packed gradsum, one call per closure evaluation):
+ * ncclAllReduce(sum, float64) on `stream`.  nccl_comm is an ncclComm_t — either the host framework's (PyTorch:
+ * ProcessGroupNCCL._comm_ptr()) or one made by tr_comm_create.  NCCL is resolved with dlopen at first use
+ * (the copy already loaded in the process, else libnccl.so.2, else $TR_B200_NCCL_LIB); single-GPU hosts never
+ * need it.  The reference has no multi-GPU path; this is the one collective of the sharded fit. */
+int tr_allreduce(tr_handle* h, double* buf, int64_t count, void* nccl_comm, void* stream);
+
+/* Communicator for hosts without a framework: rank 0 calls tr_comm_unique_id (fills 128 HOST bytes), ships them
+ * to the other ranks by any means, then every rank calls tr_comm_create(&comm, id128, rank, world, device).
+ * On failure the message is available from tr_last_error(NULL). */
+int tr_comm_unique_id(void* id128);
+int tr_comm_create(void** comm, const void* id128, int rank, int world, int device);
+int tr_comm_destroy(void* comm);
 
 /* L-BFGS building blocks (torch.optim.LBFGS as used by fit, std:366,392 / mn:355,381; algorithm of
  * torch/optim/lbfgs.py:333-536).  The update history, the two-loop recursion and every dot

@@ -13,6 +13,7 @@ SYMBOLS = [
     'tr_reserve', 'tr_forward_std', 'tr_forward_mn', 'tr_fwd_grad_std', 'tr_fwd_grad_mn',
     'tr_backward_std', 'tr_backward_mn', 'tr_finish_grad', 'tr_adam_step', 'tr_last_launch_info', 'tr_profile_enable',
     'tr_profile_read', 'tr_set_option', 'tr_lbfgs_direction', 'tr_lbfgs_point', 'tr_lbfgs_gtd',
+    'tr_adam_step_groups', 'tr_allreduce', 'tr_comm_unique_id', 'tr_comm_create', 'tr_comm_destroy',
 ]
 
 
@@ -44,6 +45,11 @@ def _load():
     lib.tr_backward_mn.argtypes = [vp, vp, vp, i64, vp, vp, u32, dbl, dbl, vp, vp]
     lib.tr_finish_grad.argtypes = [vp, vp, dbl, dbl, vp, dbl, u32, dbl, dbl, vp, vp, vp]
     lib.tr_adam_step.argtypes = [vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, dbl, dbl, vp]
+    lib.tr_adam_step_groups.argtypes = [vp, vp, vp, vp, vp, vp, i64, ctypes.POINTER(dbl), i32, dbl, dbl, dbl, dbl, vp]
+    lib.tr_allreduce.argtypes = [vp, vp, i64, vp, vp]
+    lib.tr_comm_unique_id.argtypes = [vp]
+    lib.tr_comm_create.argtypes = [ctypes.POINTER(vp), vp, i32, i32, i32]
+    lib.tr_comm_destroy.argtypes = [vp]
     lib.tr_last_launch_info.argtypes = [vp, ctypes.POINTER(i64)]
     lib.tr_profile_enable.argtypes = [vp, i32]
     lib.tr_profile_read.argtypes = [vp, ctypes.POINTER(dbl)]

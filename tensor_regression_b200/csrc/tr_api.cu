@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -141,12 +143,31 @@ int ensure(tr_handle* h, Buf& b, size_t bytes) {
     return TR_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (device, kernel), not of a handle: two handles
+// that use the same instantiation with different shared-memory sizes must never LOWER it under each other.
+// The library keeps a process-wide high-water mark per (device, kernel) and only ever raises the attribute;
+// every launch site calls this right before its launch.
+template <typename K>
+int raise_smem_limit(tr_handle* h, K kern, size_t smem) {
+    if (smem <= 48 * 1024) return TR_OK;
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> high;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& cur = high[std::make_pair(h->device, (const void*)kern)];
+    if (smem > cur) {
+        TR_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
+    return TR_OK;
+}
+
 template <typename K>
 int occupancy(tr_handle* h, K kern, size_t smem, int* out) {
-    const void* key = (const void*)kern;
+    // occupancy depends on the shared-memory size of THIS handle's launches: keyed by (kernel, smem)
+    const void* key = (const void*)((uintptr_t)kern ^ ((uintptr_t)smem << 20));
     auto it = h->occ.find(key);
     if (it != h->occ.end()) { *out = it->second; return TR_OK; }
-    if (smem > 48 * 1024) TR_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int rc = raise_smem_limit(h, kern, smem); if (rc) return rc; }
     int nb = 0;
     TR_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, TR_TPB, smem));
     if (nb < 1) return fail(h, TR_ERR_UNSUPPORTED, "kernel does not fit on an SM (dynamic smem %zu bytes)", smem);
@@ -256,6 +277,7 @@ int run_forward(tr_handle* h, const T* X, long long N, const T* theta, const T* 
     fa.X = X; fa.N = N; fa.FtT = (const T*)h->FtT.p; fa.w = w; fa.geo = g;
     fa.partial = (T*)h->partial.p; fa.WT = pl.WT; fa.Gn = pl.Gn_f; fa.mode = g.C > 0 ? 1 : 0;
     auto kern = pl.vec ? e->fwd_vec : e->fwd_sc;
+    { int rc = raise_smem_limit(h, kern, pl.smem_f); if (rc) return rc; }
     if (h->prof) { int rc = prof_fold(h, false); if (rc) return rc; TR_CUDA(h, cudaEventRecord(h->ev[0], st)); }
     kern<<<pl.grid_f, TR_TPB, pl.smem_f, st>>>(fa);
     TR_LAUNCH_CHECK(h);
@@ -344,13 +366,13 @@ int plan_fused(tr_handle* h, long long N, const void* X, FusedPlan* fp) {
         auto kern = fused_kernel<T>(E);
         const size_t smem = fixed + (size_t)NS * stage;
         // resident clusters of this (kernel, cluster size): queried once per handle
-        const void* key = (const void*)((uintptr_t)kern + (uintptr_t)CL);
+        const void* key = (const void*)(((uintptr_t)kern + (uintptr_t)CL) ^ ((uintptr_t)smem << 20));
         int NC = 0;
         auto it = h->occ_clusters.find(key);
         if (it != h->occ_clusters.end()) {
             NC = it->second;
         } else {
-            TR_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            { int rc = raise_smem_limit(h, kern, smem); if (rc) return rc; }
             if (CL > 8) {
                 if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); h->occ_clusters[key] = 0; continue; }
             }
@@ -405,6 +427,7 @@ int run_fused_std(tr_handle* h, const T* X, const T* y, long long N, const T* th
     fa.pace = h->fused_pace;
     fa.piece = (unsigned)h->fused_piece;
     auto kern = fused_kernel<T>(fp.E);
+    if ((rc = raise_smem_limit(h, kern, fp.smem))) return rc;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(fp.CL * fp.NC), 1, 1);
     cfg.blockDim = dim3(TR_FUSED_NT, 1, 1);
@@ -444,12 +467,13 @@ template <typename T>
 int launch_dfc(tr_handle* h, int dgrid, const T* w, long long N, cudaStream_t st) {
     const Geo& g = h->geo;
     const size_t smem = (size_t)4 * g.C * g.R * sizeof(double);
-    if (smem > 48 * 1024) TR_CUDA(h, cudaFuncSetAttribute(k_dfc<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int rc = raise_smem_limit(h, k_dfc<T>, smem); if (rc) return rc; }
     k_dfc<T><<<dgrid, TR_TPB, smem, st>>>((const T*)h->dZ_ws.p, (const T*)h->u_ws.p, w, N, g.C, g.R, (double*)h->dfc_part.p);
     TR_LAUNCH_CHECK(h);
     return TR_OK;
 }
 
+#ifdef TR_WITH_FLOW
 // ---------------------------------------------------------------------------------------------
 // single-launch dataflow path (tr_flow.cuh): plan + launch
 // ---------------------------------------------------------------------------------------------
@@ -557,6 +581,7 @@ int run_flow(tr_handle* h, const T* X, const void* y, const T* class_w, long lon
     if (h->prof) { rc = prof_fold(h, false); if (rc) return rc; TR_CUDA(h, cudaEventRecord(h->ev[4], st)); }
     {
         // blocks wait on one another: a cooperative launch guarantees that the whole grid is resident
+        if ((rc = raise_smem_limit(h, e->flow_vec, fp.smem))) return rc;
         void* kargs[] = {(void*)&fa};
         TR_CUDA(h, cudaLaunchCooperativeKernel((const void*)e->flow_vec, dim3((unsigned)fp.grid), dim3(TR_TPB), kargs,
                                                fp.smem, st));
@@ -592,6 +617,8 @@ int run_flow(tr_handle* h, const T* X, const void* y, const T* class_w, long lon
     h->last_fused = 2;
     return TR_OK;
 }
+
+#endif  // TR_WITH_FLOW
 
 void set_info(tr_handle* h, const Plan& pl) {
     h->info[0] = h->launches; h->info[1] = pl.grid_f; h->info[2] = pl.grid_g; h->info[3] = pl.WT;
@@ -640,6 +667,7 @@ int fwd_grad_std_t(tr_handle* h, const void* X, const void* y, long long N, cons
                                     fp, gradsum, (T*)yhat, st);
         }
     }
+#ifdef TR_WITH_FLOW
     if (!backward_only && h->flow_mode == 1) {
         FlowPlan fl; const KEntry<T>* fe = nullptr;
         if ((rc = plan_flow<T>(h, N, 1, X, &fl, &fe))) return rc;
@@ -651,6 +679,7 @@ int fwd_grad_std_t(tr_handle* h, const void* X, const void* y, long long N, cons
                                fl, fe, gradsum, (T*)yhat, st);
         }
     }
+#endif
     if ((rc = make_plan<T>(h, N, 1, vec_ok(X, g.D, sizeof(T)), &pl, &e))) return rc;
     if ((rc = reserve_for<T>(h, N, pl))) return rc;
     h->launches = 0;
@@ -689,6 +718,7 @@ int mn_t(tr_handle* h, const void* X, const long long* y, const void* class_w, l
     Plan pl; const KEntry<T>* e; int rc;
     const Geo& g = h->geo;
     h->last_fused = 0;
+#ifdef TR_WITH_FLOW
     if (y != nullptr && dP_in == nullptr && pred == nullptr && h->flow_mode == 1) {
         FlowPlan fl; const KEntry<T>* fe = nullptr;
         if ((rc = plan_flow<T>(h, N, g.R, X, &fl, &fe))) return rc;
@@ -700,6 +730,7 @@ int mn_t(tr_handle* h, const void* X, const long long* y, const void* class_w, l
                                fl, fe, gradsum, (T*)P, st);
         }
     }
+#endif
     if ((rc = make_plan<T>(h, N, g.R, vec_ok(X, g.D, sizeof(T)), &pl, &e))) return rc;
     if ((rc = reserve_for<T>(h, N, pl))) return rc;
     h->launches = 0;
@@ -953,26 +984,138 @@ int tr_finish_grad(tr_handle* h, const double* gradsum, double grad_scale, doubl
     return TR_OK;
 }
 
-int tr_adam_step(tr_handle* h, void* theta, const void* grad, void* m, void* v, void* vmax, int64_t step,
-                 double lr, double beta1, double beta2, double eps, double weight_decay, void* stream) {
+static int adam_launch(tr_handle* h, void* theta, const void* grad, void* m, void* v, void* vmax, int64_t step,
+                       double lr, const double* lr_groups, int n_groups, double beta1, double beta2, double eps,
+                       double weight_decay, void* stream) {
     if (!h) return TR_ERR_INVALID;
     if (!theta || !grad || !m || !v) return fail(h, TR_ERR_INVALID, "null pointer argument");
     if (step < 1) return fail(h, TR_ERR_INVALID, "step is 1-based (got %lld)", (long long)step);
     DeviceGuard dg(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    const long long P = h->geo.pf + (h->geo.C == 0 ? 1 : 0);
+    const Geo& g = h->geo;
+    const long long P = g.pf + (g.C == 0 ? 1 : 0);
     const double bc1 = 1.0 - pow(beta1, (double)step);
     const double bc2 = 1.0 - pow(beta2, (double)step);
-    const double step_size = lr / bc1;
     const double bc2_sqrt = sqrt(bc2);
+    AdamGroups ag;
+    memset(&ag, 0, sizeof(ag));
+    if (lr_groups) {
+        // one group per factor in theta order (feature factors, class factor) and, standard model, the bias
+        const int nfac = g.k + (g.C > 0 ? 1 : 0);
+        const int want = nfac + (g.C == 0 ? 1 : 0);
+        if (n_groups != want)
+            return fail(h, TR_ERR_INVALID, "tr_adam_step_groups: %d learning rates given, this model has %d parameter groups", n_groups, want);
+        ag.n_seg = want;
+        for (int i = 0; i < nfac; ++i) ag.seg_end[i] = (i + 1 < nfac) ? g.foff[i + 1] : g.pf;
+        if (g.C == 0) ag.seg_end[nfac] = g.pf + 1;
+        for (int i = 0; i < want; ++i) ag.step_size[i] = lr_groups[i] / bc1;
+    }
+    const double step_size = lr / bc1;
     const int grid = (int)std::min<long long>((P + 255) / 256, 1024);
     if (h->dtype == TR_F32)
         k_adam<float><<<grid, 256, 0, st>>>((float*)theta, (const float*)grad, (float*)m, (float*)v, (float*)vmax, P,
-                                            beta1, beta2, eps, weight_decay, step_size, bc2_sqrt);
+                                            beta1, beta2, eps, weight_decay, step_size, bc2_sqrt, ag);
     else
         k_adam<double><<<grid, 256, 0, st>>>((double*)theta, (const double*)grad, (double*)m, (double*)v, (double*)vmax,
-                                             P, beta1, beta2, eps, weight_decay, step_size, bc2_sqrt);
+                                             P, beta1, beta2, eps, weight_decay, step_size, bc2_sqrt, ag);
     TR_LAUNCH_CHECK(h);
+    return TR_OK;
+}
+
+int tr_adam_step(tr_handle* h, void* theta, const void* grad, void* m, void* v, void* vmax, int64_t step,
+                 double lr, double beta1, double beta2, double eps, double weight_decay, void* stream) {
+    return adam_launch(h, theta, grad, m, v, vmax, step, lr, nullptr, 0, beta1, beta2, eps, weight_decay, stream);
+}
+
+int tr_adam_step_groups(tr_handle* h, void* theta, const void* grad, void* m, void* v, void* vmax, int64_t step,
+                        const double* lr_groups, int n_groups, double beta1, double beta2, double eps,
+                        double weight_decay, void* stream) {
+    if (h && !lr_groups) return fail(h, TR_ERR_INVALID, "lr_groups is null");
+    return adam_launch(h, theta, grad, m, v, vmax, step, 0.0, lr_groups, n_groups, beta1, beta2, eps, weight_decay, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cross-GPU sum of the packed gradient sums: NCCL, resolved at run time so that
+// the library neither links against nor requires NCCL on single-GPU hosts.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct TrNcclId { char internal[128]; };     // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128), passed by value
+struct NcclApi {
+    void* lib = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, TrNcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GetVersion)(int*) = nullptr;
+    std::string err;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* env = getenv("TR_B200_NCCL_LIB");
+        // prefer the NCCL the host process already loaded (torch's bundled one), then the system library
+        if (env && *env) api.lib = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+        if (!api.lib) api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!api.lib) api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.lib) { api.err = std::string("NCCL library not found (libnccl.so.2; set TR_B200_NCCL_LIB): ") + (dlerror() ? dlerror() : ""); return; }
+        api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+        api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+        api.GetVersion = (decltype(api.GetVersion))dlsym(api.lib, "ncclGetVersion");
+        if (!api.AllReduce || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy) api.err = "NCCL library lacks ncclAllReduce / ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy";
+    });
+    return &api;
+}
+const char* nccl_str(NcclApi* a, int rc) { return a->GetErrorString ? a->GetErrorString(rc) : "?"; }
+}  // namespace
+
+int tr_comm_unique_id(void* id128) {
+    if (!id128) return fail(nullptr, TR_ERR_INVALID, "id128 is null");
+    NcclApi* a = nccl_api();
+    if (!a->err.empty()) return fail(nullptr, TR_ERR_UNSUPPORTED, "%s", a->err.c_str());
+    const int rc = a->GetUniqueId(id128);
+    if (rc != 0) return fail(nullptr, TR_ERR_CUDA, "ncclGetUniqueId failed: %s", nccl_str(a, rc));
+    return TR_OK;
+}
+
+int tr_comm_create(void** comm, const void* id128, int rank, int world, int device) {
+    if (!comm || !id128) return fail(nullptr, TR_ERR_INVALID, "null comm / id128 pointer");
+    *comm = nullptr;
+    if (world < 1 || rank < 0 || rank >= world) return fail(nullptr, TR_ERR_INVALID, "rank %d of world %d", rank, world);
+    NcclApi* a = nccl_api();
+    if (!a->err.empty()) return fail(nullptr, TR_ERR_UNSUPPORTED, "%s", a->err.c_str());
+    DeviceGuard dg(device);
+    TrNcclId id;
+    memcpy(&id, id128, sizeof(id));
+    const int rc = a->CommInitRank(comm, world, id, rank);
+    if (rc != 0) return fail(nullptr, TR_ERR_CUDA, "ncclCommInitRank failed: %s", nccl_str(a, rc));
+    return TR_OK;
+}
+
+int tr_comm_destroy(void* comm) {
+    if (!comm) return TR_OK;
+    NcclApi* a = nccl_api();
+    if (!a->err.empty()) return fail(nullptr, TR_ERR_UNSUPPORTED, "%s", a->err.c_str());
+    const int rc = a->CommDestroy(comm);
+    if (rc != 0) return fail(nullptr, TR_ERR_CUDA, "ncclCommDestroy failed: %s", nccl_str(a, rc));
+    return TR_OK;
+}
+
+int tr_allreduce(tr_handle* h, double* buf, int64_t count, void* nccl_comm, void* stream) {
+    if (!h) return TR_ERR_INVALID;
+    if (!buf || count < 0) return fail(h, TR_ERR_INVALID, "null buffer / negative count");
+    if (!nccl_comm) return fail(h, TR_ERR_INVALID, "nccl_comm is null (single GPU: do not call tr_allreduce)");
+    if (count == 0) return TR_OK;
+    NcclApi* a = nccl_api();
+    if (!a->err.empty()) return fail(h, TR_ERR_UNSUPPORTED, "%s", a->err.c_str());
+    DeviceGuard dg(h->device);
+    const int rc = a->AllReduce(buf, buf, (size_t)count, /* ncclFloat64 */ 8, /* ncclSum */ 0, nccl_comm, (cudaStream_t)stream);
+    if (rc != 0) return fail(h, TR_ERR_CUDA, "ncclAllReduce failed: %s", nccl_str(a, rc));
     return TR_OK;
 }
 
@@ -1004,6 +1147,9 @@ int tr_set_option(tr_handle* h, const char* name, int64_t value) {
         return TR_OK;
     }
     if (strcmp(name, "flow") == 0) {
+#ifndef TR_WITH_FLOW
+        if (value == 1) return fail(h, TR_ERR_UNSUPPORTED, "option flow=1: this build does not contain the experimental dataflow kernel (make FLOW=1)");
+#endif
         if (value < -1 || value > 1) return fail(h, TR_ERR_INVALID, "option flow: 0 (never, default), 1 (always the experimental dataflow kernel), -1 (auto = 0 for now)");
         h->flow_mode = (int)value;
         return TR_OK;

@@ -1,7 +1,15 @@
 // tr_dispatch.h — table of streaming-kernel instantiations shared by tr_api.cu and tr_stream.cu.
 #pragma once
 #include "tr_kernels.cuh"
+// The experimental single-launch dataflow kernel (tr_flow.cuh, DESIGN 4b: correct, measured 2-6 x slower than the
+// two-pass kernels, never auto-selected) is compiled only with -DTR_WITH_FLOW (make FLOW=1).
+#ifdef TR_WITH_FLOW
 #include "tr_flow.cuh"
+#define TR_FLOW_ENTRY(T, RK, E, UF, UG) k_flow<T, RK, E, UF, UG, VN<T>::v>
+#else
+template <typename T> struct FlowArgs;
+#define TR_FLOW_ENTRY(T, RK, E, UF, UG) nullptr
+#endif
 
 template <typename T> struct VN;
 template <> struct VN<float> { static constexpr int v = 4; };
@@ -20,7 +28,7 @@ struct KEntry {
 #define TR_ENTRY(T, RK, E, UF, UG)                                                                  \
     { RK, E, UF, UG, k_fwd<T, RK, E, UF, VN<T>::v>, k_fwd<T, RK, E * VN<T>::v, UF, 1>,              \
       k_grad<T, RK, E, UG, VN<T>::v>, k_grad<T, RK, E * VN<T>::v, UG, 1>,                           \
-      k_flow<T, RK, E, UF, UG, VN<T>::v> }
+      TR_FLOW_ENTRY(T, RK, E, UF, UG) }
 
 const KEntry<float>* tr_entries_f32_0(int* n);
 const KEntry<float>* tr_entries_f32_1(int* n);

@@ -227,12 +227,26 @@ template <typename T> __device__ __forceinline__ T tr_sqrt(T x);
 template <> __device__ __forceinline__ float tr_sqrt<float>(float x) { return sqrtf(x); }
 template <> __device__ __forceinline__ double tr_sqrt<double>(double x) { return sqrt(x); }
 
+// Per-parameter-group step sizes (torch.optim.Adam with one parameter group per factor, e.g. the three groups of
+// hier:436-440): group g = factor g of theta (boundaries seg_end[], the bias is the last group of the standard
+// model); n_seg == 0 means one group with step size `step_size`.
+struct AdamGroups {
+    int n_seg;
+    int seg_end[TR_MAX_MODES + 2];
+    double step_size[TR_MAX_MODES + 2];
+};
+
 template <typename T>
 __global__ void k_adam(T* __restrict__ theta, const T* __restrict__ grad, T* __restrict__ m, T* __restrict__ v,
                        T* __restrict__ vmax, long long P, double beta1, double beta2, double eps, double wd,
-                       double step_size, double bc2_sqrt) {
+                       double step_size, double bc2_sqrt, const AdamGroups groups) {
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P;
          p += (long long)gridDim.x * blockDim.x) {
+        if (groups.n_seg > 0) {
+            int sgi = 0;
+            while (sgi + 1 < groups.n_seg && p >= groups.seg_end[sgi]) ++sgi;
+            step_size = groups.step_size[sgi];
+        }
         T g = grad[p];
         const T th = theta[p];
         if (wd != 0.0) g = g + (T)wd * th;
@@ -256,6 +270,10 @@ __global__ void k_adam(T* __restrict__ theta, const T* __restrict__ grad, T* __r
 }
 
 
+// max that propagates NaN like torch's flat_grad.abs().max(): a NaN gradient must not read as "max|g| = 0"
+// (lbfgs.py would then stop with "optimality reached" on a corrupted state; torch compares NaN <= tol -> False)
+__device__ __forceinline__ double tr_nanmax(double a, double b) { return (a != a || b != b) ? NAN : fmax(a, b); }
+
 // ---------------------------------------------------------------------------------------------
 // L-BFGS on the flat parameter vector (torch/optim/lbfgs.py:333-536, used by std:366,392 and
 // mn:355,381): history, two-loop recursion and every dot product stay on the device; only the few
@@ -274,13 +292,15 @@ __device__ __forceinline__ double block_sum_bcast(double v, double* sbuf, double
 }
 __device__ __forceinline__ double block_max_bcast(double v, double* sbuf, double* sb) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    v = warp_max(v);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = tr_nanmax(v, __shfl_xor_sync(TR_FULL, v, off));
     __syncthreads();
     if (lane == 0) sbuf[wid] = v;
     __syncthreads();
     if (wid == 0) {
         double r = lane < nw ? sbuf[lane] : 0.0;
-        r = warp_max(r);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) r = tr_nanmax(r, __shfl_xor_sync(TR_FULL, r, off));
         if (lane == 0) *sb = r;
     }
     __syncthreads();
@@ -359,8 +379,8 @@ __global__ void __launch_bounds__(1024) k_lbfgs_direction(const T* __restrict__ 
         prev_g[p] = g[p];
         gtd += gv * dv;
         g1 += fabs(gv);
-        gm = fmax(gm, fabs(gv));
-        dm = fmax(dm, fabs(dv));
+        gm = tr_nanmax(gm, fabs(gv));
+        dm = tr_nanmax(dm, fabs(dv));
     }
     gtd = block_sum_bcast(gtd, sbuf, &sb);
     g1 = block_sum_bcast(g1, sbuf, &sb);
@@ -389,7 +409,7 @@ __global__ void __launch_bounds__(1024) k_lbfgs_gtd(const T* __restrict__ g, con
     for (long long p = threadIdx.x; p < P; p += blockDim.x) {
         const double gv = (double)g[p];
         gtd += gv * (d ? (double)d[p] : 0.0);
-        gm = fmax(gm, fabs(gv));
+        gm = tr_nanmax(gm, fabs(gv));
     }
     gtd = block_sum_bcast(gtd, sbuf, &sb);
     gm = block_max_bcast(gm, sbuf, &sb);

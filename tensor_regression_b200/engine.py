@@ -231,12 +231,28 @@ class Engine:
         self.launches += 1
         return grad, loss
 
-    def adam_step(self, theta, grad, m, v, vmax, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
-        self._ck(_lib.lib.tr_adam_step(self._h, theta.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(),
-                                       vmax.data_ptr() if vmax is not None else None, int(step), float(lr),
-                                       float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
-                                       self._stream()))
+    def adam_step(self, theta, grad, m, v, vmax, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                  lr_groups=None):
+        """``lr_groups``: one learning rate per parameter group (the factors of theta in order, plus the bias
+        for the standard model) — torch.optim.Adam with a list of parameter groups (hier:436-440)."""
+        if lr_groups is not None:
+            arr = (ctypes.c_double * len(lr_groups))(*[float(x) for x in lr_groups])
+            self._ck(_lib.lib.tr_adam_step_groups(self._h, theta.data_ptr(), grad.data_ptr(), m.data_ptr(),
+                                                  v.data_ptr(), vmax.data_ptr() if vmax is not None else None,
+                                                  int(step), arr, len(lr_groups), float(betas[0]), float(betas[1]),
+                                                  float(eps), float(weight_decay), self._stream()))
+        else:
+            self._ck(_lib.lib.tr_adam_step(self._h, theta.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                           vmax.data_ptr() if vmax is not None else None, int(step), float(lr),
+                                           float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                           self._stream()))
         self.launches += 1
+
+    def allreduce(self, buf, nccl_comm):
+        """In-place sum of a float64 device vector over the ranks of ``nccl_comm`` (an ncclComm_t as an int),
+        enqueued on the current stream by the library (tr_allreduce)."""
+        self._ck(_lib.lib.tr_allreduce(self._h, self._vec(buf, buf.numel(), 'buf', torch.float64).data_ptr(),
+                                       buf.numel(), ctypes.c_void_p(int(nccl_comm)), self._stream()))
 
 
     # -- L-BFGS vector kernels (see lbfgs.py) ------------------------------------------------
@@ -262,21 +278,45 @@ class ShardedSum:
     axis: one all-reduce of P+2 doubles per closure evaluation.  With
     ``group=None`` and no initialised default group this is the identity (single GPU)."""
 
-    def __init__(self, group=None, enabled=None):
+    def __init__(self, group=None, enabled=None, engine=None):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
         if enabled is None:
             enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.enabled = bool(enabled)
+        self.engine = engine          # with an Engine and an NCCL group the sum goes through the C ABI (tr_allreduce)
+        self._comm = None
+        self.via = 'none' if not self.enabled else 'torch.distributed'
 
     @property
     def world(self):
         return self.dist.get_world_size(self.group) if self.enabled else 1
 
+    def _nccl_comm(self, device):
+        """ncclComm_t of the group's NCCL backend (ProcessGroupNCCL._comm_ptr), or None (gloo groups, a
+        communicator that has not been created yet, older torch)."""
+        if self._comm is not None:
+            return self._comm or None
+        try:
+            pg = self.group if self.group is not None else self.dist.distributed_c10d._get_default_group()
+            ptr = int(pg._get_backend(torch.device(device))._comm_ptr())
+            if ptr:
+                self._comm = ptr
+                return ptr
+        except Exception:
+            pass
+        return None
+
     def sum_(self, t):
         if self.enabled:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            comm = self._nccl_comm(t.device) if (self.engine is not None and t.is_cuda
+                                                 and t.dtype == torch.float64) else None
+            if comm:
+                self.engine.allreduce(t, comm)
+                self.via = 'tr_allreduce (C ABI, NCCL communicator of the process group)'
+            else:
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t
 
     def total(self, value, device):

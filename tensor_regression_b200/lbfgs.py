@@ -64,7 +64,9 @@ class LBFGS:
 
     def _strong_wolfe(self, closure, x, t, f, gtd, d_norm, c1=1e-4, c2=0.9, max_ls=25):
         """lbfgs.py:40-209.  self.g holds g(x) on entry and the accepted point's gradient on return."""
-        tol = self.tolerance_change
+        # torch.optim.LBFGS.step does not forward its tolerance_change to _strong_wolfe: the bracket-width exit
+        # always uses the function's default of 1e-9 (lbfgs.py:40, call at 455-457)
+        tol = 1e-9
         eng, theta, d = self.eng, self.theta, self.d
 
         def obj(tt):

@@ -140,7 +140,7 @@ class CP_logistic_regression():
         if self._out_of_core:
             self.X = X
         elif isinstance(X, torch.Tensor) and X.is_cuda:
-            self.X = X.to(device=dev, dtype=torch.float32)
+            self.X = X.to(device=dev, dtype=torch.float32).contiguous()
         elif hasattr(X, 'shape') and len(X.shape) >= 1 and int(X.shape[0]) > 0:
             self.X = _engine.upload_resident(X, torch.float32, dev)   # host data: pinned, double-buffered upload
         else:
@@ -180,6 +180,13 @@ class CP_logistic_regression():
             self.n_classes = int(t.item())
         else:
             self.n_classes = len(torch.unique(self.y))
+        # labels index the class factor and the class weights: the reference fails with "Target ... is out of
+        # bounds" from CrossEntropyLoss (mn:366) for labels outside [0, n_classes); here the check is up front
+        if self.y.numel():
+            lo, hi = int(self.y.min().item()), int(self.y.max().item())
+            if lo < 0 or hi >= self.n_classes:
+                raise ValueError(f'class labels must lie in [0, n_classes={self.n_classes}): found min {lo}, max {hi} '
+                                 f'(use squeeze_integers to make labels consecutive from 0)')
         self._dims = [int(d) for d in self.X.shape[1:]]
         B_dims = np.concatenate((np.array(self.X.shape[1:]), [self.n_classes]))
         if Bcp_init is None:
@@ -212,8 +219,14 @@ class CP_logistic_regression():
 
     def _engine(self):
         if self._eng is None:
-            self._eng = _engine_for(self._dims, self.rank, self.n_classes, torch.float32, self._torch_device())
+            self._eng = _engine.Engine(self._dims, self.rank, self.n_classes, torch.float32, self._torch_device())
         return self._eng
+
+    def close(self):
+        """Release the library handle and its device workspace (also done when the object is deleted)."""
+        if self._eng is not None:
+            self._eng.close()
+            self._eng = None
 
     def _mask(self):
         return nn_mask_of(self.non_negative, len(self._dims) + 1)
@@ -225,7 +238,10 @@ class CP_logistic_regression():
         g = self._shard_group
         if g is None:
             return _engine.ShardedSum(enabled=False)
-        return _engine.ShardedSum(group=None if g == 'world' else g)
+        return _engine.ShardedSum(group=None if g == 'world' else g, engine=self._engine() if self._dims_known() else None)
+
+    def _dims_known(self):
+        return hasattr(self, '_dims') and hasattr(self, 'n_classes')
 
     def __getstate__(self):
         st = dict(self.__dict__)
@@ -362,7 +378,7 @@ class CP_logistic_regression():
             sharder.sum_(gs)
             eng.finish(gs, 1.0 / W, 1.0 / W, self.theta, lambda_L2, self._mask(), beta, thr, grad=grad, loss=loss)
             eng.adam_step(self.theta, grad, m, v, vmax, ii + 1, lr=hyper['lr'], betas=hyper['betas'],
-                          eps=hyper['eps'], weight_decay=hyper['weight_decay'])
+                          eps=hyper['eps'], weight_decay=hyper['weight_decay'], lr_groups=self._adam_lr_groups(hyper))
             self.loss_running.append(loss[1].item())
             if verbose == 2:
                 print(f'Iteration: {ii}, Loss: {self.loss_running[-1]}')
@@ -376,6 +392,10 @@ class CP_logistic_regression():
             else:
                 print('Reached maximum number of iterations without convergence')
         return convergence_reached
+
+    def _adam_lr_groups(self, hyper):
+        """None = one parameter group (mn:447); the hierarchical subclass returns one rate per factor."""
+        return None
 
     def predict(self, X=None, y_true=None, Bcp=None, device=None):
         """mn:474-545 — returns (probabilities (N,C) numpy, argmax labels (N,) numpy)."""

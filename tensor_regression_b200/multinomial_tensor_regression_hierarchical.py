@@ -55,6 +55,13 @@ class CP_logistic_regression(_mn.CP_logistic_regression):
         return super().fit_Adam(lambda_L2=lambda_L2, max_iter=max_iter, tol=tol, patience=patience,
                                 weights=self._ones(), verbose=verbose, Adam_kwargs=Adam_kwargs)
 
+    def _adam_lr_groups(self, hyper):
+        """hier:436-440 — three explicit parameter groups {'params': Bcp[i], 'lr': Adam_kwargs['lr']}: one step
+        size per factor through tr_adam_step_groups (a ``lr_groups`` list of three rates in Adam_kwargs-style
+        callers can be set on the instance as ``self.lr_groups`` to give the factors different rates)."""
+        g = getattr(self, 'lr_groups', None)
+        return [float(x) for x in g] if g is not None else [float(hyper['lr'])] * 3
+
     def predict(self, X=None, y_true=None, Bcp=None, device=None, plot_pref=False):
         """hier:473-544 — (probabilities, argmax labels); ``plot_pref`` is accepted and unused, as in the
         reference (its plotting block is commented out)."""

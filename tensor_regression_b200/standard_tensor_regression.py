@@ -49,7 +49,12 @@ def non_neg_fn(B_cp, non_negative, softplus_kwargs=None):
             yield B_cp[ii]
 
 
+# Engines (library handle + its cudaMalloc'ed workspace) used by the MODULE-LEVEL functions lin_model / model:
+# a small LRU keyed by geometry; an evicted engine is closed (its workspace freed).  Estimator objects own their
+# engine (one handle per model: no scratch buffers shared between models) and release it with close() / on
+# deletion.  A handle's workspace is single-stream: do not drive one model from two CUDA streams at once.
 _ENGINES = {}
+_ENGINES_MAX = 4
 
 
 def _engine_for(dims, rank, n_classes, dtype, device):
@@ -57,11 +62,19 @@ def _engine_for(dims, rank, n_classes, dtype, device):
     if device.type == 'cuda' and device.index is None:
         device = torch.device('cuda', torch.cuda.current_device())
     key = (tuple(int(d) for d in dims), int(rank), int(n_classes), dtype, str(device))
-    eng = _ENGINES.get(key)
+    eng = _ENGINES.pop(key, None)
     if eng is None:
         eng = _engine.Engine(dims, rank, n_classes, dtype, device)
-        _ENGINES[key] = eng
+        while len(_ENGINES) >= _ENGINES_MAX:
+            _ENGINES.pop(next(iter(_ENGINES))).close()       # least recently used first (dicts keep insertion order)
+    _ENGINES[key] = eng
     return eng
+
+
+def release_engines():
+    """Free the workspaces of the engines cached for lin_model / model."""
+    while _ENGINES:
+        _ENGINES.popitem()[1].close()
 
 
 def _flatten(Bcp, bias, dtype, device):
@@ -198,8 +211,14 @@ class CP_linear_regression():
 
     def _engine(self):
         if self._eng is None:
-            self._eng = _engine_for(self._dims, self.rank, 0, self.dtype, self._torch_device())
+            self._eng = _engine.Engine(self._dims, self.rank, 0, self.dtype, self._torch_device())
         return self._eng
+
+    def close(self):
+        """Release the library handle and its device workspace (also done when the object is deleted)."""
+        if self._eng is not None:
+            self._eng.close()
+            self._eng = None
 
     def _mask(self):
         return nn_mask_of(self.non_negative, len(self._dims))
@@ -212,11 +231,11 @@ class CP_linear_regression():
         if not isinstance(y, torch.Tensor):
             y = torch.as_tensor(y)
         if isinstance(X, torch.Tensor) and X.is_cuda:
-            X = X.to(device=dev, dtype=self.dtype)
+            X = X.to(device=dev, dtype=self.dtype).contiguous()    # made contiguous once, not per iteration
         elif hasattr(X, 'shape') and len(X.shape) >= 1 and int(X.shape[0]) > 0:
             X = _engine.upload_resident(X, self.dtype, dev)        # host data: pinned, double-buffered upload
         else:
-            X = torch.as_tensor(np.asarray(X)).to(device=dev, dtype=self.dtype)
+            X = torch.as_tensor(np.asarray(X)).to(device=dev, dtype=self.dtype).contiguous()
         y = y.to(device=dev, dtype=self.dtype).reshape(-1).contiguous()
         if X.shape[0] != y.shape[0]:
             raise ValueError('X.shape[0] must match len(y)')
@@ -226,7 +245,7 @@ class CP_linear_regression():
         g = self._shard_group
         if g is None:
             return _engine.ShardedSum(enabled=False)
-        return _engine.ShardedSum(group=None if g == 'world' else g)
+        return _engine.ShardedSum(group=None if g == 'world' else g, engine=self._engine())
 
     def __getstate__(self):
         st = dict(self.__dict__)
@@ -263,16 +282,35 @@ class CP_linear_regression():
             patience=10,
             verbose=False,
             running_loss_logging_interval=10,
-            LBFGS_kwargs=None):
+            LBFGS_kwargs=None,
+            *,
+            out_of_core=False,
+            chunk_samples=None):
         """std:305-398 — L-BFGS with torch.optim.LBFGS's algorithm and keyword arguments; history,
         two-loop recursion and vector algebra are device-resident (lbfgs.py), every closure
-        evaluation is one tr_fwd_grad_std + tr_finish_grad."""
+        evaluation is one tr_fwd_grad_std + tr_finish_grad.
+
+        ``out_of_core=True`` (keyword-only extension; the reference's abandoned fit_batch_LBFGS, std:478-620,
+        done exactly): X stays in host memory and every closure evaluation streams it to the device in chunks
+        of ``chunk_samples``; the gradient is the exact full-batch sum, so the optimizer takes the same steps
+        as with a resident X."""
         if LBFGS_kwargs is None:
             # the reference's "default" dict (std:353-362) is a bare expression: None raises there too
             raise TypeError('LBFGS_kwargs must be a dict of torch.optim.LBFGS keyword arguments (got None)')
-        X, y = self._prep_xy(X, y)
+        streamer = None
+        if out_of_core:
+            dev = self._torch_device()
+            y = torch.as_tensor(y).to(device=dev, dtype=self.dtype).reshape(-1).contiguous()
+            if int(X.shape[0]) != y.shape[0]:
+                raise ValueError('X.shape[0] must match len(y)')
+            streamer = _engine.HostStreamer(X, self.dtype, dev, chunk_samples=chunk_samples)
+            self.h2d_bytes_per_iteration = streamer.bytes_per_pass
+            n_local = y.shape[0]
+        else:
+            X, y = self._prep_xy(X, y)
+            n_local = X.shape[0]
         sharder = self._sharder()
-        n_total = sharder.total(X.shape[0], X.device)
+        n_total = sharder.total(n_local, y.device)
         eng = self._engine()
         beta, thr = self._sp()
 
@@ -280,16 +318,27 @@ class CP_linear_regression():
         # is torch.optim.LBFGS's algorithm with device-resident history / two-loop recursion (lbfgs.py)
         optimizer = _lbfgs.LBFGS(eng, self.theta, **LBFGS_kwargs)
         gs = torch.empty(eng.n_gradsum, dtype=torch.float64, device=self.theta.device)
+        gs_chunk = torch.empty_like(gs) if streamer is not None else None
 
         def closure(grad_out, loss_out):
-            eng.fwd_grad_std(X, y, self.theta, self.weights, self._mask(), beta, thr, gradsum=gs)
+            if streamer is None:
+                eng.fwd_grad_std(X, y, self.theta, self.weights, self._mask(), beta, thr, gradsum=gs)
+            else:
+                gs.zero_()
+                for lo, hi, xd in streamer.chunks():
+                    eng.fwd_grad_std(xd, y[lo:hi], self.theta, self.weights, self._mask(), beta, thr, gradsum=gs_chunk)
+                    gs.add_(gs_chunk)
             sharder.sum_(gs)
             eng.finish(gs, 2.0 / n_total, 1.0 / n_total, self.theta, lambda_L2, self._mask(), beta, thr,
                        grad=grad_out, loss=loss_out)
 
         def logged_loss():
             # extra forward without the penalty (std:380-382): one pass over X
-            y_hat = eng.forward_std(X, self.theta, self.weights, self._mask(), beta, thr)
+            if streamer is None:
+                y_hat = eng.forward_std(X, self.theta, self.weights, self._mask(), beta, thr)
+            else:
+                y_hat = torch.cat([eng.forward_std(xd, self.theta, self.weights, self._mask(), beta, thr)
+                                   for _, _, xd in streamer.chunks()])
             sq = torch.sum((y_hat - y).to(torch.float64) ** 2).reshape(1)
             return (sharder.sum_(sq) / n_total).item(), y_hat
 

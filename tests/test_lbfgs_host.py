@@ -77,10 +77,16 @@ CASES = [
     {'lr': 1, 'max_iter': 20, 'max_eval': 20, 'tolerance_grad': 1e-07, 'tolerance_change': 1e-09,
      'history_size': 3, 'line_search_fn': 'strong_wolfe'},
     {'lr': 0.05, 'max_iter': 7, 'history_size': 5, 'line_search_fn': None},
+    # tolerance_change != 1e-9: torch does NOT forward it to _strong_wolfe (the bracket-width exit keeps its
+    # default 1e-9), only the outer stopping rules use it
+    {'lr': 1, 'max_iter': 20, 'max_eval': None, 'tolerance_grad': 1e-07, 'tolerance_change': 1e-06,
+     'history_size': 100, 'line_search_fn': 'strong_wolfe'},
+    {'lr': 1, 'max_iter': 30, 'max_eval': 60, 'tolerance_grad': 1e-09, 'tolerance_change': 1e-03,
+     'history_size': 10, 'line_search_fn': 'strong_wolfe'},
 ]
 
 
-@pytest.mark.parametrize('kw', CASES, ids=['reference_kwargs', 'short_history', 'fixed_step'])
+@pytest.mark.parametrize('kw', CASES, ids=['reference_kwargs', 'short_history', 'fixed_step', 'tolchange_1e-6', 'tolchange_1e-3'])
 def test_native_lbfgs_matches_torch_lbfgs(kw):
     L = _load_lbfgs()
     torch.manual_seed(3)
