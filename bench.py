@@ -246,61 +246,93 @@ def cpu_baseline(wl, budget_s=12.0, n_s=None):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path on the host cores
-    (oracle port here: the Python reference cannot travel to the GPU box), rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the fit_Adam iteration on the host cores, rank 0
+    only.  The UNMODIFIED reference modules are used when they can be imported (oracle.ref_loader: $TR_REFERENCE_DIR
+    or /root/reference, then baseline/_ref — build container only, kind "reference"); on the GPU box they do not
+    exist and the pinned oracle port of the same algorithm runs instead (kind "port")."""
     if rank != 0:
         return
     wl = args.workload
     kind, _, dims, R, C, dt = WORKLOADS[wl]
     from oracle import tr_oracle as O
+    from oracle import ref_loader
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     D = int(np.prod(dims))
     n_s = int(max(64, min(2000, (1 << 30) // (D * (4 if dt == torch.float32 else 8)))))
+    ref_kind, ref_src = 'port', 'oracle port (oracle/tr_oracle.py)'
+    for cand in (ref_loader.REFERENCE_DIR, os.path.join(ROOT, 'baseline', '_ref')):
+        if os.path.isfile(os.path.join(cand, 'standard_tensor_regression.py')):
+            ref_loader.REFERENCE_DIR = cand
+            ref_kind, ref_src = 'reference', f'unmodified reference modules from {cand} (tensorly stand-in)'
+            break
+    print(f'reference arm: using the {ref_src}', file=sys.stderr)
+    nn = [False] * (len(dims) + 1)
     if kind == 'std':
         X, y, _ = O.synth_std(n_s, dims, R, 1234 + 2, dtype=dt)
-        nn = [False] * (len(dims) + 1)
-        B = [b.clone().requires_grad_(True) for b in O.init_std(dims, R, nn, dtype=dt)]
-        bias = torch.tensor([0.0], dtype=dt, requires_grad=True)
-        w = torch.ones(R, dtype=dt)
-        opt = torch.optim.Adam(B + [bias], **ADAM)
-        loss_fn = torch.nn.MSELoss()
-
-        def step():
-            opt.zero_grad()
-            loss = loss_fn(O.lin_model(X, B, w, nn, bias), y) + LAMBDA * O.L2_penalty(B)
-            loss.backward()
-            opt.step()
-            return loss.item()
+        B0 = O.init_std(dims, R, nn, dtype=dt)
     else:
         X, y, _ = O.synth_mn(n_s, dims, R, C, 1234 + 3)
-        nn = [False] * (len(dims) + 1)
-        B = [b.clone().requires_grad_(True) for b in O.init_mn(list(dims) + [C], R, nn)]
-        w = torch.ones(R)
-        opt = torch.optim.Adam(B, **ADAM)
-        loss_fn = torch.nn.CrossEntropyLoss(weight=torch.ones(C))
+        B0 = O.init_mn(list(dims) + [C], R, nn)
+    if ref_kind == 'reference':
+        if kind == 'std':
+            ref = ref_loader.standard()
+            mdl = ref.CP_linear_regression(X.shape, dtype=dt, rank=R, non_negative=False,
+                                           Bcp_init=[b.clone().requires_grad_(True) for b in B0], device='cpu')
+            run = lambda k: mdl.fit_Adam(X, y, lambda_L2=LAMBDA, max_iter=k, tol=0.0, patience=10 ** 9,  # noqa: E731
+                                         Adam_kwargs=dict(ADAM))
+        else:
+            ref = ref_loader.multinomial()
+            mdl = ref.CP_logistic_regression(X, y, rank=R, non_negative=False,
+                                             Bcp_init=[b.clone().requires_grad_(True) for b in B0], device='cpu')
+            run = lambda k: mdl.fit_Adam(lambda_L2=LAMBDA, max_iter=k, tol=0.0, patience=10 ** 9,  # noqa: E731
+                                         weights=np.ones(C, dtype=np.float32), Adam_kwargs=dict(ADAM))
+        if args.warmup > 0:
+            run(args.warmup)
+        t0 = time.perf_counter()
+        run(args.steps)
+        dt_s = time.perf_counter() - t0
+    else:
+        if kind == 'std':
+            B = [b.clone().requires_grad_(True) for b in B0]
+            bias = torch.tensor([0.0], dtype=dt, requires_grad=True)
+            w = torch.ones(R, dtype=dt)
+            opt = torch.optim.Adam(B + [bias], **ADAM)
+            loss_fn = torch.nn.MSELoss()
 
-        def step():
-            opt.zero_grad()
-            loss = loss_fn(O.mn_model(X, B, w, nn), y) + LAMBDA * O.L2_penalty(B)
-            loss.backward()
-            opt.step()
-            return loss.item()
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt_s = time.perf_counter() - t0
+            def step():
+                opt.zero_grad()
+                loss = loss_fn(O.lin_model(X, B, w, nn, bias), y) + LAMBDA * O.L2_penalty(B)
+                loss.backward()
+                opt.step()
+                return loss.item()
+        else:
+            B = [b.clone().requires_grad_(True) for b in B0]
+            w = torch.ones(R)
+            opt = torch.optim.Adam(B, **ADAM)
+            loss_fn = torch.nn.CrossEntropyLoss(weight=torch.ones(C))
+
+            def step():
+                opt.zero_grad()
+                loss = loss_fn(O.mn_model(X, B, w, nn), y) + LAMBDA * O.L2_penalty(B)
+                loss.backward()
+                opt.step()
+                return loss.item()
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt_s = time.perf_counter() - t0
     val = n_s * args.steps / dt_s
     sample = (f'{n_s} samples of the {wl} sample shape {tuple(dims)} per step (bounded sample of the workload), '
-              f'oracle port of the reference fit_Adam iteration on torch CPU, {torch.get_num_threads()} threads')
+              f'{ref_src}: fit_Adam iteration on torch CPU, {torch.get_num_threads()} threads')
     out = {'impl': 'reference', 'metric': 'samples/sec per fit iteration (fwd+grad+step)', 'value': val,
            'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
            'ms_per_step': dt_s / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
            'dtype': 'f32' if dt == torch.float32 else 'f64', 'data': 'synthetic',
            'config': {'workload': DESCR[wl], 'sample': sample},
-           'cpu_baseline': {'value': val, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+           'cpu_baseline': {'value': val, 'unit': 'samples/s', 'cores': cores, 'kind': ref_kind, 'sample': sample},
            'e2e': {'value': val, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     emit(out)
 
@@ -319,6 +351,220 @@ def emit(obj):
         sys.stdout.flush()
 
 
+def fmt_dtype(dt):
+    return 'f32' if dt == torch.float32 else 'f64'
+
+
+class Workload:
+    """One BASELINE config resident on this rank's GPU: data, engine, optimizer state and the fit-iteration step."""
+
+    def __init__(self, wl, n_local, rank, world, device, E, STR, MTR, fused=-1, flow=-1):
+        self.wl, self.n_local, self.world, self.device = wl, int(n_local), world, device
+        kind, _, dims, R, C, dt = WORKLOADS[wl]
+        self.kind, self.dims, self.R, self.C, self.dt = kind, dims, R, C, dt
+        self.D = int(np.prod(dims))
+        self.elt = 4 if dt == torch.float32 else 8
+        self.x_bytes = self.n_local * self.D * self.elt
+        self.X, Fstar = make_device_data(wl, self.n_local, rank, device)
+        self.sharder = None
+        nn = [False] * (len(dims) + 1)
+        torch.manual_seed(321)
+        if kind == 'std':
+            self.eng = E.Engine(dims, R, 0, dt, device)
+            self.w = torch.ones(R, dtype=dt, device=device)
+            theta_star = torch.cat([f.reshape(-1) for f in Fstar] + [torch.tensor([0.1], dtype=dt)]).to(device)
+            self.y = self.eng.forward_std(self.X, theta_star, self.w, 0, 50.0, 1.0)
+            self.y += 0.01 * torch.randn(self.y.shape, dtype=dt, device=device)
+            self.B0 = STR.make_BcpInit(list(dims), R, nn, scale=1, device='cpu', dtype=dt)
+            self.theta = torch.cat([b.reshape(-1) for b in self.B0] + [torch.zeros(1, dtype=dt)]).to(device).contiguous()
+            self.cw = None
+        else:
+            self.eng = E.Engine(dims, R, C, torch.float32, device)
+            self.w = torch.ones(R, device=device)
+            theta_star = torch.cat([f.reshape(-1) for f in Fstar]).to(device)
+            _, self.y = self.eng.forward_mn(self.X, theta_star, self.w, 0, 50.0, 1.0)
+            self.B0 = MTR.make_BcpInit(list(dims) + [C], R, nn, scale=0.2, device='cpu')
+            self.theta = torch.cat([b.reshape(-1) for b in self.B0]).to(device=device, dtype=torch.float32).contiguous()
+            self.cw = torch.ones(C, device=device)
+        self.sharder = E.ShardedSum(engine=self.eng) if world > 1 else E.ShardedSum(enabled=False)
+        self.eng.set_option('fused', fused)
+        if flow == 1:
+            self.eng.set_option('flow', 1)
+        self.reset()
+
+    def reset(self):
+        th = self.theta
+        self.th = th.clone()
+        self.m_, self.v_, self.vm_ = torch.zeros_like(th), torch.zeros_like(th), torch.zeros_like(th)
+        self.gs = torch.empty(self.eng.n_gradsum, dtype=torch.float64, device=self.device)
+        self.grad = torch.empty_like(th)
+        self.loss = torch.empty(2, dtype=torch.float64, device=self.device)
+        self.step_no = 0
+
+    def step(self, X=None, y=None, n_total=None):
+        """One fit iteration: fwd + grad over X + all-reduce + penalty/normalise + Adam."""
+        X = self.X if X is None else X
+        y = self.y if y is None else y
+        self.step_no += 1
+        eng = self.eng
+        if self.kind == 'std':
+            eng.fwd_grad_std(X, y, self.th, self.w, 0, 50.0, 1.0, gradsum=self.gs)
+            self.sharder.sum_(self.gs)
+            eng.finish(self.gs, 2.0 / n_total, 1.0 / n_total, self.th, LAMBDA, 0, 50.0, 1.0, grad=self.grad, loss=self.loss)
+        else:
+            eng.fwd_grad_mn(X, y, self.cw, self.th, self.w, 0, 50.0, 1.0, gradsum=self.gs)
+            self.sharder.sum_(self.gs)
+            eng.finish(self.gs, 1.0 / n_total, 1.0 / n_total, self.th, LAMBDA, 0, 50.0, 1.0, grad=self.grad, loss=self.loss)
+        eng.adam_step(self.th, self.grad, self.m_, self.v_, self.vm_, self.step_no, lr=ADAM['lr'])
+
+    def free(self):
+        self.X = None
+        self.y = None
+        self.eng.close()
+
+
+def timed_steps(wk, steps, warmup, dist, rank, local_rank, sample_clocks, X=None, y=None, n_total=None):
+    """W untimed + K timed steps between barrier + synchronize, CUDA events, max over ranks.  Returns a dict
+    with ms_per_step, value, the library's per-kernel event times, launch count / info and the clocks."""
+    world = wk.world
+    device = wk.device
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if n_total is None:
+        n_total = wk.sharder.total(wk.n_local if X is None else X.shape[0], device)
+    wk.reset()
+    for _ in range(warmup):
+        wk.step(X, y, n_total)
+    barrier()
+    wk.eng.profile(True)
+    launches0 = wk.eng.launches
+    sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        wk.step(X, y, n_total)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = ev0.elapsed_time(ev1)
+    prof = wk.eng.profile_read()
+    wk.eng.profile(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / steps
+    return {'ms_per_step': ms_per_step, 'value': n_total / (ms_per_step * 1e-3), 'n_total': int(n_total), 'prof': prof,
+            'launches': wk.eng.launches - launches0, 'launch_info': wk.eng.launch_info(), 'clocks': clocks,
+            'final_loss': wk.loss.cpu().tolist(), 'allreduce_via': wk.sharder.via}
+
+
+def roofline_of(res, wk, x_bytes, ratios):
+    """roofline object of the dominant streaming kernel from the library's CUDA-event times (this rank)."""
+    peak, peak_src = peaks()
+    prof, ms_per_step = res['prof'], res['ms_per_step']
+    fwd_ms = prof['fwd_ms'] / max(1, prof['fwd_launches'])
+    grad_ms = prof['grad_ms'] / max(1, prof['grad_launches'])
+    fused_ms = prof['fused_ms'] / max(1, prof['fused_launches'])
+    if prof['fused_launches'] > 0:
+        # single-pass kernel: does the work of both passes (algorithmic bytes = 2 x bytes(X), SURVEY 8d / H8) while
+        # reading X from HBM once -> "achieved" exceeds the HBM peak by design; frac_physical and traffic show the
+        # bytes that really cross the HBM interface
+        path = res['launch_info']['path']
+        dom = 'k_flow' if path.startswith('single-launch dataflow') else ('k_fused_mn' if wk.kind == 'mn' else 'k_fused_std')
+        dom_ms, alg, phys = fused_ms, 2 * x_bytes, x_bytes
+        extra = {'k_single_ms': fused_ms,
+                 'note': 'single-pass kernel: X is read from HBM once, the second (gradient) pass is served from '
+                         'cluster shared memory; frac counts the 2-pass algorithmic bytes (the contract of SURVEY 8d), '
+                         'frac_physical the bytes that cross the HBM interface',
+                 'share_of_step': {dom: fused_ms / ms_per_step}}
+    else:
+        dom = 'k_grad' if grad_ms >= fwd_ms else 'k_fwd'
+        dom_ms, alg, phys = max(grad_ms, fwd_ms), x_bytes, x_bytes
+        extra = {'k_fwd_ms': fwd_ms, 'k_grad_ms': grad_ms,
+                 'k_fwd_gbs': x_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None,
+                 'k_grad_gbs': x_bytes / (grad_ms * 1e-3) / 1e9 if grad_ms else None,
+                 'share_of_step': {'k_fwd': fwd_ms / ms_per_step, 'k_grad': grad_ms / ms_per_step}}
+    achieved = alg / (dom_ms * 1e-3) / 1e9 if dom_ms else None
+    tr = ratios.get(f'{dom}_{wk.kind}') or ratios.get(dom)
+    out = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+           'frac': achieved / peak if achieved else None,
+           'frac_physical': phys / (dom_ms * 1e-3) / 1e9 / peak if dom_ms else None,
+           'physical_gbs': phys / (dom_ms * 1e-3) / 1e9 if dom_ms else None,
+           'traffic': (tr['dram_bytes_per_algorithmic_byte'] * alg) if tr else None,
+           'traffic_source': tr['source'] if tr else None,
+           'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg,
+           'iteration_gbs': 2 * x_bytes / (ms_per_step * 1e-3) / 1e9,
+           'iteration_frac_of_2pass_roofline': 2 * x_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
+    out.update(extra)
+    return out
+
+
+def multi_gpu_check(rank, world, device, dist, E, STR, MTR):
+    """Do N NCCL ranks compute the single-GPU answer?  Every rank builds the SAME small global dataset from a CPU
+    seed; rank g fits its shard_bounds slice for K Adam steps with shard_group='world' (one all-reduce of the packed
+    gradient sums per step); rank 0 also fits the whole set alone.  Reports the norm-relative difference of the
+    fitted parameters / losses and whether the replicas' parameters are bit-identical after the K steps."""
+    from oracle import tr_oracle as O            # synthetic data generators only (checker side)
+    K = 5
+    out = {'steps': K, 'world': world}
+    ok = True
+    cases = [('std_f32_single_pass', 'std', (64, 64, 32), 8, 0, torch.float32, 1, 1e-6),
+             ('std_f64_two_pass', 'std', (16, 16, 16, 32), 12, 0, torch.float64, 0, 1e-12),
+             ('mn_f32', 'mn', (100, 50, 20), 6, 10, torch.float32, -1, 1e-6)]
+    for name, kind, dims, R, C, dt, fused, tol in cases:
+        n_glob = 24 * world + 5                         # uneven split on purpose
+        nn = [False] * (len(dims) + 1)
+        if kind == 'std':
+            X, y, _ = O.synth_std(n_glob, dims, R, 4242, dtype=dt)
+            B0 = O.init_std(dims, R, nn, dtype=dt)
+        else:
+            X, y, _ = O.synth_mn(n_glob, dims, R, C, 4243)
+            B0 = O.init_mn(list(dims) + [C], R, nn, scale=0.2)
+        lo, hi = E.shard_bounds(n_glob, rank, world)
+
+        def fit(Xs, ys, group):
+            if kind == 'std':
+                m = STR.CP_linear_regression((Xs.shape[0], *dims), dtype=dt, rank=R, Bcp_init=[b.clone() for b in B0],
+                                             device=device, shard_group=group)
+                if fused >= 0:
+                    m._engine().set_option('fused', fused)
+                m.fit_Adam(Xs.to(device), ys.to(device), lambda_L2=LAMBDA, max_iter=K, tol=0.0, patience=10 ** 9,
+                           Adam_kwargs=ADAM)
+            else:
+                m = MTR.CP_logistic_regression(Xs.to(device), ys, rank=R, Bcp_init=[b.clone() for b in B0], device=device,
+                                               shard_group=group, n_classes=C)
+                m.fit_Adam(lambda_L2=LAMBDA, max_iter=K, tol=0.0, patience=10 ** 9,
+                           weights=np.ones(C, dtype=np.float32), Adam_kwargs=ADAM)
+            th, losses = m.theta.detach().clone(), list(m.loss_running)
+            if kind == 'mn':
+                m.X = None
+            m.close()
+            return th, losses
+
+        th_sh, loss_sh = fit(X[lo:hi], y[lo:hi], 'world')
+        gathered = [torch.empty_like(th_sh) for _ in range(world)]
+        dist.all_gather(gathered, th_sh)
+        identical = all(torch.equal(gathered[0], g) for g in gathered)
+        rec = {'n_global': n_glob, 'replicas_bit_identical': bool(identical), 'tol': tol}
+        if rank == 0:
+            th_1, loss_1 = fit(X, y, None)
+            rec['theta_rel_diff'] = float((th_sh - th_1).abs().max() / th_1.abs().max())
+            rec['loss_rel_diff'] = float(max(abs(a - b) for a, b in zip(loss_sh, loss_1)) / abs(loss_1[0]))
+            rec['pass'] = bool(identical and rec['theta_rel_diff'] <= tol * 10 and rec['loss_rel_diff'] <= tol)
+            ok = ok and rec['pass']
+        dist.barrier()
+        out[name] = rec
+    out['pass'] = bool(ok)
+    return out
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -330,14 +576,18 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help="weak: every rank holds the workload's per-GPU N (default); strong: the workload's N is split over the ranks")
+    ap.add_argument('--secondary', default='cfg3,cfg4,cfg5', help='comma list of further workloads measured after the primary (device-timed only); "" = none')
     ap.add_argument('--n-local', type=int, default=0, help='override samples per GPU (debug)')
+    ap.add_argument('--secondary-n-local', type=int, default=0, help='override samples per GPU of the secondary workloads (debug)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-check', action='store_true', help='skip the multi-rank parity check')
     ap.add_argument('--e2e-steps', type=int, default=2)
-    ap.add_argument('--fused', type=int, default=-1, help='-1 auto, 0 never, 1 always: single-pass cluster kernel (std)')
-    ap.add_argument('--flow', type=int, default=-1, help='-1 auto, 0 never, 1 always: single-launch dataflow kernel')
-    ap.add_argument('--flow-debug', type=int, default=0, help='timing experiments only (wrong results)')
-    ap.add_argument('--flow-window-mb', type=int, default=0, help='dataflow kernel: MB of X kept in flight in L2 (0 = default)')
+    ap.add_argument('--pageable-gib', type=float, default=8.0, help='size of the plain numpy array of the pageable e2e leg')
+    ap.add_argument('--fused', type=int, default=-1, help='-1 auto, 0 never, 1 always: single-pass cluster kernels')
+    ap.add_argument('--flow', type=int, default=-1, help='1: experimental dataflow kernel (needs a FLOW=1 build)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -364,177 +614,70 @@ def main():
     if args.warmup < 3 and rank == 0:
         print(f'note: --warmup {args.warmup} < 3 (timing rules ask for >= 3)', file=sys.stderr)
 
-    wl = args.workload
-    kind, n_local, dims, R, C, dt = WORKLOADS[wl]
-    if args.n_local:
-        n_local = args.n_local
-    D = int(np.prod(dims))
-    elt = 4 if dt == torch.float32 else 8
-    x_bytes = n_local * D * elt
-
-    # ---- data resident in HBM ------------------------------------------------------------
-    X, Fstar = make_device_data(wl, n_local, rank, device)
-    sharder = E.ShardedSum() if world > 1 else E.ShardedSum(enabled=False)
-    nn = [False] * (len(dims) + 1)
-    torch.manual_seed(321)
-    if kind == 'std':
-        eng = E.Engine(dims, R, 0, dt, device)
-        w = torch.ones(R, dtype=dt, device=device)
-        theta_star = torch.cat([f.reshape(-1) for f in Fstar] + [torch.tensor([0.1], dtype=dt)]).to(device)
-        y = eng.forward_std(X, theta_star, w, 0, 50.0, 1.0)
-        y += 0.01 * torch.randn(y.shape, dtype=dt, device=device)
-        B0 = STR.make_BcpInit(list(dims), R, nn, scale=1, device='cpu', dtype=dt)
-        model = STR.CP_linear_regression((n_local, *dims), dtype=dt, rank=R, non_negative=False, Bcp_init=B0,
-                                         device=device, shard_group='world' if world > 1 else None)
-        cw = None
-    else:
-        eng = E.Engine(dims, R, C, torch.float32, device)
-        w = torch.ones(R, device=device)
-        theta_star = torch.cat([f.reshape(-1) for f in Fstar]).to(device)
-        _, y = eng.forward_mn(X, theta_star, w, 0, 50.0, 1.0)
-        B0 = MTR.make_BcpInit(list(dims) + [C], R, nn, scale=0.2, device='cpu')
-        model = None
-        cw = torch.ones(C, device=device)
-    n_total = sharder.total(n_local, device)
-    eng.set_option('fused', args.fused)
-    eng.set_option('flow', args.flow)
-    if args.flow_debug:
-        eng.set_option('flow_debug', args.flow_debug)
-    if args.flow_window_mb:
-        eng.set_option('flow_window_mb', args.flow_window_mb)
-
-    theta = (model.theta if model is not None else
-             torch.cat([b.reshape(-1) for b in B0]).to(device=device, dtype=torch.float32).contiguous())
-    m_, v_, vm_ = torch.zeros_like(theta), torch.zeros_like(theta), torch.zeros_like(theta)
-    gs = torch.empty(eng.n_gradsum, dtype=torch.float64, device=device)
-    grad = torch.empty_like(theta)
-    loss = torch.empty(2, dtype=torch.float64, device=device)
-    W_total = n_total                                     # class weights are ones in the bench
-
-    step_no = [0]
-
-    def step():
-        """One fit iteration: fwd + grad (2 passes over X) + all-reduce + penalty/normalise + Adam."""
-        step_no[0] += 1
-        if kind == 'std':
-            eng.fwd_grad_std(X, y, theta, w, 0, 50.0, 1.0, gradsum=gs)
-            sharder.sum_(gs)
-            eng.finish(gs, 2.0 / n_total, 1.0 / n_total, theta, LAMBDA, 0, 50.0, 1.0, grad=grad, loss=loss)
-        else:
-            eng.fwd_grad_mn(X, y, cw, theta, w, 0, 50.0, 1.0, gradsum=gs)
-            sharder.sum_(gs)
-            eng.finish(gs, 1.0 / W_total, 1.0 / W_total, theta, LAMBDA, 0, 50.0, 1.0, grad=grad, loss=loss)
-        eng.adam_step(theta, grad, m_, v_, vm_, step_no[0], lr=ADAM['lr'])
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    eng.profile(True)
-    launches0 = eng.launches
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    prof = eng.profile_read()
-    eng.profile(False)
-    launches = eng.launches - launches0
-    launch_info = eng.launch_info()
-    n_gradsum = eng.n_gradsum
-    final_loss = loss.cpu().tolist()
-    t = torch.tensor([ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = n_total / (ms_per_step * 1e-3)
+    def maxrank(x):
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---- roofline of the dominant kernel (CUDA events on the launching stream, this rank) ----
-    peak, peak_src = peaks()
-    fwd_ms = prof['fwd_ms'] / max(1, prof['fwd_launches'])
-    grad_ms = prof['grad_ms'] / max(1, prof['grad_launches'])
-    fused_ms = prof['fused_ms'] / max(1, prof['fused_launches'])
     ratios = {}
     try:
         ratios = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_ratios.json')))
     except Exception:
         pass
-    if prof['fused_launches'] > 0:
-        # single-pass kernel: does the work of both passes (algorithmic bytes = 2 x bytes(X), SURVEY §8d / H8)
-        # while reading X from HBM once -> "achieved" exceeds the HBM peak by design; traffic shows the real bytes
-        is_flow = launch_info['path'].startswith('single-launch dataflow')
-        dom, dom_ms, alg = ('k_flow' if is_flow else 'k_fused_std'), fused_ms, 2 * x_bytes
-        extra = {'k_single_ms': fused_ms, 'hbm_gbs_if_x_read_once': x_bytes / (fused_ms * 1e-3) / 1e9,
-                 'hbm_frac_if_x_read_once': x_bytes / (fused_ms * 1e-3) / 1e9 / peak,
-                 'note': ('single-launch dataflow kernel: the gradient warps re-read each sample from L2 a bounded '
-                          'number of samples behind the forward warps' if is_flow else
-                          'single-pass kernel: the second pass over X is served from shared memory') +
-                         ', so DRAM traffic approaches 1 x bytes(X) while the algorithmic (2-pass) byte count is '
-                         '2 x bytes(X); see traffic for the measured DRAM bytes',
-                 'share_of_step': {dom: fused_ms / ms_per_step}}
-    else:
-        dom = 'k_grad' if grad_ms >= fwd_ms else 'k_fwd'
-        dom_ms, alg = max(grad_ms, fwd_ms), x_bytes
-        extra = {'k_fwd_ms': fwd_ms, 'k_grad_ms': grad_ms,
-                 'k_fwd_gbs': x_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None,
-                 'k_grad_gbs': x_bytes / (grad_ms * 1e-3) / 1e9 if grad_ms else None,
-                 'share_of_step': {'k_fwd': fwd_ms / ms_per_step, 'k_grad': grad_ms / ms_per_step}}
-    achieved = alg / (dom_ms * 1e-3) / 1e9
-    tr = ratios.get(f'{dom}_{kind}') or ratios.get(dom)
-    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak,
-                'traffic': (tr['dram_bytes_per_algorithmic_byte'] * alg) if tr else None,
-                'traffic_source': tr['source'] if tr else None,
-                'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg,
-                'iteration_gbs': 2 * x_bytes / (ms_per_step * 1e-3) / 1e9,
-                'iteration_frac_of_2pass_roofline': 2 * x_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
-    roofline.update(extra)
 
-    # ---- end to end through the public API with HOST buffers (std workloads) -----------------
+    # ---- multi-rank parity: N NCCL ranks == one GPU, replicas bit-identical ----------------------
+    check = None
+    if world > 1 and not args.no_check:
+        check = multi_gpu_check(rank, world, device, dist, E, STR, MTR)
+
+    wl = args.workload
+    kind, n_cfg, dims, R, C, dt = WORKLOADS[wl]
+    n_local = args.n_local or n_cfg
+    if args.scaling == 'strong':
+        lo, hi = E.shard_bounds(n_local, rank, world)
+        n_local = hi - lo
+
+    # ---- primary workload, X resident in HBM ---------------------------------------------------
+    wk = Workload(wl, n_local, rank, world, device, E, STR, MTR, fused=args.fused, flow=args.flow)
+    D, elt, x_bytes = wk.D, wk.elt, wk.x_bytes
+    res = timed_steps(wk, args.steps, args.warmup, dist, rank, local_rank, True)
+    n_total, ms_per_step, value = res['n_total'], res['ms_per_step'], res['value']
+    roofline = roofline_of(res, wk, x_bytes, ratios)
+    n_gradsum = wk.eng.n_gradsum
+
+    # ---- strong scaling beside the weak number: the workload's single-GPU N split over the ranks -------------
+    strong = None
+    if args.scaling == 'weak' and world > 1:
+        lo, hi = E.shard_bounds(n_cfg if not args.n_local else args.n_local, rank, world)
+        ns = hi - lo
+        rs = timed_steps(wk, args.steps, args.warmup, dist, rank, local_rank, False, X=wk.X[:ns], y=wk.y[:ns])
+        strong = {'n_total': rs['n_total'], 'n_per_gpu': ns, 'ms_per_step': rs['ms_per_step'], 'value': rs['value'],
+                  'unit': 'samples/s', 'x_bytes_per_gpu': int(ns * D * elt),
+                  'roofline': {k: v for k, v in roofline_of(rs, wk, ns * D * elt, ratios).items()
+                               if k in ('kernel', 'achieved', 'frac', 'frac_physical', 'k_single_ms', 'k_fwd_ms', 'k_grad_ms',
+                                        'share_of_step', 'iteration_frac_of_2pass_roofline')},
+                  'note': 'fixed total N (the single-GPU workload) split over the ranks; the part of a step outside the '
+                          'streaming kernel(s) = small kernels + launches + the all-reduce (1 - sum(share_of_step))'}
+    elif args.scaling == 'weak' and world == 1:
+        # one GPU: what a 1/8 shard of the workload costs per iteration (the strong-scaling tail, measured alone)
+        ns = max(1, (n_cfg if not args.n_local else args.n_local) // 8)
+        rs = timed_steps(wk, args.steps, args.warmup, dist, rank, local_rank, False, X=wk.X[:ns], y=wk.y[:ns])
+        strong = {'proxy': 'one GPU running a 1/8 shard of the workload (what each of 8 ranks does under strong scaling, '
+                           'without the all-reduce)', 'n_per_gpu': ns, 'ms_per_step': rs['ms_per_step'],
+                  'ms_per_step_if_linear': ms_per_step * ns / n_local,
+                  'efficiency_upper_bound': (ms_per_step * ns / n_local) / rs['ms_per_step'],
+                  'share_of_step': roofline_of(rs, wk, ns * D * elt, ratios)['share_of_step']}
+
+    # ---- end to end through the public API with HOST buffers ------------------------------------------------
     e2e = None
-    if not args.no_e2e and kind == 'std':
-        pool_n = int(min(n_local, max(256, (2 << 30) // (D * elt))))
-        pool = torch.empty((pool_n, *dims), dtype=dt, pin_memory=True)
-        pool.copy_(X[:pool_n])
-        Xh = CycledHostArray(pool, n_local)
-        reps = (n_local + pool_n - 1) // pool_n
-        yh = torch.cat([y[:pool_n].cpu()] * reps)[:n_local].contiguous()
-        m2 = STR.CP_linear_regression((n_local, *dims), dtype=dt, rank=R, non_negative=False,
-                                      Bcp_init=[b.clone() for b in B0], device=device,
-                                      shard_group='world' if world > 1 else None)
-        chunk = int(max(1, min(pool_n, (1 << 30) // (D * elt))))
-        m2.fit_Adam(Xh, yh, lambda_L2=LAMBDA, max_iter=1, tol=0.0, patience=10 ** 9, Adam_kwargs=ADAM,
-                    out_of_core=True, chunk_samples=chunk)                       # warm-up pass
-        barrier()
-        t0 = time.perf_counter()
-        m2.fit_Adam(Xh, yh, lambda_L2=LAMBDA, max_iter=args.e2e_steps, tol=0.0, patience=10 ** 9, Adam_kwargs=ADAM,
-                    out_of_core=True, chunk_samples=chunk)
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-        te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
-        e2e = {'value': n_total / e2e_s, 'unit': 'samples/s', 'h2d_bytes_per_step': int(x_bytes),
-               'd2h_bytes_per_step': 8, 'steps': args.e2e_steps, 'ms_per_step': e2e_s * 1e3,
-               'api': 'CP_linear_regression.fit_Adam(X_host, y, out_of_core=True): every iteration streams X '
-                      'from pinned host memory (PCIe-bound); host y uploaded once per call (N x 4 B)',
-               'h2d_gbs_per_gpu': x_bytes / e2e_s / 1e9,
-               'host_buffer': f'{pool_n}-sample pinned pool cycled to N={n_local} (synthetic data)'}
-        del pool, m2
-    elif not args.no_e2e:
+    X, y, B0 = wk.X, wk.y, wk.B0
+    if not args.no_e2e:
         pool_n = int(min(n_local, max(256, (2 << 30) // (D * elt))))
         pool = torch.empty((pool_n, *dims), dtype=dt, pin_memory=True)
         pool.copy_(X[:pool_n])
@@ -542,79 +685,134 @@ def main():
         reps = (n_local + pool_n - 1) // pool_n
         yh = torch.cat([y[:pool_n].cpu()] * reps)[:n_local].contiguous()
         chunk = int(max(1, min(pool_n, (1 << 30) // (D * elt))))
-        m2 = MTR.CP_logistic_regression(Xh, yh, rank=R, non_negative=False, Bcp_init=[b.clone() for b in B0],
-                                        device=device, shard_group='world' if world > 1 else None, n_classes=C,
-                                        out_of_core=True, chunk_samples=chunk)
-        cwh = np.ones(C, dtype=np.float32)
-        m2.fit_Adam(lambda_L2=LAMBDA, max_iter=1, tol=0.0, patience=10 ** 9, weights=cwh, Adam_kwargs=ADAM)   # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        m2.fit_Adam(lambda_L2=LAMBDA, max_iter=args.e2e_steps, tol=0.0, patience=10 ** 9, weights=cwh, Adam_kwargs=ADAM)
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-        te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
-        e2e = {'value': n_total / e2e_s, 'unit': 'samples/s', 'h2d_bytes_per_step': int(x_bytes),
-               'd2h_bytes_per_step': 8, 'steps': args.e2e_steps, 'ms_per_step': e2e_s * 1e3,
-               'api': 'CP_logistic_regression(X_host, y, out_of_core=True).fit_Adam(...): every iteration streams X '
-                      'from pinned host memory (PCIe-bound); host y uploaded once (N x 8 B)',
-               'h2d_gbs_per_gpu': x_bytes / e2e_s / 1e9,
-               'host_buffer': f'{pool_n}-sample pinned pool cycled to N={n_local} (synthetic data)'}
-        del pool, m2
+        group = 'world' if world > 1 else None
+        cwh = np.ones(max(C, 1), dtype=np.float32)
 
-    # ---- the call a user makes: one fit_Adam(X_host, ...) of K iterations, X uploaded ONCE inside the
-    # timed region (pinned, double-buffered) and then resident.  The original X is freed first.
-    if e2e is not None and e2e.get('value') is not None:
-        pool_n = int(min(n_local, max(256, (2 << 30) // (D * elt))))
-        pool = torch.empty((pool_n, *dims), dtype=dt, pin_memory=True)
-        pool.copy_(X[:pool_n])
-        reps = (n_local + pool_n - 1) // pool_n
-        yh = torch.cat([y[:pool_n].cpu()] * reps)[:n_local].contiguous()
-        Xh = CycledHostArray(pool, n_local)
-        X = None
-        model = None
-        eng = None
+        def fit_call(Xarg, yarg, K, **kw):
+            """the reference-facing call: construct the estimator and run fit_Adam with K iterations"""
+            if kind == 'std':
+                m = STR.CP_linear_regression((Xarg.shape[0], *dims), dtype=dt, rank=R, non_negative=False,
+                                             Bcp_init=[b.clone() for b in B0], device=device, shard_group=group)
+                m.fit_Adam(Xarg, yarg, lambda_L2=LAMBDA, max_iter=K, tol=0.0, patience=10 ** 9, Adam_kwargs=ADAM, **kw)
+            else:
+                m = MTR.CP_logistic_regression(Xarg, yarg, rank=R, non_negative=False, Bcp_init=[b.clone() for b in B0],
+                                               device=device, shard_group=group, n_classes=C, **kw)
+                m.fit_Adam(lambda_L2=LAMBDA, max_iter=K, tol=0.0, patience=10 ** 9, weights=cwh, Adam_kwargs=ADAM)
+            return m
+
+        # (a) X larger than HBM / streamed on EVERY iteration (our out_of_core extension): PCIe-bound
+        fit_call(Xh, yh, 1, out_of_core=True, chunk_samples=chunk).close()              # warm-up pass
+        barrier()
+        t0 = time.perf_counter()
+        fit_call(Xh, yh, args.e2e_steps, out_of_core=True, chunk_samples=chunk).close()
+        barrier()
+        e2e_s = maxrank((time.perf_counter() - t0) / args.e2e_steps)
+        streaming = {'value': n_total / e2e_s, 'unit': 'samples/s', 'h2d_bytes_per_step': int(x_bytes),
+                     'd2h_bytes_per_step': 8, 'steps': args.e2e_steps, 'ms_per_step': e2e_s * 1e3,
+                     'api': 'fit_Adam(X_host, y, out_of_core=True): every iteration streams X from pinned host memory',
+                     'h2d_gbs_per_gpu': x_bytes / e2e_s / 1e9}
+
+        # (b) the call a user makes: ONE fit_Adam(X_host, ...) of K iterations, X uploaded once inside the timed
+        # region and then resident.  The resident copy of the device-timed legs is freed first.
+        wk.free()
+        X = y = None
         import gc
         gc.collect()
         torch.cuda.empty_cache()
         K = max(1, args.steps)
         barrier()
         t0 = time.perf_counter()
-        if kind == 'std':
-            m3 = STR.CP_linear_regression((n_local, *dims), dtype=dt, rank=R, non_negative=False,
-                                          Bcp_init=[b.clone() for b in B0], device=device,
-                                          shard_group='world' if world > 1 else None)
-            m3.fit_Adam(Xh, yh, lambda_L2=LAMBDA, max_iter=K, tol=0.0, patience=10 ** 9, Adam_kwargs=ADAM)
-        else:
-            m3 = MTR.CP_logistic_regression(Xh, yh, rank=R, non_negative=False, Bcp_init=[b.clone() for b in B0],
-                                            device=device, shard_group='world' if world > 1 else None, n_classes=C)
-            m3.fit_Adam(lambda_L2=LAMBDA, max_iter=K, tol=0.0, patience=10 ** 9, weights=np.ones(C, dtype=np.float32),
-                        Adam_kwargs=ADAM)
+        m3 = fit_call(Xh, yh, K)
         barrier()
-        call_s = time.perf_counter() - t0
-        tc = torch.tensor([call_s], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
-        call_s = float(tc.item())
-        # e2e.value = the reference-facing call with HOST buffers (the reference's own fit_Adam signature, nothing
-        # resident beforehand, every host<->device copy inside the timed region).  The variant that re-streams X
-        # on every iteration (our out_of_core extension, for X larger than HBM) is kept beside it.
-        streaming = e2e
+        call_s = maxrank(time.perf_counter() - t0)
         y_bytes = n_local * (elt if kind == 'std' else 8)
         e2e = {'value': n_total * K / call_s, 'unit': 'samples/s',
                'h2d_bytes_per_step': int((x_bytes + y_bytes) // K), 'd2h_bytes_per_step': 8,
                'iterations': K, 'seconds': call_s, 'ms_per_step': call_s * 1e3 / K,
                'h2d_bytes_total': int(x_bytes + y_bytes), 'final_loss': float(m3.loss_running[-1]),
+               'h2d_gbs_per_gpu_incl_compute': (x_bytes + y_bytes) / call_s / 1e9,
                'api': ('CP_linear_regression(...).fit_Adam(X_host, y_host, max_iter=K)' if kind == 'std' else
                        'CP_logistic_regression(X_host, y_host, ...).fit_Adam(max_iter=K)') +
                       ': ONE call with the reference signature and K = --steps iterations, timed from construction to '
-                      'return: one pinned double-buffered upload of X and y (h2d_bytes_total; h2d_bytes_per_step is '
+                      'return: one upload of X and y from pinned host memory (h2d_bytes_total; h2d_bytes_per_step is '
                       'that total / K), K resident fit iterations, one 8-byte loss read per iteration',
-               'host_buffer': streaming['host_buffer'],
+               'host_buffer': f'{pool_n}-sample pinned pool cycled to N={n_local} (synthetic data)',
                'streaming_every_iteration': streaming}
-        del pool, m3
+        m3.close()
+        if kind == 'mn':
+            m3.X = None
+        del m3
+        gc.collect()
+        torch.cuda.empty_cache()
+
+        # (c) the same call with what a user of the reference really holds: a plain, PAGEABLE numpy array
+        n_pg = int(min(n_local, max(64, int(args.pageable_gib * (1 << 30)) // (D * elt))))
+        if n_pg > 0 and args.pageable_gib > 0:
+            Xnp = np.empty((n_pg, *dims), dtype=np.float32 if dt == torch.float32 else np.float64)
+            pn = pool.numpy()
+            for lo_ in range(0, n_pg, pool_n):
+                hi_ = min(n_pg, lo_ + pool_n)
+                Xnp[lo_:hi_] = pn[:hi_ - lo_]
+            ynp = yh[:n_pg].numpy().copy()
+            fit_call(Xnp[:max(1, n_pg // 16)], ynp[:max(1, n_pg // 16)], 1).close()     # warm-up (staging ring, threads)
+            barrier()
+            t0 = time.perf_counter()
+            m4 = fit_call(Xnp, ynp, K)
+            barrier()
+            pg_s = maxrank(time.perf_counter() - t0)
+            up = E.upload_stats()
+            pg_bytes = n_pg * D * elt
+            # the pinned-source figure for the SAME size, for a like-for-like ratio
+            m4.close()
+            del m4
+            gc.collect()
+            torch.cuda.empty_cache()
+            Xpin = CycledHostArray(pool, n_pg)
+            barrier()
+            t0 = time.perf_counter()
+            m5 = fit_call(Xpin, yh[:n_pg], K)
+            barrier()
+            pin_s = maxrank(time.perf_counter() - t0)
+            m5.close()
+            del m5
+            e2e['pageable_numpy'] = {
+                'value': n_pg * world * K / pg_s, 'unit': 'samples/s', 'n_per_gpu': n_pg, 'iterations': K,
+                'seconds': pg_s, 'h2d_bytes_total': int(pg_bytes),
+                'upload_seconds': up['seconds'], 'upload_gbs': pg_bytes / up['seconds'] / 1e9 if up['seconds'] else None,
+                'host_fill_seconds': up['host_fill_seconds'], 'upload_threads': up['threads'],
+                'same_size_from_pinned_pool_seconds': pin_s, 'pageable_over_pinned_time': pg_s / pin_s,
+                'api': 'the same fit_Adam call with X a plain np.ndarray (pageable, %.1f GiB): tr_upload stages it through '
+                       'a ring of pinned buffers filled by several host threads' % (pg_bytes / 2 ** 30)}
+            del Xnp, Xpin
+        del pool
+    else:
+        wk.free()
+    gc_collect()
+
+    # ---- further BASELINE configs, device-timed (the north star's multinomial / fp64 / 1 TB configurations) ----
+    secondary = []
+    for swl in [w_ for w_ in args.secondary.split(',') if w_ and w_ != wl and w_ in WORKLOADS]:
+        skind, sn, sdims, sR, sC, sdt = WORKLOADS[swl]
+        sn = args.secondary_n_local or sn
+        if args.scaling == 'strong':
+            lo, hi = E.shard_bounds(sn, rank, world)
+            sn = hi - lo
+        need = sn * int(np.prod(sdims)) * (4 if sdt == torch.float32 else 8) + (6 << 30)
+        free_b, _ = torch.cuda.mem_get_info()
+        enough = maxrank(0.0 if free_b >= need else 1.0) == 0.0
+        if not enough:
+            secondary.append({'workload': DESCR[swl], 'skipped': 'not enough free HBM (%.0f GB needed)' % (need / 1e9)})
+            continue
+        sw = Workload(swl, sn, rank, world, device, E, STR, MTR, fused=args.fused)
+        sr = timed_steps(sw, args.steps, args.warmup, dist, rank, local_rank, False)
+        secondary.append({'workload': DESCR[swl], 'name': swl, 'value': sr['value'], 'unit': 'samples/s',
+                          'ms_per_step': sr['ms_per_step'], 'n_per_gpu': sn, 'n_total': sr['n_total'],
+                          'dtype': fmt_dtype(sdt), 'x_bytes_per_gpu': int(sw.x_bytes), 'scaling': args.scaling,
+                          'roofline': roofline_of(sr, sw, sw.x_bytes, ratios), 'gpu_launches': int(sr['launches']),
+                          'launch': sr['launch_info'], 'final_loss': sr['final_loss']})
+        sw.free()
+        del sw
+        gc_collect()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -623,20 +821,28 @@ def main():
     if rank == 0:
         out = {'metric': 'samples/sec per fit iteration (fwd+grad+step)', 'value': value, 'unit': 'samples/s',
                'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
-               'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-               'dtype': 'f32' if dt == torch.float32 else 'f64', 'data': 'synthetic',
+               'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
+               'dtype': fmt_dtype(dt), 'data': 'synthetic',
                'config': {'workload': DESCR[wl], 'n_per_gpu': n_local, 'n_total': int(n_total),
                           'x_bytes_per_gpu': int(x_bytes), 'optimizer': 'Adam lr=0.01 amsgrad', 'lambda_L2': LAMBDA,
                           'l2_flush': 'not needed: X per GPU (%.1f GB) >> 126 MB L2' % (x_bytes / 1e9)
                           if x_bytes > (1 << 30) else 'X smaller than L2+: numbers are cache-assisted',
                           'parallelism': f'sample-sharded x{world}, one all-reduce of {n_gradsum} doubles/iter',
+                          'allreduce': res['allreduce_via'],
                           'host_cpus_bound_to_gpu_numa_node': numa,
-                          'launch': launch_info},
-               'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches),
-               'clocks': clocks, 'final_loss': final_loss}
+                          'launch': res['launch_info']},
+               'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(res['launches']),
+               'clocks': res['clocks'], 'final_loss': res['final_loss'], 'strong': strong,
+               'multi_gpu_check': check, 'secondary': secondary}
         emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def gc_collect():
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
 
 
 if __name__ == '__main__':

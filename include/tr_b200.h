@@ -150,6 +150,18 @@ int tr_comm_unique_id(void* id128);
 int tr_comm_create(void** comm, const void* id128, int rank, int world, int device);
 int tr_comm_destroy(void* comm);
 
+/* Host array -> device memory (the reference's one `.to(device)` of X, std:339-345 / mn:255) at close to the
+ * pinned-memory DMA rate even when src_host is PAGEABLE: a ring of pinned staging buffers is filled by `threads`
+ * host threads (0 = min(hardware threads, 16); env TR_B200_UPLOAD_THREADS) in parallel slices while the previous
+ * buffer is in flight; memory that is already pinned / registered is copied from in place.  chunk_bytes = size
+ * of one staging buffer (0 = 64 MiB).  Work queued on `stream` before the call is waited for, work queued after
+ * it sees the data; the call returns when src_host may be reused.  Errors: tr_host_last_error().
+ * tr_upload_stats: out4 = { seconds of the last upload, of which host fill seconds, threads used, 1 if staged }. */
+int tr_upload(void* dst_device, const void* src_host, size_t bytes, int device, int threads, size_t chunk_bytes,
+              void* stream);
+int tr_upload_stats(double* out4);
+const char* tr_host_last_error(void);
+
 /* L-BFGS building blocks (torch.optim.LBFGS as used by fit, std:366,392 / mn:355,381; algorithm of
  * torch/optim/lbfgs.py:333-536).  The update history, the two-loop recursion and every dot
  * product stay on the device; the host keeps only the strong-Wolfe control flow and reads back

@@ -14,6 +14,7 @@ SYMBOLS = [
     'tr_backward_std', 'tr_backward_mn', 'tr_finish_grad', 'tr_adam_step', 'tr_last_launch_info', 'tr_profile_enable',
     'tr_profile_read', 'tr_set_option', 'tr_lbfgs_direction', 'tr_lbfgs_point', 'tr_lbfgs_gtd',
     'tr_adam_step_groups', 'tr_allreduce', 'tr_comm_unique_id', 'tr_comm_create', 'tr_comm_destroy',
+    'tr_upload', 'tr_upload_stats', 'tr_host_last_error',
 ]
 
 
@@ -50,6 +51,10 @@ def _load():
     lib.tr_comm_unique_id.argtypes = [vp]
     lib.tr_comm_create.argtypes = [ctypes.POINTER(vp), vp, i32, i32, i32]
     lib.tr_comm_destroy.argtypes = [vp]
+    lib.tr_upload.argtypes = [vp, vp, ctypes.c_size_t, i32, i32, ctypes.c_size_t, vp]
+    lib.tr_upload_stats.argtypes = [ctypes.POINTER(dbl)]
+    lib.tr_host_last_error.argtypes = []
+    lib.tr_host_last_error.restype = ctypes.c_char_p
     lib.tr_last_launch_info.argtypes = [vp, ctypes.POINTER(i64)]
     lib.tr_profile_enable.argtypes = [vp, i32]
     lib.tr_profile_read.argtypes = [vp, ctypes.POINTER(dbl)]
@@ -59,7 +64,7 @@ def _load():
     lib.tr_lbfgs_gtd.argtypes = [vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ('tr_last_error',):
+        if name not in ('tr_last_error', 'tr_host_last_error'):
             fn.restype = i32
     return lib
 

@@ -325,6 +325,51 @@ class ShardedSum:
         return float(self.sum_(t).item())
 
 
+def host_pointer(X, dtype):
+    """(address, keepalive) of a host array that tr_upload can read in place — a C-contiguous numpy array /
+    np.memmap / CPU tensor whose element type already is ``dtype`` — else None."""
+    if isinstance(X, torch.Tensor):
+        if X.device.type == 'cpu' and X.dtype == dtype and X.is_contiguous() and X.numel() > 0:
+            return X.data_ptr(), X
+        return None
+    if isinstance(X, np.ndarray) and X.flags['C_CONTIGUOUS'] and X.size > 0:
+        want = torch.empty((), dtype=dtype).numpy().dtype
+        if X.dtype == want:
+            return int(X.ctypes.data), X
+    return None
+
+
+def upload_threads():
+    """Host threads one upload may use: all CPUs of this process's affinity mask, shared between the ranks of a
+    multi-GPU launch (LOCAL_WORLD_SIZE); 0 = let the library decide."""
+    import os
+    env = os.environ.get('TR_B200_UPLOAD_THREADS')
+    if env:
+        return int(env)
+    local_world = int(os.environ.get('LOCAL_WORLD_SIZE', '1') or 1)
+    if local_world <= 1:
+        return 0
+    try:
+        cpus = len(os.sched_getaffinity(0))
+    except Exception:
+        cpus = os.cpu_count() or 1
+    return max(1, min(16, cpus // local_world))
+
+
+def upload_into(dst, ptr, nbytes, stream, chunk_bytes=0):
+    """tr_upload: pageable (or pinned) host bytes at ``ptr`` -> the device tensor ``dst`` on ``stream``."""
+    rc = _lib.lib.tr_upload(dst.data_ptr(), ctypes.c_void_p(ptr), nbytes, dst.device.index, upload_threads(),
+                            chunk_bytes, ctypes.c_void_p(stream.cuda_stream))
+    if rc != 0:
+        raise TRError(f'tr_upload failed ({rc}): {_lib.lib.tr_host_last_error().decode()}')
+
+
+def upload_stats():
+    out = (ctypes.c_double * 4)()
+    _lib.lib.tr_upload_stats(out)
+    return {'seconds': out[0], 'host_fill_seconds': out[1], 'threads': int(out[2]), 'staged': bool(out[3])}
+
+
 class HostStreamer:
     """Double-buffered host -> device streaming of a sample-major array that stays in host memory
     (numpy array, np.memmap, CPU tensor, or anything with ``.shape`` and ``[lo:hi]`` slicing).
@@ -349,6 +394,8 @@ class HostStreamer:
         self._ready = [torch.cuda.Event() for _ in range(2)]
         self._done = [torch.cuda.Event() for _ in range(2)]
         self._used = [False, False]
+        self._row = row
+        self._ptr = host_pointer(X, dtype)      # in-place source for tr_upload (parallel staging in the library)
 
     def _host_chunk(self, lo, hi, s):
         c = self.X[lo:hi]
@@ -368,11 +415,17 @@ class HostStreamer:
             s = i % 2
             if self._used[s]:
                 self._done[s].synchronize()       # kernels reading dev[s] finished; staging buffer reusable
-            src = self._host_chunk(lo, hi, s)
-            self._copy.wait_event(self._done[s]) if self._used[s] else None
-            with torch.cuda.stream(self._copy):
-                self._dev[s][:hi - lo].copy_(src, non_blocking=True)
+            if self._ptr is not None:
+                # the library stages the chunk through its pinned ring with several host threads and returns
+                # when the DMA is done; the kernels of the previous chunk keep the GPU busy meanwhile
+                upload_into(self._dev[s][:hi - lo], self._ptr[0] + lo * self._row, (hi - lo) * self._row, self._copy)
                 self._ready[s].record(self._copy)
+            else:
+                src = self._host_chunk(lo, hi, s)
+                self._copy.wait_event(self._done[s]) if self._used[s] else None
+                with torch.cuda.stream(self._copy):
+                    self._dev[s][:hi - lo].copy_(src, non_blocking=True)
+                    self._ready[s].record(self._copy)
             main.wait_event(self._ready[s])
             yield lo, hi, self._dev[s][:hi - lo]
             self._done[s].record(main)
@@ -381,7 +434,9 @@ class HostStreamer:
 
 def upload_resident(X, dtype, device, chunk_bytes=256 << 20):
     """Host array (numpy / memmap / CPU tensor / anything with ``.shape`` and ``[lo:hi]``) -> ONE resident
-    device tensor.  Chunks are copied on a side stream straight into their place; chunks that are not
+    device tensor.  A contiguous array of the model dtype goes through the library's tr_upload (parallel
+    staging, see csrc/tr_host.cu).  Anything else (dtype conversion needed, array-like objects) is copied chunk
+    by chunk on a side stream straight into its place; chunks that are not
     already pinned go through two pinned staging buffers, so the host-side staging copy of chunk i+1
     overlaps the DMA of chunk i.  (``torch.as_tensor(X).to(device)`` does one synchronous pageable copy
     and needs X materialised as a single host tensor first.)"""
@@ -392,6 +447,12 @@ def upload_resident(X, dtype, device, chunk_bytes=256 << 20):
     step = int(max(1, min(N, chunk_bytes // row)))
     out = torch.empty((N, *shape), dtype=dtype, device=device)
     main = torch.cuda.current_stream(device)
+    hp = host_pointer(X, dtype)
+    if hp is not None:
+        # one contiguous host array of the right type (the reference's case: a numpy array / CPU tensor):
+        # tr_upload stages it through pinned buffers with several host threads, or DMAs in place if it is pinned
+        upload_into(out, hp[0], N * row, main)
+        return out
     copy = torch.cuda.Stream(device=device)
     copy.wait_stream(main)
     pin, busy = [None, None], [None, None]
