@@ -102,43 +102,15 @@ struct EpiMnArgs {
     double* part;       // (gridDim.x): sum -omega log Q
 };
 
-// model()'s softmax (mn:180-187), CrossEntropyLoss on the probabilities (second softmax, mn:364-366 /
-// 448-450) and its backward down to v[n,r], for sample n.  rd = reader of the sample's tile partials;
-// sFC (C,R) / sW (R) in shared memory (double).
-// RMAX >= R and 32*JC >= C are compile-time bounds of the unrolled loops (register arrays u[RMAX], z/P/dP/dZ[JC]):
-// the kernels are instantiated for (8,1), (16,1) and (TR_MAX_RANK_MN, TR_JC); the arithmetic on the live
-// entries — and therefore every bit of the result — does not depend on the bounds.
-template <typename T, typename Reader, int RMAX = TR_MAX_RANK_MN, int JC = TR_JC>
-__device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n, const Reader& rd, int lane,
-                                              const double* sFC, const double* sW, double& loss) {
+// Everything after the contraction, given the sample's u[r] (already summed over the feature axis, replicated in
+// every lane): logits, softmax, second softmax, loss, dP -> dZ -> v.  yn / omega = the sample's label and class
+// weight (loaded by the caller so that the loads can be in flight early; ignored when a.y == nullptr).
+// vout (may be null): v[r] = w_r sum_c dZ[c] FC[c,r] for r < R, replicated in every lane.
+template <typename T, int RMAX = TR_MAX_RANK_MN, int JC = TR_JC>
+__device__ __forceinline__ void epi_mn_core(const EpiMnArgs<T>& a, long long n, const double (&u)[RMAX], int lane,
+                                            const double* sFC, const double* sW, int yn, double omega, double& loss,
+                                            double* vout) {
     const int R = a.R, C = a.C;
-    // u[r] = sum over warp tiles: lane t-strided, all channels of a tile are contiguous, so every
-    // lane keeps RKs independent accumulators and several tiles' loads in flight
-    double u[RMAX];
-    bool ok;
-    do {
-        ok = true;
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) u[r] = 0.0;
-        // four tiles per step: their partials are pre-summed in T in a fixed order, ((a+b)+(c+d)), and only
-        // the sum is widened — the T -> double conversions (XU pipe) were 36 % of this kernel's issue slots
-        for (int t0 = lane; t0 < a.WT; t0 += 128) {
-#pragma unroll
-            for (int r = 0; r < RMAX; ++r)
-                if (r < R) {
-                    T v[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        v[q] = (T)0;
-                        if (t0 + 32 * q < a.WT) ok &= rd.get(t0 + 32 * q, r, v[q]);
-                    }
-                    u[r] += (double)((v[0] + v[1]) + (v[2] + v[3]));
-                }
-        }
-    } while (!__all_sync(TR_FULL, ok));
-#pragma unroll
-    for (int r = 0; r < RMAX; ++r)
-        if (r < R) u[r] = warp_sum(u[r]);
     // logits of this lane's classes, softmax
     double z[JC], P[JC];
     double zmax = -INFINITY;
@@ -209,8 +181,6 @@ __device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n
             qs += Q[jc];
         }
         qs = warp_sum(qs);
-        const int yn = (int)a.y[n];
-        const double omega = a.class_w ? (double)a.class_w[yn] : 1.0;
 #pragma unroll
         for (int jc = 0; jc < JC; ++jc) {
             const int c = lane + 32 * jc;
@@ -242,6 +212,7 @@ __device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n
                 if (c < C) s += dZ[jc] * sFC[c * R + r];
             }
             s = warp_sum(s) * sW[r];
+            if (vout) vout[r] = s;
             if (lane == 0) {
                 if (a.V) a.V[n * a.RKs + r] = tr_canon((T)s);
                 if (a.u_ws) a.u_ws[n * R + r] = (T)u[r];
@@ -249,6 +220,52 @@ __device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n
         }
     }
     if (a.V && lane >= R && lane < a.RKs) a.V[n * a.RKs + lane] = (T)0;   // padding channels
+}
+
+// model()'s softmax (mn:180-187), CrossEntropyLoss on the probabilities (second softmax, mn:364-366 /
+// 448-450) and its backward down to v[n,r], for sample n.  rd = reader of the sample's tile partials;
+// sFC (C,R) / sW (R) in shared memory (double).
+// RMAX >= R and 32*JC >= C are compile-time bounds of the unrolled loops (register arrays u[RMAX], z/P/dP/dZ[JC]):
+// the kernels are instantiated for (8,1), (16,1) and (TR_MAX_RANK_MN, TR_JC); the arithmetic on the live
+// entries — and therefore every bit of the result — does not depend on the bounds.
+template <typename T, typename Reader, int RMAX = TR_MAX_RANK_MN, int JC = TR_JC>
+__device__ __forceinline__ void epi_mn_sample(const EpiMnArgs<T>& a, long long n, const Reader& rd, int lane,
+                                              const double* sFC, const double* sW, double& loss) {
+    const int R = a.R;
+    // u[r] = sum over warp tiles: lane t-strided, all channels of a tile are contiguous, so every
+    // lane keeps RKs independent accumulators and several tiles' loads in flight
+    double u[RMAX];
+    bool ok;
+    do {
+        ok = true;
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) u[r] = 0.0;
+        // four tiles per step: their partials are pre-summed in T in a fixed order, ((a+b)+(c+d)), and only
+        // the sum is widened — the T -> double conversions (XU pipe) were 36 % of this kernel's issue slots
+        for (int t0 = lane; t0 < a.WT; t0 += 128) {
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r)
+                if (r < R) {
+                    T v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        v[q] = (T)0;
+                        if (t0 + 32 * q < a.WT) ok &= rd.get(t0 + 32 * q, r, v[q]);
+                    }
+                    u[r] += (double)((v[0] + v[1]) + (v[2] + v[3]));
+                }
+        }
+    } while (!__all_sync(TR_FULL, ok));
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r)
+        if (r < R) u[r] = warp_sum(u[r]);
+    int yn = 0;
+    double omega = 1.0;
+    if (a.y != nullptr && a.dP_in == nullptr) {
+        yn = (int)a.y[n];
+        omega = a.class_w ? (double)a.class_w[yn] : 1.0;
+    }
+    epi_mn_core<T, RMAX, JC>(a, n, u, lane, sFC, sW, yn, omega, loss, nullptr);
 }
 
 template <typename T, int RMAX = TR_MAX_RANK_MN, int JC = TR_JC>

@@ -48,6 +48,28 @@ def dev(t, dtype=None):
     return t.to(device=DEV, dtype=dtype or t.dtype).contiguous()
 
 
+_FLOW = []
+
+
+def flow_built():
+    """The experimental dataflow kernel (tr_flow.cuh) is only in builds made with `make FLOW=1`."""
+    if not _FLOW:
+        from tensor_regression_b200 import engine
+        eng = engine.Engine((4, 4), 2, 0, torch.float32, DEV)
+        try:
+            eng.set_option('flow', 1)
+            _FLOW.append(True)
+        except engine.TRError:
+            _FLOW.append(False)
+        eng.close()
+    return _FLOW[0]
+
+
+def need_flow():
+    if not flow_built():
+        pytest.skip('library built without the experimental dataflow kernel (make FLOW=1)')
+
+
 # ------------------------------------------------------------------------------------------
 # (a) golden fixtures: kernels through the C ABI
 # ------------------------------------------------------------------------------------------
@@ -463,6 +485,7 @@ FLOW_STD = [
 @pytest.mark.parametrize('name,N,dims,R,dt', FLOW_STD, ids=[c[0] for c in FLOW_STD])
 @pytest.mark.parametrize('window', [32, 1], ids=['win32', 'win1'])
 def test_flow_std_matches_two_pass_and_oracle(name, N, dims, R, dt, window):
+    need_flow()
     X, y, _ = O.synth_std(N, dims, R, 1234 + 7, dtype=dt)
     y = y.reshape(-1)
     nn = [True] + [False] * len(dims)
@@ -504,6 +527,7 @@ FLOW_MN = [
 
 @pytest.mark.parametrize('name,N,dims,C,R,dt', FLOW_MN, ids=[c[0] for c in FLOW_MN])
 def test_flow_mn_matches_two_pass_and_oracle(name, N, dims, C, R, dt):
+    need_flow()
     X, y, _ = O.synth_mn(N, dims, R, C, 1234 + 3)
     X = X.to(dt)
     nn = [False, True] + [False] * (len(dims) - 1)
@@ -534,6 +558,7 @@ def test_flow_mn_matches_two_pass_and_oracle(name, N, dims, C, R, dt):
 
 
 def test_flow_not_eligible_fails_loudly():
+    need_flow()
     from tensor_regression_b200 import engine
     dims, R = (5, 7, 3), 2                       # D = 105: rows are not 16-byte multiples
     X, y, _ = O.synth_std(64, dims, R, 3)
@@ -906,8 +931,8 @@ def test_randomised_geometry_sweep_vs_oracle():
         from tensor_regression_b200 import engine as _E
         for opt in ('fused', 'flow'):
             eng.set_option('fused', 0)
-            eng.set_option(opt, 1)
             try:
+                eng.set_option(opt, 1)
                 alt = eng.fwd_grad_std(dev(X), dev(y), dev(O.pack(B0, bias)), dev(w), mask, 50.0, 1.0)
             except _E.TRError:
                 alt = None                      # geometry / alignment not eligible: loud refusal, not a fallback
@@ -927,8 +952,8 @@ def test_randomised_geometry_sweep_vs_oracle():
         cm = O.closed_form_mn(Xm.double(), ym, [b.double() for b in Bm], w.double(), nn, cw.double().numpy())
         assert rel(P, cm['P']) < tol, ('mn P', case, dims, R, C, N, dt, rel(P, cm['P']))
         assert rel(gm, cm['gradsum']) < tol, ('mn', case, dims, R, C, N, dt, rel(gm, cm['gradsum']))
-        engm.set_option('flow', 1)
         try:
+            engm.set_option('flow', 1)
             gf = engm.fwd_grad_mn(dev(Xm), dev(ym), dev(cw), dev(O.pack(Bm)), dev(w), mask_mn, 50.0, 1.0)
         except _E.TRError:
             gf = None
