@@ -15,6 +15,7 @@
 #include "tr_dispatch.h"
 #include "tr_small.cuh"
 #include "tr_fused.cuh"
+#include "tr_fused_mn.h"
 
 namespace {
 
@@ -97,11 +98,13 @@ struct tr_handle {
     int fused_pace = 0;                 // cycles between TMA issues (tuning knob, option "fused_pace")
     int fused_piece = 32768;            // bytes per bulk-copy instruction (option "fused_piece")
     int last_fused = 0;
+    int fused_cl = 0;                   // testing knob (option "fused_cl"): force the cluster size of the single-pass multinomial kernel
     std::map<const void*, int> occ_clusters;
     int flow_mode = 0;                  // dataflow kernel (tr_flow.cuh), experimental: 0 never (default), 1 always (error when
                                         // not eligible); -1 is accepted and currently means 0 (it measured slower)
     long long flow_window_mb = 32;      // bytes of X the forward warps may lead the gradient warps by (option "flow_window_mb")
     Buf flow_ring, flow_sync;
+    Buf Apart, Spart;                   // single-pass multinomial kernel: flushed A / S partial sums
     int flow_debug = 0;
 };
 
@@ -462,6 +465,198 @@ int run_fused_std(tr_handle* h, const T* X, const T* y, long long N, const T* th
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// single-pass fused path (multinomial model, tr_fused_mn.cuh): plan + launch
+// ---------------------------------------------------------------------------------------------
+struct FusedMnPlan {
+    int ok;
+    int CL, NS, NC, nchunk, IKC, RKS, rows_max, NR;
+    long long spc;
+    unsigned stage_x, stage_t, head;
+    size_t smem;
+    const void* kern;
+};
+
+template <typename T> const TrmEntry* trm_find(int IKC, int RKS);
+static const TrmEntry* trm_scan(const TrmEntry* t, int n, int IKC, int RKS) {
+    for (int i = 0; i < n; ++i)
+        if (t[i].IKC == IKC && t[i].RKS == RKS) return &t[i];
+    return nullptr;
+}
+template <> const TrmEntry* trm_find<float>(int IKC, int RKS) {
+    int n; const TrmEntry* t; const TrmEntry* e;
+    t = trm_entries_f32_0(&n); if ((e = trm_scan(t, n, IKC, RKS))) return e;
+    t = trm_entries_f32_1(&n); if ((e = trm_scan(t, n, IKC, RKS))) return e;
+    t = trm_entries_f32_2(&n); if ((e = trm_scan(t, n, IKC, RKS))) return e;
+    return nullptr;
+}
+template <> const TrmEntry* trm_find<double>(int IKC, int RKS) {
+    int n; const TrmEntry* t = trm_entries_f64_0(&n);
+    return trm_scan(t, n, IKC, RKS);
+}
+
+// fp->ok = 1 when the geometry fits: last feature mode = 2..8 16-byte chunks, rank <= 8, classes <= 32, the rows of
+// a sample spread over a cluster with <= TRM_GMAX*128 rows per CTA and >= 4 shared-memory stages
+template <typename T>
+int plan_fused_mn(tr_handle* h, long long N, const void* X, FusedMnPlan* fp) {
+    fp->ok = 0;
+    const Geo& g = h->geo;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    if (g.C < 1 || g.C > 32 || g.R > TRM_RKMAX || g.k < 2 || !vec_ok(X, g.D, sizeof(T)) || N < 1) return TR_OK;
+    const int IK = g.dims[g.k - 1];
+    if (IK % VEC != 0) return TR_OK;
+    const int IKC = IK / VEC;
+    const TrmEntry* ent = nullptr;
+    int RKS = std::max(2, (g.R + 1) / 2 * 2);
+    for (; RKS <= TRM_RKMAX && !(ent = trm_find<T>(IKC, RKS)); RKS += 2) {}
+    if (!ent) return TR_OK;
+    const int NR = (int)(g.D / IK);
+    size_t head = (sizeof(FusedMnCtl<T>) + 15) / 16 * 16;
+    head += (size_t)IK * RKS * sizeof(T);
+    head += (size_t)TRM_GMAX * TRM_NCT * RKS * sizeof(T);
+    head = (head + 15) / 16 * 16;
+    head += (size_t)(g.C * g.R + g.R) * sizeof(double);
+    head = (head + 127) / 128 * 128;
+    const size_t budget = 226 * 1024;
+    int bestCL = 0, bestNS = 0;
+    unsigned best_sx = 0, best_st = 0;
+    for (int CL = 1; CL <= TRM_MAX_CL; CL *= 2) {
+        if (h->fused_cl > 0 && CL != h->fused_cl) continue;
+        const int rows_max = (NR + CL - 1) / CL;
+        if (rows_max > TRM_GMAX * TRM_NCT) continue;
+        const size_t sx = ((size_t)rows_max * IK * sizeof(T) + 127) / 128 * 128;
+        const size_t st = ((size_t)rows_max * RKS * sizeof(T) + 15) / 16 * 16;
+        if (head + 4 * (sx + st) > budget) continue;
+        int NS = (int)((budget - head) / (sx + st));
+        if (NS > TRM_MAX_NS) NS = TRM_MAX_NS;
+        // the smallest cluster that still gives a deep pipeline (>= 6 stages); otherwise the deepest one
+        const bool better = bestCL == 0 || (bestNS < 6 && NS > bestNS);
+        if (better) { bestCL = CL; bestNS = NS; best_sx = (unsigned)sx; best_st = (unsigned)st; }
+    }
+    if (bestCL == 0) return TR_OK;
+    const int CL = bestCL, NS = bestNS;
+    const size_t smem = head + (size_t)NS * (best_sx + best_st);
+    const void* key = (const void*)(((uintptr_t)ent->kern + (uintptr_t)CL) ^ ((uintptr_t)smem << 20));
+    int NC = 0;
+    auto it = h->occ_clusters.find(key);
+    if (it != h->occ_clusters.end()) {
+        NC = it->second;
+    } else {
+        { int rc = raise_smem_limit(h, ent->kern, smem); if (rc) return rc; }
+        bool okc = true;
+        if (CL > 8 && cudaFuncSetAttribute(ent->kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); okc = false; }
+        if (okc) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(CL * h->sms), 1, 1);
+            cfg.blockDim = dim3(TRM_NT, 1, 1);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&NC, ent->kern, &cfg);
+            if (e != cudaSuccess) { cudaGetLastError(); NC = 0; }
+        }
+        h->occ_clusters[key] = NC;
+    }
+    if (NC < 1) return TR_OK;
+    if (h->fused_cl == 0 && (long long)NC * CL * 10 < (long long)h->sms * 6) return TR_OK;   // would leave > 40 % of the SMs idle
+    if (NC > N) NC = (int)N;
+    fp->CL = CL; fp->NS = NS; fp->NC = NC; fp->IKC = IKC; fp->RKS = RKS; fp->NR = NR;
+    fp->rows_max = (NR + CL - 1) / CL;
+    fp->stage_x = best_sx; fp->stage_t = best_st; fp->head = (unsigned)head; fp->smem = smem; fp->kern = ent->kern;
+    const long long cnt = (N + NC - 1) / NC;
+    const long long target = sizeof(T) == 4 ? 2048 : (1LL << 40);
+    long long nchunk = std::max<long long>(1, (cnt + target - 1) / target);
+    fp->nchunk = (int)nchunk;
+    fp->spc = std::max<long long>(1, (cnt + nchunk - 1) / nchunk);
+    fp->ok = 1;
+    return TR_OK;
+}
+
+template <typename T> int launch_dfc(tr_handle* h, int dgrid, const T* w, long long N, cudaStream_t st);
+
+template <typename T>
+int run_fused_mn(tr_handle* h, const T* X, const long long* y, const T* class_w, long long N, const T* theta, const T* w,
+                 uint32_t nn_mask, double beta, double thr, const FusedMnPlan& fp, double* gradsum, T* P, cudaStream_t st) {
+    const Geo& g = h->geo;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int IK = fp.IKC * VEC;
+    int rc;
+    const size_t slots = (size_t)fp.NC * fp.nchunk;
+    const size_t a_bytes = slots * fp.CL * TRM_NWG * (size_t)IK * fp.RKS * sizeof(T);
+    const size_t s_bytes = slots * (size_t)fp.RKS * fp.NR * sizeof(T);
+    if ((rc = ensure(h, h->FtT, (size_t)g.pf * sizeof(T)))) return rc;
+    if ((rc = ensure(h, h->Ft64, (size_t)g.pf * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->u_ws, (size_t)N * g.R * sizeof(T)))) return rc;
+    if ((rc = ensure(h, h->dZ_ws, (size_t)N * g.C * sizeof(T)))) return rc;
+    if ((rc = ensure(h, h->dfc_part, (size_t)h->sms * 2 * g.C * g.R * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->epi_part, std::max((size_t)fp.NC * fp.CL, (size_t)h->sms * 8) * 2 * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->Apart, a_bytes))) return rc;
+    if ((rc = ensure(h, h->Spart, s_bytes))) return rc;
+    if ((rc = ensure(h, h->Gred, (size_t)fp.RKS * fp.NR * sizeof(double)))) return rc;
+    k_prep<T><<<std::max(1, std::min(64, (g.pf + 255) / 256)), 256, 0, st>>>(theta, g, nn_mask, beta, thr,
+                                                                           (T*)h->FtT.p, (double*)h->Ft64.p);
+    TR_LAUNCH_CHECK(h);
+    // slots of chunks a cluster never reaches must be defined for the reductions
+    TR_CUDA(h, cudaMemsetAsync(h->Apart.p, 0, a_bytes, st));
+    TR_CUDA(h, cudaMemsetAsync(h->Spart.p, 0, s_bytes, st));
+    FusedMnArgs<T> fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.X = X; fa.y = y; fa.class_w = class_w; fa.N = N; fa.FtT = (const T*)h->FtT.p; fa.Ft64 = (const double*)h->Ft64.p;
+    fa.w = w; fa.geo = g; fa.NR = fp.NR; fa.Apart = (T*)h->Apart.p; fa.Spart = (T*)h->Spart.p; fa.P = P;
+    fa.u_ws = (T*)h->u_ws.p; fa.dZ_ws = (T*)h->dZ_ws.p; fa.losspart = (double*)h->epi_part.p;
+    fa.CL = fp.CL; fa.NC = fp.NC; fa.NS = fp.NS; fa.nchunk = fp.nchunk; fa.spc = fp.spc;
+    fa.stage_x_bytes = fp.stage_x; fa.stage_t_bytes = fp.stage_t; fa.head_bytes = fp.head;
+    fa.piece = (unsigned)h->fused_piece;
+    if ((rc = raise_smem_limit(h, fp.kern, fp.smem))) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(fp.CL * fp.NC), 1, 1);
+    cfg.blockDim = dim3(TRM_NT, 1, 1);
+    cfg.dynamicSmemBytes = fp.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)fp.CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (h->prof) { rc = prof_fold(h, false); if (rc) return rc; TR_CUDA(h, cudaEventRecord(h->ev[4], st)); }
+    {
+        void* kargs[] = {(void*)&fa};
+        TR_CUDA(h, cudaLaunchKernelExC(&cfg, fp.kern, kargs));
+    }
+    TR_LAUNCH_CHECK(h);
+    if (h->prof) { TR_CUDA(h, cudaEventRecord(h->ev[5], st)); h->ev_set[2] = true; }
+    // loss, class-factor gradient
+    k_colsum<<<1, 128, 0, st>>>((const double*)h->epi_part.p, fp.NC * fp.CL, 1, gradsum + g.pf);
+    TR_LAUNCH_CHECK(h);
+    const int dgrid = (int)std::min<long long>((N + 63) / 64, (long long)h->sms * 2);
+    if ((rc = launch_dfc<T>(h, dgrid, w, N, st))) return rc;
+    k_colsum<<<g.C * g.R, 128, 0, st>>>((const double*)h->dfc_part.p, dgrid, g.C * g.R, gradsum + g.pfeat);
+    TR_LAUNCH_CHECK(h);
+    // last feature mode: sum of the flushed A partials
+    k_reduce_A<T><<<IK * g.R, 128, 0, st>>>((const T*)h->Apart.p, (int)(slots * fp.CL * TRM_NWG), IK, fp.RKS, g.R,
+                                            gradsum + g.foff[g.k - 1]);
+    TR_LAUNCH_CHECK(h);
+    // other feature modes: S (rows x channels) summed over the slots, then its (k-1)-mode MTTKRP
+    const long long tot = (long long)fp.RKS * fp.NR;
+    const int rgrid = (int)std::min<long long>((tot + 255) / 256, (long long)h->sms * 8);
+    k_reduce_G<T><<<rgrid, 256, 0, st>>>((const T*)h->Spart.p, (int)slots, fp.RKS, fp.NR, fp.NR, (double*)h->Gred.p);
+    TR_LAUNCH_CHECK(h);
+    MtArgs ma;
+    ma.G = (const double*)h->Gred.p; ma.Ft64 = (const double*)h->Ft64.p; ma.w = w;
+    ma.w_is_f64 = sizeof(T) == 8; ma.per_rank = 1; ma.geo = g; ma.gradsum = gradsum;
+    ma.geo.k = g.k - 1;
+    ma.geo.D = fp.NR;
+    int rows = 0;
+    for (int m = 0; m < g.k - 1; ++m) rows += g.dims[m];
+    k_mttkrp<<<rows, TR_TPB, 0, st>>>(ma);
+    TR_LAUNCH_CHECK(h);
+    h->info[0] = h->launches; h->info[1] = fp.CL * fp.NC; h->info[2] = fp.CL; h->info[3] = fp.NS;
+    h->info[4] = fp.NC; h->info[5] = fp.nchunk; h->info[6] = fp.RKS; h->info[7] = -(16 / (int)sizeof(T));
+    h->last_fused = 1;
+    return TR_OK;
+}
+
 // class-factor gradient partial sums (dZ_ws, u_ws -> dfc_part)
 template <typename T>
 int launch_dfc(tr_handle* h, int dgrid, const T* w, long long N, cudaStream_t st) {
@@ -718,6 +913,20 @@ int mn_t(tr_handle* h, const void* X, const long long* y, const void* class_w, l
     Plan pl; const KEntry<T>* e; int rc;
     const Geo& g = h->geo;
     h->last_fused = 0;
+    if (y != nullptr && dP_in == nullptr && pred == nullptr && h->fused_mode != 0) {
+        FusedMnPlan fp;
+        if ((rc = plan_fused_mn<T>(h, N, X, &fp))) return rc;
+        if (h->fused_mode == 1 && !fp.ok)
+            return fail(h, TR_ERR_UNSUPPORTED, "fused=1 requested but this geometry / alignment is not eligible for the single-pass multinomial kernel");
+        // auto: as for the standard model — every cluster has samples to pipeline and X is well beyond L2; rows whose
+        // 16-byte chunk count is even make the row-per-thread shared-memory reads bank-conflicted: two-pass is kept
+        const bool big = (size_t)N * (size_t)g.D * sizeof(T) >= 3 * h->l2_bytes;
+        if (fp.ok && (h->fused_mode == 1 || (N >= 8LL * fp.NC && big && (fp.IKC & 1)))) {
+            h->launches = 0;
+            return run_fused_mn<T>(h, (const T*)X, y, (const T*)class_w, N, (const T*)theta, (const T*)w, nn_mask, beta, thr,
+                                   fp, gradsum, (T*)P, st);
+        }
+    }
 #ifdef TR_WITH_FLOW
     if (y != nullptr && dP_in == nullptr && pred == nullptr && h->flow_mode == 1) {
         FlowPlan fl; const KEntry<T>* fe = nullptr;
@@ -833,7 +1042,7 @@ int tr_destroy(tr_handle* h) {
     DeviceGuard dg(h->device);
     cudaDeviceSynchronize();
     Buf* bufs[] = {&h->FtT, &h->Ft64, &h->partial, &h->V, &h->u_ws, &h->dZ_ws, &h->Gpart, &h->Gred, &h->epi_part, &h->dfc_part,
-                   &h->flow_ring, &h->flow_sync};
+                   &h->flow_ring, &h->flow_sync, &h->Apart, &h->Spart};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
@@ -1161,6 +1370,12 @@ int tr_set_option(tr_handle* h, const char* name, int64_t value) {
         return TR_OK;
     }
     if (strcmp(name, "fused_pace") == 0) { h->fused_pace = (int)value; return TR_OK; }
+    if (strcmp(name, "fused_cl") == 0) {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
+            return fail(h, TR_ERR_INVALID, "fused_cl must be 0 (auto), 1, 2, 4, 8 or 16");
+        h->fused_cl = (int)value;
+        return TR_OK;
+    }
     if (strcmp(name, "fused_piece") == 0) {
         if (value < 16 || value % 16) return fail(h, TR_ERR_INVALID, "fused_piece must be a positive multiple of 16");
         h->fused_piece = (int)value;

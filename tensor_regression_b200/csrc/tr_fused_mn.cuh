@@ -1,0 +1,454 @@
+// tr_fused_mn.cuh — single-pass fused forward + gradient kernel for the MULTINOMIAL model (SURVEY H8 ii,
+// VERDICT r1 item 3): X is read from HBM once per fit iteration, as in k_fused_std, but the R gradient
+// channels do not fit a dense D x R accumulator per cluster, so the CP structure is used on both sides.
+//
+// Split the feature axis into ROWS x INNER:  inner = the last feature mode (I_k = IKC 16-byte chunks),
+// rows = all other modes (NR = D / I_k).  With K[i,r] = F12[row,r] * F3[i_k,r]  (F12 = product of the other
+// modes' factor rows, F3 = the last mode's factor):
+//
+//   forward   t[row,r]  = sum_{i_k} X[n,row,i_k] F3[i_k,r]            (thread-private: a thread owns whole rows)
+//             u[n,r]    = sum_row  t[row,r] F12[row,r]                 (warp shuffle + cluster exchange)
+//   epilogue  P = softmax(Z), Q = softmax(P), loss, dZ, v[n,r]          (tr_epi.cuh, once per sample)
+//   gradient  A[i_k,r]  += X[n,row,i_k] * (v[n,r] F12[row,r])           -> dFt_k   (I_k x R sums per thread)
+//             S[row,r]  += v[n,r] * t[row,r]                            -> dFt_m, m < k, by a (k-1)-mode MTTKRP of S
+//
+// so a cluster keeps I_k*R + NR*R running sums instead of D*R, at R FMA per element in each phase — the same
+// arithmetic per element as the two-pass kernels.  t[row,:] stays in shared memory next to the sample until the
+// gradient phase has used it.
+//
+// One CLUSTER holds one sample: CTA c owns a contiguous range of rows, NS stages deep.  512 threads per CTA:
+//   warps 0-3    forward          (wait full[s]; t, u partial -> pA, arrive redA[s])
+//   warps 4-7    gradient A       (chunks [0,QA) of every row -> A;              wait rready[s], arrive empty[s])
+//   warps 8-11   gradient B       (chunks [QA,IKC) of every row -> A, and S;     wait rready[s], arrive empty[s])
+//   warp 12      TMA producer     (cp.async.bulk of the CTA's rows of sample j into stage j % NS)
+//   warp 13      reducer          (sums the 4 warp partials, sends the CTA partial to the sample's OWNER CTA)
+//   warp 14      epilogue         (for the samples this CTA owns, i mod CL == rank: sums the CL partials, runs the
+//                                  per-sample epilogue in fp64, broadcasts v[n,:] to every CTA of the cluster)
+// All hand-offs are mbarriers; partials and v travel through DSMEM with st.async (data + complete_tx together).
+// Deterministic: fixed summation orders, no atomics.
+#pragma once
+#include "tr_fused.cuh"
+#include "tr_epi.cuh"
+
+#define TRM_NWF 4
+#define TRM_NWG 4
+#define TRM_NCT 128
+#define TRM_NT 512
+#define TRM_GMAX 3                      // rows per thread: a CTA holds at most TRM_GMAX * 128 rows
+#define TRM_MAX_NS 8
+#define TRM_MAX_CL 16
+#define TRM_QO (TRM_MAX_NS + 2)         // partial slots at the owner (> NS / CL + 1 owned samples can be in flight)
+#define TRM_RKMAX 8
+
+template <typename T>
+struct FusedMnArgs {
+    const T* X;
+    const long long* y;
+    const T* class_w;
+    long long N;
+    const T* FtT;            // softplus-ed factors (T)
+    const double* Ft64;      // same in double (class factor for the epilogue)
+    const T* w;              // rank weights
+    Geo geo;
+    int NR;                  // rows per sample = D / I_k
+    T* Apart;                // (NC * nchunk, CL, TRM_NWG, I_k * RKS)
+    T* Spart;                // (NC * nchunk, RKS, NR)
+    T* P;                    // (N, C) or null
+    T* u_ws;                 // (N, R)
+    T* dZ_ws;                // (N, C)
+    double* losspart;        // (NC * CL)
+    int CL, NC, NS, nchunk;
+    long long spc;
+    unsigned stage_x_bytes;  // stride of an X stage (>= rows_max * I_k * sizeof(T), multiple of 128)
+    unsigned stage_t_bytes;  // stride of a t stage (>= rows_max * RKS * sizeof(T), multiple of 16)
+    unsigned head_bytes;     // offset of X stage 0 in the dynamic shared memory
+    unsigned piece;          // bytes per bulk-copy instruction
+};
+
+template <typename T>
+struct FusedMnCtl {
+    uint64_t full[TRM_MAX_NS];
+    uint64_t empty[TRM_MAX_NS];
+    uint64_t redA[TRM_MAX_NS];
+    uint64_t rready[TRM_MAX_NS];
+    uint64_t cready[TRM_QO];
+    T pA[TRM_MAX_NS][TRM_NWF][TRM_RKMAX];
+    T vbuf[TRM_MAX_NS][TRM_RKMAX];               // written remotely (owner -> every CTA)
+    T cpart[TRM_QO][TRM_MAX_CL][TRM_RKMAX];      // written remotely (every CTA -> owner)
+    int dims[TR_MAX_MODES];
+    int foff[TR_MAX_MODES + 2];
+};
+
+namespace trf {
+__device__ __forceinline__ void st_async_val(uint32_t remote_addr, float v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void st_async_val(uint32_t remote_addr, double v, uint32_t remote_bar) {
+    st_async_f64(remote_addr, v, remote_bar);
+}
+// acc[r] += x * c[r], r < RKS: FFMA2 over channel pairs for float (same bits as scalar FMAs)
+template <typename T, int RKS>
+__device__ __forceinline__ void fma_row(T (&acc)[RKS], T x, const T (&c)[RKS]) {
+#pragma unroll
+    for (int r = 0; r < RKS; ++r) acc[r] = tr_fma<T>(x, c[r], acc[r]);
+}
+template <int RKS>
+__device__ __forceinline__ void fma_row(float (&acc)[RKS], float x, const float (&c)[RKS]) {
+#pragma unroll
+    for (int r = 0; r + 1 < RKS; r += 2) tr_ffma2(acc[r], acc[r + 1], x, x, c[r], c[r + 1]);
+    if (RKS & 1) acc[RKS - 1] = fmaf(x, c[RKS - 1], acc[RKS - 1]);
+}
+// RKS consecutive T values from shared memory (base 8-byte aligned; RKS even): 8-byte loads
+template <typename T, int RKS> struct SVec;
+template <int RKS> struct SVec<float, RKS> {
+    static __device__ __forceinline__ void ld(const float* p, float (&o)[RKS]) {
+#pragma unroll
+        for (int r = 0; r < RKS; r += 2) {
+            const float2 v = *reinterpret_cast<const float2*>(p + r);
+            o[r] = v.x; o[r + 1] = v.y;
+        }
+    }
+    static __device__ __forceinline__ void st(float* p, const float (&o)[RKS]) {
+#pragma unroll
+        for (int r = 0; r < RKS; r += 2) *reinterpret_cast<float2*>(p + r) = make_float2(o[r], o[r + 1]);
+    }
+};
+template <int RKS> struct SVec<double, RKS> {
+    static __device__ __forceinline__ void ld(const double* p, double (&o)[RKS]) {
+#pragma unroll
+        for (int r = 0; r < RKS; ++r) o[r] = p[r];
+    }
+    static __device__ __forceinline__ void st(double* p, const double (&o)[RKS]) {
+#pragma unroll
+        for (int r = 0; r < RKS; ++r) p[r] = o[r];
+    }
+};
+}  // namespace trf
+
+// One gradient group: chunks [Q0, Q0 + QN) of every row of this CTA (and the row sums S when WITH_S).
+template <typename T, int IKC, int RKS, int Q0, int QN, bool WITH_S>
+__device__ __forceinline__ void trm_gradient_role(const FusedMnArgs<T>& a, FusedMnCtl<T>* ctl, const T* sF12,
+                                                  const unsigned char* stageX0, const unsigned char* stageT0,
+                                                  int cnt, int cid, unsigned crank, int nrows, int row0) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int IK = IKC * VEC;
+    const int lane = threadIdx.x & 31;
+    const int tb = threadIdx.x & (TRM_NCT - 1);
+    const int gw = tb >> 5;
+    const int NS = a.NS;
+    T acc[QN * VEC][RKS];
+#pragma unroll
+    for (int e = 0; e < QN * VEC; ++e)
+#pragma unroll
+        for (int r = 0; r < RKS; ++r) acc[e][r] = (T)0;
+    T S[WITH_S ? TRM_GMAX : 1][RKS];
+#pragma unroll
+    for (int j = 0; j < (WITH_S ? TRM_GMAX : 1); ++j)
+#pragma unroll
+        for (int r = 0; r < RKS; ++r) S[j][r] = (T)0;
+
+    int s = 0;
+    unsigned ph = 0;
+    int left = (int)(a.spc < cnt ? a.spc : cnt);
+    int chunk_idx = 0;
+    for (int i = 0; i < cnt; ++i) {
+        trf::mbar_wait(&ctl->rready[s], ph);                       // v[n,:] of this sample arrived (all lanes wait)
+        if (WITH_S) trf::mbar_wait(&ctl->redA[s], ph);             // acquire the forward warps' t[row,:] stores
+        __syncwarp();
+        T v[RKS];
+        trf::SVec<T, RKS>::ld(&ctl->vbuf[s][0], v);
+        const T* xs = reinterpret_cast<const T*>(stageX0 + (size_t)s * a.stage_x_bytes);
+        const T* ts = reinterpret_cast<const T*>(stageT0 + (size_t)s * a.stage_t_bytes);
+#pragma unroll
+        for (int j = 0; j < TRM_GMAX; ++j) {
+            const int rl = tb + j * TRM_NCT;
+            if (rl < nrows) {
+                T c[RKS];
+                trf::SVec<T, RKS>::ld(sF12 + (size_t)rl * RKS, c);
+#pragma unroll
+                for (int r = 0; r < RKS; ++r) c[r] *= v[r];
+                if (WITH_S) {
+                    T tt[RKS];
+                    trf::SVec<T, RKS>::ld(ts + (size_t)rl * RKS, tt);
+#pragma unroll
+                    for (int r = 0; r < RKS; ++r) S[j][r] = tr_fma<T>(v[r], tt[r], S[j][r]);
+                }
+#pragma unroll
+                for (int qq = 0; qq < QN; ++qq) {
+                    T x[VEC];
+                    trf::SLoad<T, VEC>::ld(xs + (size_t)rl * IK + (Q0 + qq) * VEC, x);
+#pragma unroll
+                    for (int vv = 0; vv < VEC; ++vv) trf::fma_row(acc[qq * VEC + vv], x[vv], c);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) trf::mbar_arrive(&ctl->empty[s]);           // this warp's reads of the stage are done
+        if (++s == NS) { s = 0; ph ^= 1u; }
+        if (--left == 0) {
+            // chunk boundary: flush the running sums (bounds the length of every fp32 sum); lanes hold different rows
+            const size_t slot = (size_t)cid * a.nchunk + chunk_idx;
+            T* ap = a.Apart + ((slot * a.CL + crank) * TRM_NWG + gw) * (size_t)(IK * RKS);
+#pragma unroll
+            for (int e = 0; e < QN * VEC; ++e)
+#pragma unroll
+                for (int r = 0; r < RKS; ++r) {
+                    T sum = acc[e][r];
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(TR_FULL, sum, off);
+                    if (lane == 0) ap[(Q0 * VEC + e) * RKS + r] = sum;
+                    acc[e][r] = (T)0;
+                }
+            if (WITH_S) {
+                T* sp = a.Spart + slot * (size_t)RKS * a.NR;
+#pragma unroll
+                for (int j = 0; j < TRM_GMAX; ++j) {
+                    const int rl = tb + j * TRM_NCT;
+                    if (rl < nrows) {
+#pragma unroll
+                        for (int r = 0; r < RKS; ++r) {
+                            sp[(size_t)r * a.NR + row0 + rl] = S[j][r];
+                            S[j][r] = (T)0;
+                        }
+                    }
+                }
+            }
+            ++chunk_idx;
+            const int rem = cnt - (i + 1);
+            left = (int)(a.spc < rem ? a.spc : rem);
+        }
+    }
+}
+
+template <typename T, int IKC, int RKS, int QA>
+__global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int IK = IKC * VEC;
+    static_assert(RKS % 2 == 0 && RKS <= TRM_RKMAX, "channel count must be even and <= 8");
+    static_assert(QA >= 1 && QA < IKC, "chunk split: both gradient groups need at least one chunk of a row");
+    extern __shared__ __align__(128) unsigned char trm_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned crank = trf::cluster_ctarank();
+    const int cid = blockIdx.x / a.CL;
+    const int NS = a.NS, CL = a.CL;
+    const int k = a.geo.k, R = a.geo.R, C = a.geo.C;
+
+    // layout: [control | F3 (I_k, RKS) | F12 (GMAX*128, RKS) | class factor + rank weights (double) | pad | X stages | t stages]
+    FusedMnCtl<T>* ctl = reinterpret_cast<FusedMnCtl<T>*>(trm_smem);
+    size_t off = (sizeof(FusedMnCtl<T>) + 15) / 16 * 16;
+    T* sF3 = reinterpret_cast<T*>(trm_smem + off);
+    off += (size_t)IK * RKS * sizeof(T);
+    T* sF12 = reinterpret_cast<T*>(trm_smem + off);
+    off += (size_t)TRM_GMAX * TRM_NCT * RKS * sizeof(T);
+    off = (off + 15) / 16 * 16;
+    double* sFC = reinterpret_cast<double*>(trm_smem + off);
+    double* sW = sFC + C * R;
+    const unsigned char* stageX0 = trm_smem + a.head_bytes;
+    const unsigned char* stageT0 = stageX0 + (size_t)NS * a.stage_x_bytes;
+
+    // rows of this CTA: the first (NR mod CL) ranks hold one more
+    const int rq = a.NR / CL, rrem = a.NR % CL;
+    const int nrows = rq + ((int)crank < rrem ? 1 : 0);
+    const int row0 = (int)crank * rq + ((int)crank < rrem ? (int)crank : rrem);
+
+    if (threadIdx.x < TR_MAX_MODES) ctl->dims[threadIdx.x] = a.geo.dims[threadIdx.x];
+    if (threadIdx.x < TR_MAX_MODES + 2) ctl->foff[threadIdx.x] = a.geo.foff[threadIdx.x];
+    for (int idx = threadIdx.x; idx < IK * RKS; idx += TRM_NT) {
+        const int i3 = idx / RKS, r = idx % RKS;
+        sF3[idx] = r < R ? a.FtT[a.geo.foff[k - 1] + i3 * R + r] : (T)0;
+    }
+    for (int idx = threadIdx.x; idx < TRM_GMAX * TRM_NCT * RKS; idx += TRM_NT) {
+        const int rl = idx / RKS, r = idx % RKS;
+        T p = (T)0;
+        if (rl < nrows && r < R) {
+            p = (T)1;
+            unsigned rem = (unsigned)(row0 + rl);
+            for (int m = k - 2; m >= 0; --m) {
+                const unsigned d = (unsigned)a.geo.dims[m];
+                const unsigned q = rem / d;
+                p *= a.FtT[a.geo.foff[m] + (int)(rem - q * d) * R + r];
+                rem = q;
+            }
+        }
+        sF12[idx] = p;
+    }
+    for (int idx = threadIdx.x; idx < C * R + R; idx += TRM_NT)
+        sFC[idx] = idx < C * R ? a.Ft64[a.geo.pfeat + idx] : (double)a.w[idx - C * R];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) {
+            trf::mbar_init(&ctl->full[s], 1);
+            trf::mbar_init(&ctl->empty[s], 2 * TRM_NWG);
+            trf::mbar_init(&ctl->redA[s], TRM_NWF);
+            trf::mbar_init(&ctl->rready[s], 1);
+        }
+        for (int q = 0; q < TRM_QO; ++q) trf::mbar_init(&ctl->cready[q], 1);
+        trf::fence_mbar_init();
+    }
+    __syncthreads();
+    trf::cluster_arrive();
+    trf::cluster_wait();
+
+    // samples of this cluster: n = cid + i*NC, i = 0..cnt-1; sample i is OWNED by CTA (i mod CL)
+    const int cnt = cid < a.N ? (int)((a.N - cid + a.NC - 1) / a.NC) : 0;
+    const size_t sample_stride = (size_t)a.NC * (size_t)a.geo.D;
+
+    if (warp < TRM_NWF) {
+        // ===================================== forward =====================================
+        const int tid = threadIdx.x;                              // 0..127
+        T f12[TRM_GMAX][RKS];
+#pragma unroll
+        for (int j = 0; j < TRM_GMAX; ++j) trf::SVec<T, RKS>::ld(sF12 + (size_t)(tid + j * TRM_NCT) * RKS, f12[j]);   // zeros past nrows
+        int s = 0;
+        unsigned ph = 0;
+        for (int i = 0; i < cnt; ++i) {
+            trf::mbar_wait(&ctl->full[s], ph);                     // every lane waits on the barrier itself (tr_fused.cuh)
+            __syncwarp();
+            const T* xs = reinterpret_cast<const T*>(stageX0 + (size_t)s * a.stage_x_bytes);
+            T* ts = reinterpret_cast<T*>(const_cast<unsigned char*>(stageT0) + (size_t)s * a.stage_t_bytes);
+            T t[TRM_GMAX][RKS];
+#pragma unroll
+            for (int j = 0; j < TRM_GMAX; ++j)
+#pragma unroll
+                for (int r = 0; r < RKS; ++r) t[j][r] = (T)0;
+#pragma unroll
+            for (int q = 0; q < IKC; ++q) {
+                T f3[VEC][RKS];                                    // F3 rows of this chunk: broadcast loads
+#pragma unroll
+                for (int vv = 0; vv < VEC; ++vv) trf::SVec<T, RKS>::ld(sF3 + (size_t)(q * VEC + vv) * RKS, f3[vv]);
+#pragma unroll
+                for (int j = 0; j < TRM_GMAX; ++j) {
+                    const int rl = tid + j * TRM_NCT;
+                    if (rl < nrows) {
+                        T x[VEC];
+                        trf::SLoad<T, VEC>::ld(xs + (size_t)rl * IK + q * VEC, x);
+#pragma unroll
+                        for (int vv = 0; vv < VEC; ++vv) trf::fma_row(t[j], x[vv], f3[vv]);
+                    }
+                }
+            }
+            T vals[TRM_RKMAX];
+#pragma unroll
+            for (int r = 0; r < TRM_RKMAX; ++r) vals[r] = (T)0;
+#pragma unroll
+            for (int j = 0; j < TRM_GMAX; ++j) {
+                const int rl = tid + j * TRM_NCT;
+                if (rl < nrows) {
+                    trf::SVec<T, RKS>::st(ts + (size_t)rl * RKS, t[j]);
+#pragma unroll
+                    for (int r = 0; r < RKS; ++r) vals[r] = tr_fma<T>(t[j][r], f12[j][r], vals[r]);
+                }
+            }
+            warp_reduce_transpose<T, TRM_RKMAX, 0>(vals, lane);   // lane l: total of channel l >> 2
+            if ((lane & 3) == 0) ctl->pA[s][warp][lane >> 2] = vals[0];
+            __syncwarp();
+            if (lane == 0) trf::mbar_arrive(&ctl->redA[s]);
+            if (++s == NS) { s = 0; ph ^= 1u; }
+        }
+    } else if (warp < TRM_NWF + TRM_NWG) {
+        trm_gradient_role<T, IKC, RKS, 0, QA, false>(a, ctl, sF12, stageX0, stageT0, cnt, cid, crank, nrows, row0);
+    } else if (warp < TRM_NWF + 2 * TRM_NWG) {
+        trm_gradient_role<T, IKC, RKS, QA, IKC - QA, true>(a, ctl, sF12, stageX0, stageT0, cnt, cid, crank, nrows, row0);
+    } else if (warp == TRM_NWF + 2 * TRM_NWG) {
+        // ================================== TMA producer ==================================
+        if (lane == 0) {
+            const unsigned my_bytes = (unsigned)nrows * (unsigned)IK * (unsigned)sizeof(T);
+            const T* src = a.X + (size_t)cid * (size_t)a.geo.D + (size_t)row0 * IK;
+            int s = 0;
+            unsigned ph = 0;
+            for (int j = 0; j < cnt; ++j) {
+                if (j >= NS) trf::mbar_wait(&ctl->empty[s], ph);
+                trf::mbar_arrive_expect_tx(&ctl->full[s], my_bytes);
+                const unsigned char* sp = reinterpret_cast<const unsigned char*>(src);
+                unsigned char* dst = const_cast<unsigned char*>(stageX0) + (size_t)s * a.stage_x_bytes;
+                for (unsigned o2 = 0; o2 < my_bytes; o2 += a.piece) {
+                    const unsigned len = my_bytes - o2 < a.piece ? my_bytes - o2 : a.piece;
+                    trf::bulk_g2s(dst + o2, sp + o2, len, &ctl->full[s]);
+                }
+                src += sample_stride;
+                if (++s == NS) { s = 0; if (j >= NS) ph ^= 1u; }
+            }
+        }
+    } else if (warp == TRM_NWF + 2 * TRM_NWG + 1) {
+        // ===================== reducer: CTA partial of u[n,:] -> owner CTA =====================
+        int s = 0, owner = 0, slot = 0;
+        unsigned ph = 0;
+        for (int i = 0; i < cnt; ++i) {
+            trf::mbar_wait(&ctl->redA[s], ph);
+            __syncwarp();
+            // the previous use of rready[s] (sample i - NS) has completed: its gradient phase released the stage
+            // before this sample could be loaded.  Arm it for v[n,:] of this sample.
+            if (lane == 0) trf::mbar_arrive_expect_tx(&ctl->rready[s], (unsigned)(RKS * sizeof(T)));
+            if (lane < RKS) {
+                T pc = (T)0;
+#pragma unroll
+                for (int w4 = 0; w4 < TRM_NWF; ++w4) pc += ctl->pA[s][w4][lane];          // fixed order
+                trf::st_async_val(trf::mapa(trf::smem_u32(&ctl->cpart[slot][crank][lane]), (unsigned)owner), pc,
+                                  trf::mapa(trf::smem_u32(&ctl->cready[slot]), (unsigned)owner));
+            }
+            __syncwarp();
+            if (++s == NS) { s = 0; ph ^= 1u; }
+            if (++owner == CL) { owner = 0; if (++slot == TRM_QO) slot = 0; }
+        }
+    } else if (warp == TRM_NWF + 2 * TRM_NWG + 2) {
+        // ============== epilogue of the samples this CTA owns; v[n,:] -> every CTA ==============
+        EpiMnArgs<T> ea;
+        ea.partial = nullptr; ea.WT = 0; ea.RKs = RKS; ea.N = a.N; ea.R = R; ea.C = C;
+        ea.FC = nullptr; ea.w = a.w; ea.y = a.y; ea.dP_in = nullptr; ea.class_w = a.class_w;
+        ea.P = a.P; ea.pred = nullptr; ea.V = nullptr; ea.u_ws = a.u_ws; ea.dZ_ws = a.dZ_ws; ea.part = nullptr;
+        double loss = 0.0;
+        int slot = 0;
+        unsigned phc = 0;
+        int s = (int)crank % NS;
+        const int sstep = CL % NS;
+        for (int i = (int)crank; i < cnt; i += CL) {
+            const long long n = (long long)cid + (long long)i * a.NC;
+            // label and class weight: in flight while the partials arrive
+            const int yn = (int)__ldg(a.y + n);
+            const double omega = a.class_w ? (double)__ldg(a.class_w + yn) : 1.0;
+            if (lane == 0) trf::mbar_arrive_expect_tx(&ctl->cready[slot], (unsigned)(CL * RKS * sizeof(T)));
+            trf::mbar_wait(&ctl->cready[slot], phc);
+            __syncwarp();
+            double u[RKS];
+#pragma unroll
+            for (int r = 0; r < RKS; ++r) {
+                double sum = 0.0;
+                for (int c = 0; c < CL; ++c) sum += (double)ctl->cpart[slot][c][r];      // fixed order: same bits on every launch
+                u[r] = sum;
+            }
+            double vv[RKS];
+#pragma unroll
+            for (int r = 0; r < RKS; ++r) vv[r] = 0.0;
+            epi_mn_core<T, RKS, 1>(ea, n, u, lane, sFC, sW, yn, omega, loss, vv);
+            if (lane < CL) {
+#pragma unroll
+                for (int r = 0; r < RKS; ++r)
+                    trf::st_async_val(trf::mapa(trf::smem_u32(&ctl->vbuf[s][r]), (unsigned)lane), (T)vv[r],
+                                      trf::mapa(trf::smem_u32(&ctl->rready[s]), (unsigned)lane));
+            }
+            __syncwarp();
+            if (++slot == TRM_QO) { slot = 0; phc ^= 1u; }
+            s += sstep;
+            if (s >= NS) s -= NS;
+        }
+        loss = warp_sum(loss);
+        if (lane == 0) a.losspart[(size_t)cid * CL + crank] = loss;
+    }
+    // no CTA may exit while a peer can still write into its shared memory
+    __syncwarp();
+    trf::cluster_arrive();
+    trf::cluster_wait();
+}
+
+// dFt_k[i_k, r] = sum over (slot, CTA, warp) of the flushed A partials, in double; one block per (i_k, r)
+template <typename T>
+__global__ void __launch_bounds__(128) k_reduce_A(const T* __restrict__ Apart, int nparts, int IK, int RKS, int R,
+                                                  double* __restrict__ out /* gradsum + foff[k-1] */) {
+    __shared__ double sbuf[32];
+    const int i3 = blockIdx.x / R, r = blockIdx.x % R;
+    double s = 0.0;
+    for (int p = threadIdx.x; p < nparts; p += blockDim.x) s += (double)Apart[(size_t)p * IK * RKS + i3 * RKS + r];
+    s = block_sum(s, sbuf);
+    if (threadIdx.x == 0) out[i3 * R + r] = s;
+}
