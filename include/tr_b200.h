@@ -154,7 +154,7 @@ int tr_comm_destroy(void* comm);
  * pinned-memory DMA rate even when src_host is PAGEABLE: a ring of pinned staging buffers is filled by `threads`
  * host threads (0 = min(hardware threads, 16); env TR_B200_UPLOAD_THREADS) in parallel slices while the previous
  * buffer is in flight; memory that is already pinned / registered is copied from in place.  chunk_bytes = size
- * of one staging buffer (0 = 64 MiB).  Work queued on `stream` before the call is waited for, work queued after
+ * of one staging buffer (0 = 32 MiB).  Work queued on `stream` before the call is waited for, work queued after
  * it sees the data; the call returns when src_host may be reused.  Errors: tr_host_last_error().
  * tr_upload_stats: out4 = { seconds of the last upload, of which host fill seconds, threads used, 1 if staged }. */
 int tr_upload(void* dst_device, const void* src_host, size_t bytes, int device, int threads, size_t chunk_bytes,
