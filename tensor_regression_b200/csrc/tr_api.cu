@@ -105,6 +105,7 @@ struct tr_handle {
     long long flow_window_mb = 32;      // bytes of X the forward warps may lead the gradient warps by (option "flow_window_mb")
     Buf flow_ring, flow_sync;
     Buf Apart, Spart;                   // single-pass multinomial kernel: flushed A / S partial sums
+    Buf trace;                          // debug timeline of k_fused_mn (builds with -DTRM_TRACE only)
     int flow_debug = 0;
 };
 
@@ -515,9 +516,13 @@ int plan_fused_mn(tr_handle* h, long long N, const void* X, FusedMnPlan* fp) {
     head += (size_t)IK * RKS * sizeof(T);
     head += (size_t)TRM_GMAX * TRM_NCT * RKS * sizeof(T);
     head = (head + 15) / 16 * 16;
-    head += (size_t)(g.C * g.R + g.R) * sizeof(double);
+    head += (size_t)g.C * RKS * sizeof(T);
     head = (head + 127) / 128 * 128;
+    #ifdef TRM_TRACE
+    const size_t budget = 218 * 1024;       // room for the timeline stamps
+#else
     const size_t budget = 226 * 1024;
+#endif
     int bestCL = 0, bestNS = 0;
     unsigned best_sx = 0, best_st = 0;
     for (int CL = 1; CL <= TRM_MAX_CL; CL *= 2) {
@@ -609,11 +614,17 @@ int run_fused_mn(tr_handle* h, const T* X, const long long* y, const T* class_w,
     fa.CL = fp.CL; fa.NC = fp.NC; fa.NS = fp.NS; fa.nchunk = fp.nchunk; fa.spc = fp.spc;
     fa.stage_x_bytes = fp.stage_x; fa.stage_t_bytes = fp.stage_t; fa.head_bytes = fp.head;
     fa.piece = (unsigned)h->fused_piece;
-    if ((rc = raise_smem_limit(h, fp.kern, fp.smem))) return rc;
+    size_t smem_launch = fp.smem;
+#ifdef TRM_TRACE
+    if ((rc = ensure(h, h->trace, (size_t)TRM_TRACE_N * TRM_TRACE_EV * sizeof(long long)))) return rc;
+    fa.trace = (long long*)h->trace.p;
+    smem_launch += (size_t)TRM_TRACE_N * TRM_TRACE_EV * sizeof(long long);
+#endif
+    if ((rc = raise_smem_limit(h, fp.kern, smem_launch))) return rc;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(fp.CL * fp.NC), 1, 1);
     cfg.blockDim = dim3(TRM_NT, 1, 1);
-    cfg.dynamicSmemBytes = fp.smem;
+    cfg.dynamicSmemBytes = smem_launch;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1042,7 +1053,7 @@ int tr_destroy(tr_handle* h) {
     DeviceGuard dg(h->device);
     cudaDeviceSynchronize();
     Buf* bufs[] = {&h->FtT, &h->Ft64, &h->partial, &h->V, &h->u_ws, &h->dZ_ws, &h->Gpart, &h->Gred, &h->epi_part, &h->dfc_part,
-                   &h->flow_ring, &h->flow_sync, &h->Apart, &h->Spart};
+                   &h->flow_ring, &h->flow_sync, &h->Apart, &h->Spart, &h->trace};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
@@ -1427,6 +1438,17 @@ int tr_lbfgs_gtd(tr_handle* h, const void* g, const void* d, double* scal2, void
     TR_LAUNCH_CHECK(h);
     return TR_OK;
 }
+
+#ifdef TRM_TRACE
+// debug builds only (not part of include/tr_b200.h): the timeline of the last k_fused_mn launch, TRM_TRACE_N x TRM_TRACE_EV stamps
+int tr_debug_trace(tr_handle* h, long long* out, int n) {
+    if (!h || !out || !h->trace.p) return TR_ERR_INVALID;
+    DeviceGuard dg(h->device);
+    TR_CUDA(h, cudaDeviceSynchronize());
+    TR_CUDA(h, cudaMemcpy(out, h->trace.p, (size_t)std::min(n, TRM_TRACE_N * TRM_TRACE_EV) * sizeof(long long), cudaMemcpyDeviceToHost));
+    return TR_OK;
+}
+#endif
 
 int tr_last_launch_info(tr_handle* h, int64_t* info8) {
     if (!h || !info8) return TR_ERR_INVALID;

@@ -63,6 +63,7 @@ struct FusedMnArgs {
     unsigned stage_t_bytes;  // stride of a t stage (>= rows_max * RKS * sizeof(T), multiple of 16)
     unsigned head_bytes;     // offset of X stage 0 in the dynamic shared memory
     unsigned piece;          // bytes per bulk-copy instruction
+    long long* trace;        // debug timeline (build with -DTRM_TRACE, tools/fused_mn_trace.py), else null
 };
 
 template <typename T>
@@ -78,6 +79,23 @@ struct FusedMnCtl {
     int dims[TR_MAX_MODES];
     int foff[TR_MAX_MODES + 2];
 };
+
+// debug timeline: clock64 stamps of cluster 0 / CTA rank TRM_TRACE_RANK for TRM_TRACE_N samples from TRM_TRACE_I0, kept in
+// shared memory during the run (a global store before an mbarrier.arrive would distort the timeline)
+#ifndef TRM_TRACE_I0
+#define TRM_TRACE_I0 320
+#endif
+#define TRM_TRACE_N 48
+#define TRM_TRACE_EV 16
+#ifdef TRM_TRACE
+#define TRM_STAMP(ev, i)                                                                                   \
+    do {                                                                                                   \
+        if (a.trace && cid == 0 && crank == 0 && (i) >= TRM_TRACE_I0 && (i) < TRM_TRACE_I0 + TRM_TRACE_N)  \
+            strace[((i) - TRM_TRACE_I0) * TRM_TRACE_EV + (ev)] = clock64();                                \
+    } while (0)
+#else
+#define TRM_STAMP(ev, i) do { } while (0)
+#endif
 
 namespace trf {
 __device__ __forceinline__ void st_async_val(uint32_t remote_addr, float v, uint32_t remote_bar) {
@@ -126,11 +144,70 @@ template <int RKS> struct SVec<double, RKS> {
 };
 }  // namespace trf
 
+template <typename T> __device__ __forceinline__ T trm_exp(T x);
+template <> __device__ __forceinline__ float trm_exp<float>(float x) { return expf(x); }
+template <> __device__ __forceinline__ double trm_exp<double>(double x) { return exp(x); }
+template <typename T> __device__ __forceinline__ T trm_log(T x);
+template <> __device__ __forceinline__ float trm_log<float>(float x) { return logf(x); }
+template <> __device__ __forceinline__ double trm_log<double>(double x) { return log(x); }
+
+// Per-sample epilogue of the single-pass kernel, one warp, lane = class (C <= 32), arithmetic in the model dtype T
+// like the reference's own (mn:180-187 softmax, mn:364-366 / 448-450 CrossEntropyLoss on the probabilities = second
+// softmax, autograd down to v[n,:]).  It sits on the critical path of the cluster pipeline (the sample stays in shared
+// memory until v is known), so it is written for latency: reductions over the next power of two >= C lanes only, no
+// max-subtraction in the second softmax (its arguments are probabilities in [0,1]; exp(P)/sum exp(P) is the same
+// quotient), one table sFCw[c][r] = w_r * FC[c,r] for both the logits and v.  The fp64 epilogue of the two-pass path
+// (epi_mn_core) agrees with it to a few ulp of T; both are checked against the oracle at the north-star tolerance.
+template <typename T, int RKS>
+__device__ __forceinline__ void trm_epilogue(const EpiMnArgs<T>& a, long long n, const T (&u)[RKS], int lane, const T* sFCw,
+                                             int red_hi, int yn, T omega, double& loss, T (&vout)[RKS]) {
+    const int C = a.C, R = a.R;
+    const bool act = lane < C;
+    T fc[RKS];
+    trf::SVec<T, RKS>::ld(sFCw + (size_t)(act ? lane : 0) * RKS, fc);
+    T z = (T)0;
+#pragma unroll
+    for (int r = 0; r < RKS; ++r) z = tr_fma<T>(u[r], fc[r], z);
+    T zmax = act ? z : -INFINITY;
+    for (int off = red_hi; off >= 1; off >>= 1) zmax = fmax(zmax, __shfl_xor_sync(TR_FULL, zmax, off));
+    const T e = act ? trm_exp<T>(z - zmax) : (T)0;
+    T zs = e;
+    for (int off = red_hi; off >= 1; off >>= 1) zs += __shfl_xor_sync(TR_FULL, zs, off);
+    const T P = e / zs;
+    if (act && a.P) a.P[n * C + lane] = P;
+    const T qe = act ? trm_exp<T>(P) : (T)0;
+    T qs = qe;
+    for (int off = red_hi; off >= 1; off >>= 1) qs += __shfl_xor_sync(TR_FULL, qs, off);
+    const T q = qe / qs;
+    if (act && lane == yn) loss += (double)(-omega * (P - trm_log<T>(qs)));          // -omega log Q[n,y_n]
+    const T dP = act ? omega * (q - (lane == yn ? (T)1 : (T)0)) : (T)0;
+    T dot = dP * P;
+    for (int off = red_hi; off >= 1; off >>= 1) dot += __shfl_xor_sync(TR_FULL, dot, off);
+    const T dZ = act ? P * (dP - dot) : (T)0;
+    if (act && a.dZ_ws) a.dZ_ws[n * C + lane] = dZ;
+    // v[r] = w_r sum_c dZ[c] FC[c,r]: RKS independent reductions, every lane ends with all of them
+#pragma unroll
+    for (int r = 0; r < RKS; ++r) vout[r] = dZ * fc[r];
+    for (int off = red_hi; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int r = 0; r < RKS; ++r) vout[r] += __shfl_xor_sync(TR_FULL, vout[r], off);
+    }
+    // lanes outside the reduction group of lane 0 (C small) hold sums of inactive lanes: every lane takes lane 0's
+#pragma unroll
+    for (int r = 0; r < RKS; ++r) vout[r] = __shfl_sync(TR_FULL, vout[r], 0);
+    if (lane < R && a.u_ws) {
+        T ur = (T)0;
+#pragma unroll
+        for (int r = 0; r < RKS; ++r) if (r == lane) ur = u[r];
+        a.u_ws[n * R + lane] = ur;
+    }
+}
+
 // One gradient group: chunks [Q0, Q0 + QN) of every row of this CTA (and the row sums S when WITH_S).
 template <typename T, int IKC, int RKS, int Q0, int QN, bool WITH_S>
 __device__ __forceinline__ void trm_gradient_role(const FusedMnArgs<T>& a, FusedMnCtl<T>* ctl, const T* sF12,
                                                   const unsigned char* stageX0, const unsigned char* stageT0,
-                                                  int cnt, int cid, unsigned crank, int nrows, int row0) {
+                                                  int cnt, int cid, unsigned crank, int nrows, int row0, long long* strace) {
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int IK = IKC * VEC;
     const int lane = threadIdx.x & 31;
@@ -156,6 +233,7 @@ __device__ __forceinline__ void trm_gradient_role(const FusedMnArgs<T>& a, Fused
         trf::mbar_wait(&ctl->rready[s], ph);                       // v[n,:] of this sample arrived (all lanes wait)
         if (WITH_S) trf::mbar_wait(&ctl->redA[s], ph);             // acquire the forward warps' t[row,:] stores
         __syncwarp();
+        if (tb == 0) TRM_STAMP(WITH_S ? 10 : 8, i);
         T v[RKS];
         trf::SVec<T, RKS>::ld(&ctl->vbuf[s][0], v);
         const T* xs = reinterpret_cast<const T*>(stageX0 + (size_t)s * a.stage_x_bytes);
@@ -184,6 +262,7 @@ __device__ __forceinline__ void trm_gradient_role(const FusedMnArgs<T>& a, Fused
             }
         }
         __syncwarp();
+        if (tb == 0) TRM_STAMP(WITH_S ? 11 : 9, i);
         if (lane == 0) trf::mbar_arrive(&ctl->empty[s]);           // this warp's reads of the stage are done
         if (++s == NS) { s = 0; ph ^= 1u; }
         if (--left == 0) {
@@ -235,7 +314,7 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
     const int NS = a.NS, CL = a.CL;
     const int k = a.geo.k, R = a.geo.R, C = a.geo.C;
 
-    // layout: [control | F3 (I_k, RKS) | F12 (GMAX*128, RKS) | class factor + rank weights (double) | pad | X stages | t stages]
+    // layout: [control | F3 (I_k, RKS) | F12 (GMAX*128, RKS) | w * class factor (C, RKS) | pad | X stages | t stages]
     FusedMnCtl<T>* ctl = reinterpret_cast<FusedMnCtl<T>*>(trm_smem);
     size_t off = (sizeof(FusedMnCtl<T>) + 15) / 16 * 16;
     T* sF3 = reinterpret_cast<T*>(trm_smem + off);
@@ -243,10 +322,15 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
     T* sF12 = reinterpret_cast<T*>(trm_smem + off);
     off += (size_t)TRM_GMAX * TRM_NCT * RKS * sizeof(T);
     off = (off + 15) / 16 * 16;
-    double* sFC = reinterpret_cast<double*>(trm_smem + off);
-    double* sW = sFC + C * R;
+    T* sFCw = reinterpret_cast<T*>(trm_smem + off);                 // (C, RKS): w_r * FC[c,r], zero-padded channels
     const unsigned char* stageX0 = trm_smem + a.head_bytes;
     const unsigned char* stageT0 = stageX0 + (size_t)NS * a.stage_x_bytes;
+#ifdef TRM_TRACE
+    long long* strace = reinterpret_cast<long long*>(const_cast<unsigned char*>(stageT0) + (size_t)NS * a.stage_t_bytes);
+    for (int i = threadIdx.x; i < TRM_TRACE_N * TRM_TRACE_EV; i += TRM_NT) strace[i] = 0;
+#else
+    long long* strace = nullptr;
+#endif
 
     // rows of this CTA: the first (NR mod CL) ranks hold one more
     const int rq = a.NR / CL, rrem = a.NR % CL;
@@ -274,8 +358,10 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
         }
         sF12[idx] = p;
     }
-    for (int idx = threadIdx.x; idx < C * R + R; idx += TRM_NT)
-        sFC[idx] = idx < C * R ? a.Ft64[a.geo.pfeat + idx] : (double)a.w[idx - C * R];
+    for (int idx = threadIdx.x; idx < C * RKS; idx += TRM_NT) {
+        const int c = idx / RKS, r = idx % RKS;
+        sFCw[idx] = r < R ? (T)((double)a.w[r] * a.Ft64[a.geo.pfeat + c * R + r]) : (T)0;
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) {
             trf::mbar_init(&ctl->full[s], 1);
@@ -305,6 +391,7 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
         for (int i = 0; i < cnt; ++i) {
             trf::mbar_wait(&ctl->full[s], ph);                     // every lane waits on the barrier itself (tr_fused.cuh)
             __syncwarp();
+            if (tid == 0) TRM_STAMP(1, i);
             const T* xs = reinterpret_cast<const T*>(stageX0 + (size_t)s * a.stage_x_bytes);
             T* ts = reinterpret_cast<T*>(const_cast<unsigned char*>(stageT0) + (size_t)s * a.stage_t_bytes);
             T t[TRM_GMAX][RKS];
@@ -343,13 +430,14 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
             warp_reduce_transpose<T, TRM_RKMAX, 0>(vals, lane);   // lane l: total of channel l >> 2
             if ((lane & 3) == 0) ctl->pA[s][warp][lane >> 2] = vals[0];
             __syncwarp();
+            if (tid == 0) TRM_STAMP(2, i);
             if (lane == 0) trf::mbar_arrive(&ctl->redA[s]);
             if (++s == NS) { s = 0; ph ^= 1u; }
         }
     } else if (warp < TRM_NWF + TRM_NWG) {
-        trm_gradient_role<T, IKC, RKS, 0, QA, false>(a, ctl, sF12, stageX0, stageT0, cnt, cid, crank, nrows, row0);
+        trm_gradient_role<T, IKC, RKS, 0, QA, false>(a, ctl, sF12, stageX0, stageT0, cnt, cid, crank, nrows, row0, strace);
     } else if (warp < TRM_NWF + 2 * TRM_NWG) {
-        trm_gradient_role<T, IKC, RKS, QA, IKC - QA, true>(a, ctl, sF12, stageX0, stageT0, cnt, cid, crank, nrows, row0);
+        trm_gradient_role<T, IKC, RKS, QA, IKC - QA, true>(a, ctl, sF12, stageX0, stageT0, cnt, cid, crank, nrows, row0, strace);
     } else if (warp == TRM_NWF + 2 * TRM_NWG) {
         // ================================== TMA producer ==================================
         if (lane == 0) {
@@ -359,6 +447,7 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
             unsigned ph = 0;
             for (int j = 0; j < cnt; ++j) {
                 if (j >= NS) trf::mbar_wait(&ctl->empty[s], ph);
+                TRM_STAMP(0, j);
                 trf::mbar_arrive_expect_tx(&ctl->full[s], my_bytes);
                 const unsigned char* sp = reinterpret_cast<const unsigned char*>(src);
                 unsigned char* dst = const_cast<unsigned char*>(stageX0) + (size_t)s * a.stage_x_bytes;
@@ -377,6 +466,7 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
         for (int i = 0; i < cnt; ++i) {
             trf::mbar_wait(&ctl->redA[s], ph);
             __syncwarp();
+            if (lane == 0) TRM_STAMP(3, i);
             // the previous use of rready[s] (sample i - NS) has completed: its gradient phase released the stage
             // before this sample could be loaded.  Arm it for v[n,:] of this sample.
             if (lane == 0) trf::mbar_arrive_expect_tx(&ctl->rready[s], (unsigned)(RKS * sizeof(T)));
@@ -398,6 +488,9 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
         ea.FC = nullptr; ea.w = a.w; ea.y = a.y; ea.dP_in = nullptr; ea.class_w = a.class_w;
         ea.P = a.P; ea.pred = nullptr; ea.V = nullptr; ea.u_ws = a.u_ws; ea.dZ_ws = a.dZ_ws; ea.part = nullptr;
         double loss = 0.0;
+        int red_hi = 1;                                             // reductions run over the next power of two >= C lanes
+        while (red_hi * 2 < C) red_hi *= 2;
+        if (C <= 1) red_hi = 0;
         int slot = 0;
         unsigned phc = 0;
         int s = (int)crank % NS;
@@ -406,25 +499,39 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
             const long long n = (long long)cid + (long long)i * a.NC;
             // label and class weight: in flight while the partials arrive
             const int yn = (int)__ldg(a.y + n);
-            const double omega = a.class_w ? (double)__ldg(a.class_w + yn) : 1.0;
+            const T omega = a.class_w ? __ldg(a.class_w + yn) : (T)1;
             if (lane == 0) trf::mbar_arrive_expect_tx(&ctl->cready[slot], (unsigned)(CL * RKS * sizeof(T)));
+            if (lane == 0) TRM_STAMP(4, i);
             trf::mbar_wait(&ctl->cready[slot], phc);
             __syncwarp();
-            double u[RKS];
+            if (lane == 0) TRM_STAMP(5, i);
+            // u[n,:] = sum of the CL CTA partials: four interleaved running sums combined in a fixed order
+            T u4[4][RKS];
 #pragma unroll
-            for (int r = 0; r < RKS; ++r) {
-                double sum = 0.0;
-                for (int c = 0; c < CL; ++c) sum += (double)ctl->cpart[slot][c][r];      // fixed order: same bits on every launch
-                u[r] = sum;
+            for (int q4 = 0; q4 < 4; ++q4)
+#pragma unroll
+                for (int r = 0; r < RKS; ++r) u4[q4][r] = (T)0;
+            for (int c0 = 0; c0 < CL; c0 += 4) {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    if (c0 + q4 < CL) {
+                        T pc[RKS];
+                        trf::SVec<T, RKS>::ld(&ctl->cpart[slot][c0 + q4][0], pc);
+#pragma unroll
+                        for (int r = 0; r < RKS; ++r) u4[q4][r] += pc[r];
+                    }
+                }
             }
-            double vv[RKS];
+            T u[RKS], vv[RKS];
 #pragma unroll
-            for (int r = 0; r < RKS; ++r) vv[r] = 0.0;
-            epi_mn_core<T, RKS, 1>(ea, n, u, lane, sFC, sW, yn, omega, loss, vv);
+            for (int r = 0; r < RKS; ++r) u[r] = (u4[0][r] + u4[1][r]) + (u4[2][r] + u4[3][r]);
+            if (lane == 0) TRM_STAMP(6, i);
+            trm_epilogue<T, RKS>(ea, n, u, lane, sFCw, red_hi, yn, omega, loss, vv);
+            if (lane == 0) TRM_STAMP(7, i);
             if (lane < CL) {
 #pragma unroll
                 for (int r = 0; r < RKS; ++r)
-                    trf::st_async_val(trf::mapa(trf::smem_u32(&ctl->vbuf[s][r]), (unsigned)lane), (T)vv[r],
+                    trf::st_async_val(trf::mapa(trf::smem_u32(&ctl->vbuf[s][r]), (unsigned)lane), vv[r],
                                       trf::mapa(trf::smem_u32(&ctl->rready[s]), (unsigned)lane));
             }
             __syncwarp();
@@ -439,6 +546,11 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
     __syncwarp();
     trf::cluster_arrive();
     trf::cluster_wait();
+#ifdef TRM_TRACE
+    __syncthreads();
+    if (a.trace && cid == 0 && crank == 0)
+        for (int i = threadIdx.x; i < TRM_TRACE_N * TRM_TRACE_EV; i += TRM_NT) a.trace[i] = strace[i];
+#endif
 }
 
 // dFt_k[i_k, r] = sum over (slot, CTA, warp) of the flushed A partials, in double; one block per (i_k, r)
