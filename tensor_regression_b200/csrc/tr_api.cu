@@ -516,7 +516,7 @@ int plan_fused_mn(tr_handle* h, long long N, const void* X, FusedMnPlan* fp) {
     head += (size_t)IK * RKS * sizeof(T);
     head += (size_t)TRM_GMAX * TRM_NCT * RKS * sizeof(T);
     head = (head + 15) / 16 * 16;
-    head += (size_t)g.C * RKS * sizeof(T);
+    head += (size_t)g.C * (RKS + 1) * sizeof(T);
     head = (head + 127) / 128 * 128;
     #ifdef TRM_TRACE
     const size_t budget = 218 * 1024;       // room for the timeline stamps
@@ -528,7 +528,7 @@ int plan_fused_mn(tr_handle* h, long long N, const void* X, FusedMnPlan* fp) {
     for (int CL = 1; CL <= TRM_MAX_CL; CL *= 2) {
         if (h->fused_cl > 0 && CL != h->fused_cl) continue;
         const int rows_max = (NR + CL - 1) / CL;
-        if (rows_max > TRM_GMAX * TRM_NCT) continue;
+        if (rows_max > TRM_GMAX * TRM_NCT || NR < CL) continue;    // every CTA of the cluster needs at least one row
         const size_t sx = ((size_t)rows_max * IK * sizeof(T) + 127) / 128 * 128;
         const size_t st = ((size_t)rows_max * RKS * sizeof(T) + 15) / 16 * 16;
         if (head + 4 * (sx + st) > budget) continue;
@@ -618,6 +618,7 @@ int run_fused_mn(tr_handle* h, const T* X, const long long* y, const T* class_w,
 #ifdef TRM_TRACE
     if ((rc = ensure(h, h->trace, (size_t)TRM_TRACE_N * TRM_TRACE_EV * sizeof(long long)))) return rc;
     fa.trace = (long long*)h->trace.p;
+    fa.dbg = h->flow_debug;                       // timing experiments (option "flow_debug"), trace builds only
     smem_launch += (size_t)TRM_TRACE_N * TRM_TRACE_EV * sizeof(long long);
 #endif
     if ((rc = raise_smem_limit(h, fp.kern, smem_launch))) return rc;

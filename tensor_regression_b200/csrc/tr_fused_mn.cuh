@@ -64,6 +64,8 @@ struct FusedMnArgs {
     unsigned head_bytes;     // offset of X stage 0 in the dynamic shared memory
     unsigned piece;          // bytes per bulk-copy instruction
     long long* trace;        // debug timeline (build with -DTRM_TRACE, tools/fused_mn_trace.py), else null
+    int dbg;                 // TRM_TRACE builds only: 1 = gradient warps skip their work, 2 = forward warps skip theirs,
+                             // 4 = the epilogue skips its math (timing experiments: WRONG results)
 };
 
 template <typename T>
@@ -88,12 +90,14 @@ struct FusedMnCtl {
 #define TRM_TRACE_N 48
 #define TRM_TRACE_EV 16
 #ifdef TRM_TRACE
+#define TRM_DBG(bit) (a.dbg & (bit))
 #define TRM_STAMP(ev, i)                                                                                   \
     do {                                                                                                   \
         if (a.trace && cid == 0 && crank == 0 && (i) >= TRM_TRACE_I0 && (i) < TRM_TRACE_I0 + TRM_TRACE_N)  \
             strace[((i) - TRM_TRACE_I0) * TRM_TRACE_EV + (ev)] = clock64();                                \
     } while (0)
 #else
+#define TRM_DBG(bit) 0
 #define TRM_STAMP(ev, i) do { } while (0)
 #endif
 
@@ -158,9 +162,16 @@ template <> __device__ __forceinline__ double trm_log<double>(double x) { return
 // max-subtraction in the second softmax (its arguments are probabilities in [0,1]; exp(P)/sum exp(P) is the same
 // quotient), one table sFCw[c][r] = w_r * FC[c,r] for both the logits and v.  The fp64 epilogue of the two-pass path
 // (epi_mn_core) agrees with it to a few ulp of T; both are checked against the oracle at the north-star tolerance.
-template <typename T, int RKS>
+// a / b for b > 0: one reciprocal + one multiply for float (2 ulp; the IEEE sequence has a divergent slow path)
+__device__ __forceinline__ float trm_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double trm_div(double a, double b) { return a / b; }
+
+template <typename T, int RKS, int STEPS>
 __device__ __forceinline__ void trm_epilogue(const EpiMnArgs<T>& a, long long n, const T (&u)[RKS], int lane, const T* sFCw,
-                                             int red_hi, int yn, T omega, double& loss, T (&vout)[RKS]) {
+                                             int yn, T omega, double& loss, T (&vout)[RKS]) {
+    // reductions run over groups of 2^STEPS lanes (2^STEPS >= C, fully unrolled butterflies): every lane of group 0 —
+    // the classes, and the lanes that send v to the peers when STEPS >= 4 — ends with the group totals; the other
+    // groups (STEPS = 4 only) hold inactive lanes whose sums are patched to 1 so that nothing divides by zero
     const int C = a.C, R = a.R;
     const bool act = lane < C;
     T fc[RKS];
@@ -169,32 +180,35 @@ __device__ __forceinline__ void trm_epilogue(const EpiMnArgs<T>& a, long long n,
 #pragma unroll
     for (int r = 0; r < RKS; ++r) z = tr_fma<T>(u[r], fc[r], z);
     T zmax = act ? z : -INFINITY;
-    for (int off = red_hi; off >= 1; off >>= 1) zmax = fmax(zmax, __shfl_xor_sync(TR_FULL, zmax, off));
+#pragma unroll
+    for (int st = STEPS - 1; st >= 0; --st) zmax = fmax(zmax, __shfl_xor_sync(TR_FULL, zmax, 1 << st));
     const T e = act ? trm_exp<T>(z - zmax) : (T)0;
     T zs = e;
-    for (int off = red_hi; off >= 1; off >>= 1) zs += __shfl_xor_sync(TR_FULL, zs, off);
-    const T P = e / zs;
+#pragma unroll
+    for (int st = STEPS - 1; st >= 0; --st) zs += __shfl_xor_sync(TR_FULL, zs, 1 << st);
+    const T P = trm_div(e, zs > (T)0 ? zs : (T)1);
     if (act && a.P) a.P[n * C + lane] = P;
     const T qe = act ? trm_exp<T>(P) : (T)0;
     T qs = qe;
-    for (int off = red_hi; off >= 1; off >>= 1) qs += __shfl_xor_sync(TR_FULL, qs, off);
-    const T q = qe / qs;
+#pragma unroll
+    for (int st = STEPS - 1; st >= 0; --st) qs += __shfl_xor_sync(TR_FULL, qs, 1 << st);
+    qs = qs > (T)0 ? qs : (T)1;
+    const T q = trm_div(qe, qs);
     if (act && lane == yn) loss += (double)(-omega * (P - trm_log<T>(qs)));          // -omega log Q[n,y_n]
     const T dP = act ? omega * (q - (lane == yn ? (T)1 : (T)0)) : (T)0;
     T dot = dP * P;
-    for (int off = red_hi; off >= 1; off >>= 1) dot += __shfl_xor_sync(TR_FULL, dot, off);
+#pragma unroll
+    for (int st = STEPS - 1; st >= 0; --st) dot += __shfl_xor_sync(TR_FULL, dot, 1 << st);
     const T dZ = act ? P * (dP - dot) : (T)0;
     if (act && a.dZ_ws) a.dZ_ws[n * C + lane] = dZ;
-    // v[r] = w_r sum_c dZ[c] FC[c,r]: RKS independent reductions, every lane ends with all of them
+    // v[r] = w_r sum_c dZ[c] FC[c,r]: RKS independent butterflies
 #pragma unroll
     for (int r = 0; r < RKS; ++r) vout[r] = dZ * fc[r];
-    for (int off = red_hi; off >= 1; off >>= 1) {
 #pragma unroll
-        for (int r = 0; r < RKS; ++r) vout[r] += __shfl_xor_sync(TR_FULL, vout[r], off);
+    for (int st = STEPS - 1; st >= 0; --st) {
+#pragma unroll
+        for (int r = 0; r < RKS; ++r) vout[r] += __shfl_xor_sync(TR_FULL, vout[r], 1 << st);
     }
-    // lanes outside the reduction group of lane 0 (C small) hold sums of inactive lanes: every lane takes lane 0's
-#pragma unroll
-    for (int r = 0; r < RKS; ++r) vout[r] = __shfl_sync(TR_FULL, vout[r], 0);
     if (lane < R && a.u_ws) {
         T ur = (T)0;
 #pragma unroll
@@ -225,6 +239,9 @@ __device__ __forceinline__ void trm_gradient_role(const FusedMnArgs<T>& a, Fused
 #pragma unroll
         for (int r = 0; r < RKS; ++r) S[j][r] = (T)0;
 
+    int rlc[TRM_GMAX];
+#pragma unroll
+    for (int j = 0; j < TRM_GMAX; ++j) rlc[j] = min(tb + j * TRM_NCT, nrows - 1);
     int s = 0;
     unsigned ph = 0;
     int left = (int)(a.spc < cnt ? a.spc : cnt);
@@ -238,28 +255,36 @@ __device__ __forceinline__ void trm_gradient_role(const FusedMnArgs<T>& a, Fused
         trf::SVec<T, RKS>::ld(&ctl->vbuf[s][0], v);
         const T* xs = reinterpret_cast<const T*>(stageX0 + (size_t)s * a.stage_x_bytes);
         const T* ts = reinterpret_cast<const T*>(stageT0 + (size_t)s * a.stage_t_bytes);
+        // No branches in the row loop: rows past nrows read this CTA's last row (always written by the TMA, every CTA
+        // has at least one row) against F12 = 0, i.e. contribute exact zeros, so that all shared-memory loads of a
+        // sample can be issued ahead of the FMAs (one warp per role and sub-partition: nothing else hides LDS latency).
+        T c[TRM_GMAX][RKS];
+        if (!TRM_DBG(1)) {
 #pragma unroll
         for (int j = 0; j < TRM_GMAX; ++j) {
-            const int rl = tb + j * TRM_NCT;
-            if (rl < nrows) {
-                T c[RKS];
-                trf::SVec<T, RKS>::ld(sF12 + (size_t)rl * RKS, c);
+            trf::SVec<T, RKS>::ld(sF12 + (size_t)(tb + j * TRM_NCT) * RKS, c[j]);
 #pragma unroll
-                for (int r = 0; r < RKS; ++r) c[r] *= v[r];
-                if (WITH_S) {
-                    T tt[RKS];
-                    trf::SVec<T, RKS>::ld(ts + (size_t)rl * RKS, tt);
+            for (int r = 0; r < RKS; ++r) c[j][r] *= v[r];
+        }
+        if (WITH_S) {
 #pragma unroll
-                    for (int r = 0; r < RKS; ++r) S[j][r] = tr_fma<T>(v[r], tt[r], S[j][r]);
-                }
+            for (int j = 0; j < TRM_GMAX; ++j) {
+                T tt[RKS];
+                trf::SVec<T, RKS>::ld(ts + (size_t)rlc[j] * RKS, tt);
 #pragma unroll
-                for (int qq = 0; qq < QN; ++qq) {
-                    T x[VEC];
-                    trf::SLoad<T, VEC>::ld(xs + (size_t)rl * IK + (Q0 + qq) * VEC, x);
-#pragma unroll
-                    for (int vv = 0; vv < VEC; ++vv) trf::fma_row(acc[qq * VEC + vv], x[vv], c);
-                }
+                for (int r = 0; r < RKS; ++r) S[j][r] = tr_fma<T>(v[r], tt[r], S[j][r]);
             }
+        }
+#pragma unroll
+        for (int j = 0; j < TRM_GMAX; ++j) {
+#pragma unroll
+            for (int qq = 0; qq < QN; ++qq) {
+                T x[VEC];
+                trf::SLoad<T, VEC>::ld(xs + (size_t)rlc[j] * IK + (Q0 + qq) * VEC, x);
+#pragma unroll
+                for (int vv = 0; vv < VEC; ++vv) trf::fma_row(acc[qq * VEC + vv], x[vv], c[j]);
+            }
+        }
         }
         __syncwarp();
         if (tb == 0) TRM_STAMP(WITH_S ? 11 : 9, i);
@@ -323,6 +348,7 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
     off += (size_t)TRM_GMAX * TRM_NCT * RKS * sizeof(T);
     off = (off + 15) / 16 * 16;
     T* sFCw = reinterpret_cast<T*>(trm_smem + off);                 // (C, RKS): w_r * FC[c,r], zero-padded channels
+    T* sCW = sFCw + (size_t)C * RKS;                                // (C): class weights omega[c]
     const unsigned char* stageX0 = trm_smem + a.head_bytes;
     const unsigned char* stageT0 = stageX0 + (size_t)NS * a.stage_x_bytes;
 #ifdef TRM_TRACE
@@ -362,6 +388,7 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
         const int c = idx / RKS, r = idx % RKS;
         sFCw[idx] = r < R ? (T)((double)a.w[r] * a.Ft64[a.geo.pfeat + c * R + r]) : (T)0;
     }
+    for (int idx = threadIdx.x; idx < C; idx += TRM_NT) sCW[idx] = a.class_w ? a.class_w[idx] : (T)1;
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) {
             trf::mbar_init(&ctl->full[s], 1);
@@ -386,6 +413,9 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
         T f12[TRM_GMAX][RKS];
 #pragma unroll
         for (int j = 0; j < TRM_GMAX; ++j) trf::SVec<T, RKS>::ld(sF12 + (size_t)(tid + j * TRM_NCT) * RKS, f12[j]);   // zeros past nrows
+        int rlc[TRM_GMAX];
+#pragma unroll
+        for (int j = 0; j < TRM_GMAX; ++j) rlc[j] = min(tid + j * TRM_NCT, nrows - 1);
         int s = 0;
         unsigned ph = 0;
         for (int i = 0; i < cnt; ++i) {
@@ -399,6 +429,9 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
             for (int j = 0; j < TRM_GMAX; ++j)
 #pragma unroll
                 for (int r = 0; r < RKS; ++r) t[j][r] = (T)0;
+            // branch-free (rows past nrows recompute this CTA's last row; their t is neither stored nor summed), so the
+            // loads of chunk q+1 can be in flight during the FMAs of chunk q
+            if (!TRM_DBG(2))
 #pragma unroll
             for (int q = 0; q < IKC; ++q) {
                 T f3[VEC][RKS];                                    // F3 rows of this chunk: broadcast loads
@@ -406,13 +439,10 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
                 for (int vv = 0; vv < VEC; ++vv) trf::SVec<T, RKS>::ld(sF3 + (size_t)(q * VEC + vv) * RKS, f3[vv]);
 #pragma unroll
                 for (int j = 0; j < TRM_GMAX; ++j) {
-                    const int rl = tid + j * TRM_NCT;
-                    if (rl < nrows) {
-                        T x[VEC];
-                        trf::SLoad<T, VEC>::ld(xs + (size_t)rl * IK + q * VEC, x);
+                    T x[VEC];
+                    trf::SLoad<T, VEC>::ld(xs + (size_t)rlc[j] * IK + q * VEC, x);
 #pragma unroll
-                        for (int vv = 0; vv < VEC; ++vv) trf::fma_row(t[j], x[vv], f3[vv]);
-                    }
+                    for (int vv = 0; vv < VEC; ++vv) trf::fma_row(t[j], x[vv], f3[vv]);
                 }
             }
             T vals[TRM_RKMAX];
@@ -420,12 +450,9 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
             for (int r = 0; r < TRM_RKMAX; ++r) vals[r] = (T)0;
 #pragma unroll
             for (int j = 0; j < TRM_GMAX; ++j) {
-                const int rl = tid + j * TRM_NCT;
-                if (rl < nrows) {
-                    trf::SVec<T, RKS>::st(ts + (size_t)rl * RKS, t[j]);
+                if (tid + j * TRM_NCT < nrows) trf::SVec<T, RKS>::st(ts + (size_t)(tid + j * TRM_NCT) * RKS, t[j]);
 #pragma unroll
-                    for (int r = 0; r < RKS; ++r) vals[r] = tr_fma<T>(t[j][r], f12[j][r], vals[r]);
-                }
+                for (int r = 0; r < RKS; ++r) vals[r] = tr_fma<T>(t[j][r], f12[j][r], vals[r]);     // f12 = 0 past nrows
             }
             warp_reduce_transpose<T, TRM_RKMAX, 0>(vals, lane);   // lane l: total of channel l >> 2
             if ((lane & 3) == 0) ctl->pA[s][warp][lane >> 2] = vals[0];
@@ -488,45 +515,46 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
         ea.FC = nullptr; ea.w = a.w; ea.y = a.y; ea.dP_in = nullptr; ea.class_w = a.class_w;
         ea.P = a.P; ea.pred = nullptr; ea.V = nullptr; ea.u_ws = a.u_ws; ea.dZ_ws = a.dZ_ws; ea.part = nullptr;
         double loss = 0.0;
-        int red_hi = 1;                                             // reductions run over the next power of two >= C lanes
-        while (red_hi * 2 < C) red_hi *= 2;
-        if (C <= 1) red_hi = 0;
         int slot = 0;
         unsigned phc = 0;
         int s = (int)crank % NS;
         const int sstep = CL % NS;
+        // the label of the NEXT owned sample is fetched one iteration ahead: a global load issued when the partials
+        // arrive would sit on the critical path (~2 000 cycles under a saturated HBM), class weights are in shared memory
+        long long y_next = (int)crank < cnt ? __ldg(a.y + cid + (long long)crank * a.NC) : 0;
         for (int i = (int)crank; i < cnt; i += CL) {
             const long long n = (long long)cid + (long long)i * a.NC;
-            // label and class weight: in flight while the partials arrive
-            const int yn = (int)__ldg(a.y + n);
-            const T omega = a.class_w ? __ldg(a.class_w + yn) : (T)1;
+            const int yn = (int)y_next;
+            if (i + CL < cnt) y_next = __ldg(a.y + n + (long long)CL * a.NC);
+            const T omega = sCW[yn];
             if (lane == 0) trf::mbar_arrive_expect_tx(&ctl->cready[slot], (unsigned)(CL * RKS * sizeof(T)));
             if (lane == 0) TRM_STAMP(4, i);
             trf::mbar_wait(&ctl->cready[slot], phc);
             __syncwarp();
             if (lane == 0) TRM_STAMP(5, i);
-            // u[n,:] = sum of the CL CTA partials: four interleaved running sums combined in a fixed order
-            T u4[4][RKS];
+            // u[n,:] = sum of the CL CTA partials: lane c (and its twin c + 16) holds CTA c's partial, a fixed 4-step
+            // butterfly sums them (same tree on every launch)
+            T u[RKS], vv[RKS];
+            {
+                const int cc = lane & (TRM_MAX_CL - 1);
+                trf::SVec<T, RKS>::ld(&ctl->cpart[slot][cc < CL ? cc : 0][0], u);
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4)
+                for (int r = 0; r < RKS; ++r) u[r] = cc < CL ? u[r] : (T)0;
 #pragma unroll
-                for (int r = 0; r < RKS; ++r) u4[q4][r] = (T)0;
-            for (int c0 = 0; c0 < CL; c0 += 4) {
+                for (int st = 3; st >= 0; --st) {
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    if (c0 + q4 < CL) {
-                        T pc[RKS];
-                        trf::SVec<T, RKS>::ld(&ctl->cpart[slot][c0 + q4][0], pc);
-#pragma unroll
-                        for (int r = 0; r < RKS; ++r) u4[q4][r] += pc[r];
-                    }
+                    for (int r = 0; r < RKS; ++r) u[r] += __shfl_xor_sync(TR_FULL, u[r], 1 << st);
                 }
             }
-            T u[RKS], vv[RKS];
-#pragma unroll
-            for (int r = 0; r < RKS; ++r) u[r] = (u4[0][r] + u4[1][r]) + (u4[2][r] + u4[3][r]);
             if (lane == 0) TRM_STAMP(6, i);
-            trm_epilogue<T, RKS>(ea, n, u, lane, sFCw, red_hi, yn, omega, loss, vv);
+            if (TRM_DBG(4)) {
+#pragma unroll
+                for (int r = 0; r < RKS; ++r) vv[r] = u[r];
+            } else if (C <= 16) {
+                trm_epilogue<T, RKS, 4>(ea, n, u, lane, sFCw, yn, omega, loss, vv);
+            } else {
+                trm_epilogue<T, RKS, 5>(ea, n, u, lane, sFCw, yn, omega, loss, vv);
+            }
             if (lane == 0) TRM_STAMP(7, i);
             if (lane < CL) {
 #pragma unroll

@@ -241,7 +241,8 @@ def test_fused_mn_cfg3_full_size_properties():
     B_zero = [b.clone() for b in B0]
     B_zero[-1].zero_()
     gz = eng.fwd_grad_mn(X, y, ones, dev(O.pack(B_zero)), w, 0, 50.0, 1.0)
-    assert abs(float(gz[-1]) / N - np.log(C)) < 1e-9 and float(gz[:eng.P - C * R].abs().max()) == 0.0
+    # (the single-pass kernel's epilogue runs in fp32 like the reference's own arithmetic: log C to fp32 accuracy)
+    assert abs(float(gz[-1]) / N - np.log(C)) < 2e-6 and float(gz[:eng.P - C * R].abs().max()) == 0.0
     eng.close()
     del X
     torch.cuda.empty_cache()

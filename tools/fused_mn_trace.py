@@ -21,6 +21,7 @@ from tensor_regression_b200 import _lib, engine  # noqa: E402
 
 wl = sys.argv[1] if len(sys.argv) > 1 else 'cfg3'
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
+dbg = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # 1: skip gradient work, 2: skip forward work, 4: skip epilogue math
 dims, R, C = ((100, 50, 20), 6, 10) if wl == 'cfg3' else ((100, 50, 20), 4, 4)
 dev = 'cuda:0'
 X = torch.randn((N, *dims), device=dev)
@@ -30,10 +31,11 @@ w = torch.ones(R, device=dev)
 _, y = eng.forward_mn(X, th, w, 0, 50.0, 1.0)
 cw = torch.ones(C, device=dev)
 eng.set_option('fused', 1)
+eng.set_option('flow_debug', dbg)
 for _ in range(3):
     eng.fwd_grad_mn(X, y, cw, th, w, 0, 50.0, 1.0)
 torch.cuda.synchronize()
-print(eng.launch_info())
+print('dbg', dbg, eng.launch_info())
 NS, EV = 48, 16
 out = (ctypes.c_longlong * (NS * EV))()
 _lib.lib.tr_debug_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
