@@ -106,6 +106,7 @@ struct tr_handle {
     Buf flow_ring, flow_sync;
     Buf Apart, Spart;                   // single-pass multinomial kernel: flushed A / S partial sums
     Buf trace;                          // debug timeline of k_fused_mn (builds with -DTRM_TRACE only)
+    Buf f3_stage;                       // last-mode factor in the constant buffer's layout (copied to the constant bank per launch)
     int flow_debug = 0;
 };
 
@@ -476,7 +477,14 @@ struct FusedMnPlan {
     unsigned stage_x, stage_t, head;
     size_t smem;
     const void* kern;
+    const void* f3_symbol;
 };
+
+// Launches that share a constant buffer (one per translation unit of tr_fusedmn.cu) are ordered: the buffer is
+// rewritten before every launch, so a launch on another stream must wait for the previous reader.
+struct ConstUse { cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; };
+std::mutex g_const_mu;
+std::map<std::pair<int, const void*>, ConstUse> g_const_use;
 
 template <typename T> const TrmEntry* trm_find(int IKC, int RKS);
 static const TrmEntry* trm_scan(const TrmEntry* t, int n, int IKC, int RKS) {
@@ -513,8 +521,7 @@ int plan_fused_mn(tr_handle* h, long long N, const void* X, FusedMnPlan* fp) {
     if (!ent) return TR_OK;
     const int NR = (int)(g.D / IK);
     size_t head = (sizeof(FusedMnCtl<T>) + 15) / 16 * 16;
-    head += (size_t)IK * RKS * sizeof(T);
-    head += (size_t)TRM_GMAX * TRM_NCT * RKS * sizeof(T);
+    head += (size_t)TRM_F12_ROWS * RKS * sizeof(T);
     head = (head + 15) / 16 * 16;
     head += (size_t)g.C * (RKS + 1) * sizeof(T);
     head = (head + 127) / 128 * 128;
@@ -570,6 +577,7 @@ int plan_fused_mn(tr_handle* h, long long N, const void* X, FusedMnPlan* fp) {
     fp->CL = CL; fp->NS = NS; fp->NC = NC; fp->IKC = IKC; fp->RKS = RKS; fp->NR = NR;
     fp->rows_max = (NR + CL - 1) / CL;
     fp->stage_x = best_sx; fp->stage_t = best_st; fp->head = (unsigned)head; fp->smem = smem; fp->kern = ent->kern;
+    fp->f3_symbol = ent->f3_symbol;
     const long long cnt = (N + NC - 1) / NC;
     const long long target = sizeof(T) == 4 ? 2048 : (1LL << 40);
     long long nchunk = std::max<long long>(1, (cnt + target - 1) / target);
@@ -631,13 +639,25 @@ int run_fused_mn(tr_handle* h, const T* X, const long long* y, const T* class_w,
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)fp.CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (h->prof) { rc = prof_fold(h, false); if (rc) return rc; TR_CUDA(h, cudaEventRecord(h->ev[4], st)); }
     {
+        // last-mode factor -> the kernel's constant buffer (stream-ordered); launches sharing the buffer are serialised
+        const size_t f3_bytes = (size_t)IK * fp.RKS * sizeof(T);
+        if ((rc = ensure(h, h->f3_stage, f3_bytes))) return rc;
+        k_pack_f3<T><<<1, 256, 0, st>>>((const T*)h->FtT.p + g.foff[g.k - 1], IK, g.R, fp.RKS, (T*)h->f3_stage.p);
+        TR_LAUNCH_CHECK(h);
+        std::lock_guard<std::mutex> lk(g_const_mu);
+        ConstUse& cu = g_const_use[std::make_pair(h->device, fp.f3_symbol)];
+        if (cu.done && cu.stream != st) TR_CUDA(h, cudaStreamWaitEvent(st, cu.done, 0));
+        TR_CUDA(h, cudaMemcpyToSymbolAsync(fp.f3_symbol, h->f3_stage.p, f3_bytes, 0, cudaMemcpyDeviceToDevice, st));
+        if (h->prof) { rc = prof_fold(h, false); if (rc) return rc; TR_CUDA(h, cudaEventRecord(h->ev[4], st)); }
         void* kargs[] = {(void*)&fa};
         TR_CUDA(h, cudaLaunchKernelExC(&cfg, fp.kern, kargs));
+        TR_LAUNCH_CHECK(h);
+        if (h->prof) { TR_CUDA(h, cudaEventRecord(h->ev[5], st)); h->ev_set[2] = true; }
+        if (!cu.done) TR_CUDA(h, cudaEventCreateWithFlags(&cu.done, cudaEventDisableTiming));
+        TR_CUDA(h, cudaEventRecord(cu.done, st));
+        cu.stream = st;
     }
-    TR_LAUNCH_CHECK(h);
-    if (h->prof) { TR_CUDA(h, cudaEventRecord(h->ev[5], st)); h->ev_set[2] = true; }
     // loss, class-factor gradient
     k_colsum<<<1, 128, 0, st>>>((const double*)h->epi_part.p, fp.NC * fp.CL, 1, gradsum + g.pf);
     TR_LAUNCH_CHECK(h);
@@ -1054,7 +1074,7 @@ int tr_destroy(tr_handle* h) {
     DeviceGuard dg(h->device);
     cudaDeviceSynchronize();
     Buf* bufs[] = {&h->FtT, &h->Ft64, &h->partial, &h->V, &h->u_ws, &h->dZ_ws, &h->Gpart, &h->Gred, &h->epi_part, &h->dfc_part,
-                   &h->flow_ring, &h->flow_sync, &h->Apart, &h->Spart, &h->trace};
+                   &h->flow_ring, &h->flow_sync, &h->Apart, &h->Spart, &h->trace, &h->f3_stage};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;

@@ -30,11 +30,14 @@
 #include "tr_fused.cuh"
 #include "tr_epi.cuh"
 
-#define TRM_NWF 4
+#define TRM_NWF 4                       // forward warps 0-3 (a fifth one on warp 15 was measured: its sub-partition then hosts
+                                        // two forward warps and lags, cfg 3 went from 6.8 to 7.0 ms)
+#define TRM_NFT (TRM_NWF * 32)          // forward threads: row of thread t, iteration j = t + j * TRM_NFT
 #define TRM_NWG 4
 #define TRM_NCT 128
 #define TRM_NT 512
 #define TRM_GMAX 3                      // rows per thread: a CTA holds at most TRM_GMAX * 128 rows
+#define TRM_F12_ROWS (TRM_GMAX * TRM_NFT)   // rows of the zero-padded F12 table in shared memory
 #define TRM_MAX_NS 8
 #define TRM_MAX_CL 16
 #define TRM_QO (TRM_MAX_NS + 2)         // partial slots at the owner (> NS / CL + 1 owned samples can be in flight)
@@ -67,6 +70,14 @@ struct FusedMnArgs {
     int dbg;                 // TRM_TRACE builds only: 1 = gradient warps skip their work, 2 = forward warps skip theirs,
                              // 4 = the epilogue skips its math (timing experiments: WRONG results)
 };
+
+// The last mode's factor F3 (I_k x RKS values, <= 1 KB) is the one coefficient set every forward thread needs for
+// every sample and it is warp-uniform: it lives in CONSTANT memory, so the forward FMAs take it as a constant-bank
+// operand instead of 6 broadcast LDS.128 per 16-byte chunk of a row (shared-memory bandwidth is what bounds this
+// kernel).  One buffer per translation unit; the host copies F3 into it (stream-ordered, device to device) before
+// each launch and orders launches from different streams with an event (tr_api.cu).
+#define TRM_F3_MAX (8 * 4 * TRM_RKMAX)          // IKC <= 8 chunks x 4 floats x 8 channels
+static __constant__ __align__(16) double trm_c_f3[TRM_F3_MAX];       // holds T values (float kernels use the first half)
 
 template <typename T>
 struct FusedMnCtl {
@@ -168,7 +179,7 @@ __device__ __forceinline__ double trm_div(double a, double b) { return a / b; }
 
 template <typename T, int RKS, int STEPS>
 __device__ __forceinline__ void trm_epilogue(const EpiMnArgs<T>& a, long long n, const T (&u)[RKS], int lane, const T* sFCw,
-                                             int yn, T omega, double& loss, T (&vout)[RKS]) {
+                                             int yn, T omega, T (&vout)[RKS], T& P_out, T& qs_out, T& dZ_out) {
     // reductions run over groups of 2^STEPS lanes (2^STEPS >= C, fully unrolled butterflies): every lane of group 0 —
     // the classes, and the lanes that send v to the peers when STEPS >= 4 — ends with the group totals; the other
     // groups (STEPS = 4 only) hold inactive lanes whose sums are patched to 1 so that nothing divides by zero
@@ -187,20 +198,17 @@ __device__ __forceinline__ void trm_epilogue(const EpiMnArgs<T>& a, long long n,
 #pragma unroll
     for (int st = STEPS - 1; st >= 0; --st) zs += __shfl_xor_sync(TR_FULL, zs, 1 << st);
     const T P = trm_div(e, zs > (T)0 ? zs : (T)1);
-    if (act && a.P) a.P[n * C + lane] = P;
     const T qe = act ? trm_exp<T>(P) : (T)0;
     T qs = qe;
 #pragma unroll
     for (int st = STEPS - 1; st >= 0; --st) qs += __shfl_xor_sync(TR_FULL, qs, 1 << st);
     qs = qs > (T)0 ? qs : (T)1;
     const T q = trm_div(qe, qs);
-    if (act && lane == yn) loss += (double)(-omega * (P - trm_log<T>(qs)));          // -omega log Q[n,y_n]
     const T dP = act ? omega * (q - (lane == yn ? (T)1 : (T)0)) : (T)0;
     T dot = dP * P;
 #pragma unroll
     for (int st = STEPS - 1; st >= 0; --st) dot += __shfl_xor_sync(TR_FULL, dot, 1 << st);
     const T dZ = act ? P * (dP - dot) : (T)0;
-    if (act && a.dZ_ws) a.dZ_ws[n * C + lane] = dZ;
     // v[r] = w_r sum_c dZ[c] FC[c,r]: RKS independent butterflies
 #pragma unroll
     for (int r = 0; r < RKS; ++r) vout[r] = dZ * fc[r];
@@ -209,6 +217,18 @@ __device__ __forceinline__ void trm_epilogue(const EpiMnArgs<T>& a, long long n,
 #pragma unroll
         for (int r = 0; r < RKS; ++r) vout[r] += __shfl_xor_sync(TR_FULL, vout[r], 1 << st);
     }
+    P_out = P; qs_out = qs; dZ_out = dZ;
+}
+
+// What the gradient warps do not wait for: outputs and the loss term, after v[n,:] is on its way to the peers
+template <typename T, int RKS>
+__device__ __forceinline__ void trm_epilogue_tail(const EpiMnArgs<T>& a, long long n, const T (&u)[RKS], int lane, int yn,
+                                                  T omega, T P, T qs, T dZ, double& loss) {
+    const int C = a.C, R = a.R;
+    const bool act = lane < C;
+    if (act && a.P) a.P[n * C + lane] = P;
+    if (act && a.dZ_ws) a.dZ_ws[n * C + lane] = dZ;
+    if (act && lane == yn) loss += (double)(-omega * (P - trm_log<T>(qs)));          // -omega log Q[n,y_n]
     if (lane < R && a.u_ws) {
         T ur = (T)0;
 #pragma unroll
@@ -218,15 +238,91 @@ __device__ __forceinline__ void trm_epilogue(const EpiMnArgs<T>& a, long long n,
 }
 
 // One gradient group: chunks [Q0, Q0 + QN) of every row of this CTA (and the row sums S when WITH_S).
-template <typename T, int IKC, int RKS, int Q0, int QN, bool WITH_S>
+// One sample of the forward role for a warp with NJ row iterations (rows tid + j * TRM_NFT): t[row,:] to shared memory,
+// the lane's partial of u[n,:] in vals.  Branch-free like trm_gradient_sample.
+template <typename T, int IKC, int RKS, int NJ>
+__device__ __forceinline__ void trm_forward_sample(T (&vals)[TRM_RKMAX], const T* cF3, const T (&f12)[TRM_GMAX][RKS], const T* xs,
+                                                   T* ts, int tid, int nrows, const int (&rlc)[TRM_GMAX], bool store_t) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int IK = IKC * VEC;
+    T t[NJ][RKS];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int r = 0; r < RKS; ++r) t[j][r] = (T)0;
+#pragma unroll
+    for (int q = 0; q < IKC; ++q) {
+        T f3[VEC][RKS];                                    // F3 rows of this chunk: constant-bank operands
+#pragma unroll
+        for (int vv = 0; vv < VEC; ++vv)
+#pragma unroll
+            for (int r = 0; r < RKS; ++r) f3[vv][r] = cF3[(q * VEC + vv) * RKS + r];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            T x[VEC];
+            trf::SLoad<T, VEC>::ld(xs + (size_t)rlc[j] * IK + q * VEC, x);
+#pragma unroll
+            for (int vv = 0; vv < VEC; ++vv) trf::fma_row(t[j], x[vv], f3[vv]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        if (tid + j * TRM_NFT < nrows && store_t) trf::SVec<T, RKS>::st(ts + (size_t)(tid + j * TRM_NFT) * RKS, t[j]);
+#pragma unroll
+        for (int r = 0; r < RKS; ++r) vals[r] = tr_fma<T>(t[j][r], f12[j][r], vals[r]);     // f12 = 0 past nrows
+    }
+}
+
+// One sample of a gradient group for a warp with NJ row iterations.  No branches: lanes whose row of iteration j lies
+// past nrows read this CTA's last row (always written by the TMA) against F12 = 0, i.e. contribute exact zeros, so all
+// shared-memory loads of the sample can be issued ahead of the FMAs (one warp per role and sub-partition: nothing else
+// hides the LDS latency).
+template <typename T, int IKC, int RKS, int Q0, int QN, bool WITH_S, int NJ>
+__device__ __forceinline__ void trm_gradient_sample(T (&acc)[QN * (16 / (int)sizeof(T))][RKS], T (&S)[WITH_S ? TRM_GMAX : 1][RKS],
+                                                    const T (&v)[RKS], const T* sF12, const T* xs, const T* ts, int tb,
+                                                    const int (&rlc)[TRM_GMAX]) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int IK = IKC * VEC;
+    T c[NJ][RKS];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        trf::SVec<T, RKS>::ld(sF12 + (size_t)(tb + j * TRM_NCT) * RKS, c[j]);
+#pragma unroll
+        for (int r = 0; r < RKS; ++r) c[j][r] *= v[r];
+    }
+    if (WITH_S) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            T tt[RKS];
+            trf::SVec<T, RKS>::ld(ts + (size_t)rlc[j] * RKS, tt);
+#pragma unroll
+            for (int r = 0; r < RKS; ++r) S[j][r] = tr_fma<T>(v[r], tt[r], S[j][r]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+        for (int qq = 0; qq < QN; ++qq) {
+            T x[VEC];
+            trf::SLoad<T, VEC>::ld(xs + (size_t)rlc[j] * IK + (Q0 + qq) * VEC, x);
+#pragma unroll
+            for (int vv = 0; vv < VEC; ++vv) trf::fma_row(acc[qq * VEC + vv], x[vv], c[j]);
+        }
+    }
+}
+
+// ROT rotates the thread -> row assignment by ROT warps: with nrows between 2 and 3 rows per thread the first warps of
+// a role carry one row more than the last ones; rotating the gradient roles puts their heavy warps on the
+// sub-partitions where the forward role has its light ones (warp w issues on sub-partition w % 4).
+template <typename T, int IKC, int RKS, int Q0, int QN, bool WITH_S, int ROT>
 __device__ __forceinline__ void trm_gradient_role(const FusedMnArgs<T>& a, FusedMnCtl<T>* ctl, const T* sF12,
                                                   const unsigned char* stageX0, const unsigned char* stageT0,
                                                   int cnt, int cid, unsigned crank, int nrows, int row0, long long* strace) {
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int IK = IKC * VEC;
     const int lane = threadIdx.x & 31;
-    const int tb = threadIdx.x & (TRM_NCT - 1);
-    const int gw = tb >> 5;
+    const int gw = (threadIdx.x & (TRM_NCT - 1)) >> 5;                          // physical warp of the role: flush slot
+    const int tb = (threadIdx.x + ROT * 32) & (TRM_NCT - 1);                    // role-relative thread id for the row assignment
     const int NS = a.NS;
     T acc[QN * VEC][RKS];
 #pragma unroll
@@ -242,6 +338,9 @@ __device__ __forceinline__ void trm_gradient_role(const FusedMnArgs<T>& a, Fused
     int rlc[TRM_GMAX];
 #pragma unroll
     for (int j = 0; j < TRM_GMAX; ++j) rlc[j] = min(tb + j * TRM_NCT, nrows - 1);
+    int nj = 0;
+#pragma unroll
+    for (int j = 0; j < TRM_GMAX; ++j) nj += ((tb & ~31) + j * TRM_NCT < nrows) ? 1 : 0;
     int s = 0;
     unsigned ph = 0;
     int left = (int)(a.spc < cnt ? a.spc : cnt);
@@ -258,33 +357,11 @@ __device__ __forceinline__ void trm_gradient_role(const FusedMnArgs<T>& a, Fused
         // No branches in the row loop: rows past nrows read this CTA's last row (always written by the TMA, every CTA
         // has at least one row) against F12 = 0, i.e. contribute exact zeros, so that all shared-memory loads of a
         // sample can be issued ahead of the FMAs (one warp per role and sub-partition: nothing else hides LDS latency).
-        T c[TRM_GMAX][RKS];
+        // row iterations this WARP really has (warp-uniform): a warp whose rows of iteration j all lie past nrows skips it
         if (!TRM_DBG(1)) {
-#pragma unroll
-        for (int j = 0; j < TRM_GMAX; ++j) {
-            trf::SVec<T, RKS>::ld(sF12 + (size_t)(tb + j * TRM_NCT) * RKS, c[j]);
-#pragma unroll
-            for (int r = 0; r < RKS; ++r) c[j][r] *= v[r];
-        }
-        if (WITH_S) {
-#pragma unroll
-            for (int j = 0; j < TRM_GMAX; ++j) {
-                T tt[RKS];
-                trf::SVec<T, RKS>::ld(ts + (size_t)rlc[j] * RKS, tt);
-#pragma unroll
-                for (int r = 0; r < RKS; ++r) S[j][r] = tr_fma<T>(v[r], tt[r], S[j][r]);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < TRM_GMAX; ++j) {
-#pragma unroll
-            for (int qq = 0; qq < QN; ++qq) {
-                T x[VEC];
-                trf::SLoad<T, VEC>::ld(xs + (size_t)rlc[j] * IK + (Q0 + qq) * VEC, x);
-#pragma unroll
-                for (int vv = 0; vv < VEC; ++vv) trf::fma_row(acc[qq * VEC + vv], x[vv], c[j]);
-            }
-        }
+            if (nj == 3) trm_gradient_sample<T, IKC, RKS, Q0, QN, WITH_S, 3>(acc, S, v, sF12, xs, ts, tb, rlc);
+            else if (nj == 2) trm_gradient_sample<T, IKC, RKS, Q0, QN, WITH_S, 2>(acc, S, v, sF12, xs, ts, tb, rlc);
+            else if (nj == 1) trm_gradient_sample<T, IKC, RKS, Q0, QN, WITH_S, 1>(acc, S, v, sF12, xs, ts, tb, rlc);
         }
         __syncwarp();
         if (tb == 0) TRM_STAMP(WITH_S ? 11 : 9, i);
@@ -339,13 +416,11 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
     const int NS = a.NS, CL = a.CL;
     const int k = a.geo.k, R = a.geo.R, C = a.geo.C;
 
-    // layout: [control | F3 (I_k, RKS) | F12 (GMAX*128, RKS) | w * class factor (C, RKS) | pad | X stages | t stages]
+    // layout: [control | F12 (GMAX*128, RKS) | w * class factor (C, RKS), class weights (C) | pad | X stages | t stages]
     FusedMnCtl<T>* ctl = reinterpret_cast<FusedMnCtl<T>*>(trm_smem);
     size_t off = (sizeof(FusedMnCtl<T>) + 15) / 16 * 16;
-    T* sF3 = reinterpret_cast<T*>(trm_smem + off);
-    off += (size_t)IK * RKS * sizeof(T);
     T* sF12 = reinterpret_cast<T*>(trm_smem + off);
-    off += (size_t)TRM_GMAX * TRM_NCT * RKS * sizeof(T);
+    off += (size_t)TRM_F12_ROWS * RKS * sizeof(T);
     off = (off + 15) / 16 * 16;
     T* sFCw = reinterpret_cast<T*>(trm_smem + off);                 // (C, RKS): w_r * FC[c,r], zero-padded channels
     T* sCW = sFCw + (size_t)C * RKS;                                // (C): class weights omega[c]
@@ -365,11 +440,7 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
 
     if (threadIdx.x < TR_MAX_MODES) ctl->dims[threadIdx.x] = a.geo.dims[threadIdx.x];
     if (threadIdx.x < TR_MAX_MODES + 2) ctl->foff[threadIdx.x] = a.geo.foff[threadIdx.x];
-    for (int idx = threadIdx.x; idx < IK * RKS; idx += TRM_NT) {
-        const int i3 = idx / RKS, r = idx % RKS;
-        sF3[idx] = r < R ? a.FtT[a.geo.foff[k - 1] + i3 * R + r] : (T)0;
-    }
-    for (int idx = threadIdx.x; idx < TRM_GMAX * TRM_NCT * RKS; idx += TRM_NT) {
+    for (int idx = threadIdx.x; idx < TRM_F12_ROWS * RKS; idx += TRM_NT) {
         const int rl = idx / RKS, r = idx % RKS;
         T p = (T)0;
         if (rl < nrows && r < R) {
@@ -409,13 +480,18 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
 
     if (warp < TRM_NWF) {
         // ===================================== forward =====================================
-        const int tid = threadIdx.x;                              // 0..127
+        const int fw = warp;
+        const int tid = fw * 32 + lane;                           // 0..127
+        const T* cF3 = reinterpret_cast<const T*>(trm_c_f3);
         T f12[TRM_GMAX][RKS];
 #pragma unroll
-        for (int j = 0; j < TRM_GMAX; ++j) trf::SVec<T, RKS>::ld(sF12 + (size_t)(tid + j * TRM_NCT) * RKS, f12[j]);   // zeros past nrows
+        for (int j = 0; j < TRM_GMAX; ++j) trf::SVec<T, RKS>::ld(sF12 + (size_t)(tid + j * TRM_NFT) * RKS, f12[j]);   // zeros past nrows
         int rlc[TRM_GMAX];
 #pragma unroll
-        for (int j = 0; j < TRM_GMAX; ++j) rlc[j] = min(tid + j * TRM_NCT, nrows - 1);
+        for (int j = 0; j < TRM_GMAX; ++j) rlc[j] = min(tid + j * TRM_NFT, nrows - 1);
+        int nj = 0;                                               // row iterations of this warp (warp-uniform)
+#pragma unroll
+        for (int j = 0; j < TRM_GMAX; ++j) nj += (fw * 32 + j * TRM_NFT < nrows) ? 1 : 0;
         int s = 0;
         unsigned ph = 0;
         for (int i = 0; i < cnt; ++i) {
@@ -424,48 +500,27 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
             if (tid == 0) TRM_STAMP(1, i);
             const T* xs = reinterpret_cast<const T*>(stageX0 + (size_t)s * a.stage_x_bytes);
             T* ts = reinterpret_cast<T*>(const_cast<unsigned char*>(stageT0) + (size_t)s * a.stage_t_bytes);
-            T t[TRM_GMAX][RKS];
-#pragma unroll
-            for (int j = 0; j < TRM_GMAX; ++j)
-#pragma unroll
-                for (int r = 0; r < RKS; ++r) t[j][r] = (T)0;
-            // branch-free (rows past nrows recompute this CTA's last row; their t is neither stored nor summed), so the
-            // loads of chunk q+1 can be in flight during the FMAs of chunk q
-            if (!TRM_DBG(2))
-#pragma unroll
-            for (int q = 0; q < IKC; ++q) {
-                T f3[VEC][RKS];                                    // F3 rows of this chunk: broadcast loads
-#pragma unroll
-                for (int vv = 0; vv < VEC; ++vv) trf::SVec<T, RKS>::ld(sF3 + (size_t)(q * VEC + vv) * RKS, f3[vv]);
-#pragma unroll
-                for (int j = 0; j < TRM_GMAX; ++j) {
-                    T x[VEC];
-                    trf::SLoad<T, VEC>::ld(xs + (size_t)rlc[j] * IK + q * VEC, x);
-#pragma unroll
-                    for (int vv = 0; vv < VEC; ++vv) trf::fma_row(t[j], x[vv], f3[vv]);
-                }
-            }
             T vals[TRM_RKMAX];
 #pragma unroll
             for (int r = 0; r < TRM_RKMAX; ++r) vals[r] = (T)0;
-#pragma unroll
-            for (int j = 0; j < TRM_GMAX; ++j) {
-                if (tid + j * TRM_NCT < nrows) trf::SVec<T, RKS>::st(ts + (size_t)(tid + j * TRM_NCT) * RKS, t[j]);
-#pragma unroll
-                for (int r = 0; r < RKS; ++r) vals[r] = tr_fma<T>(t[j][r], f12[j][r], vals[r]);     // f12 = 0 past nrows
+            if (!TRM_DBG(2)) {
+                if (nj == 3) trm_forward_sample<T, IKC, RKS, 3>(vals, cF3, f12, xs, ts, tid, nrows, rlc, !TRM_DBG(16));
+                else if (nj == 2) trm_forward_sample<T, IKC, RKS, 2>(vals, cF3, f12, xs, ts, tid, nrows, rlc, !TRM_DBG(16));
+                else if (nj == 1) trm_forward_sample<T, IKC, RKS, 1>(vals, cF3, f12, xs, ts, tid, nrows, rlc, !TRM_DBG(16));
             }
+            if (tid == 0) TRM_STAMP(13, i);
             warp_reduce_transpose<T, TRM_RKMAX, 0>(vals, lane);   // lane l: total of channel l >> 2
-            if ((lane & 3) == 0) ctl->pA[s][warp][lane >> 2] = vals[0];
+            if ((lane & 3) == 0) ctl->pA[s][fw][lane >> 2] = vals[0];
             __syncwarp();
             if (tid == 0) TRM_STAMP(2, i);
             if (lane == 0) trf::mbar_arrive(&ctl->redA[s]);
             if (++s == NS) { s = 0; ph ^= 1u; }
         }
-    } else if (warp < TRM_NWF + TRM_NWG) {
-        trm_gradient_role<T, IKC, RKS, 0, QA, false>(a, ctl, sF12, stageX0, stageT0, cnt, cid, crank, nrows, row0, strace);
-    } else if (warp < TRM_NWF + 2 * TRM_NWG) {
-        trm_gradient_role<T, IKC, RKS, QA, IKC - QA, true>(a, ctl, sF12, stageX0, stageT0, cnt, cid, crank, nrows, row0, strace);
-    } else if (warp == TRM_NWF + 2 * TRM_NWG) {
+    } else if (warp < 4 + TRM_NWG) {
+        trm_gradient_role<T, IKC, RKS, 0, QA, false, 2>(a, ctl, sF12, stageX0, stageT0, cnt, cid, crank, nrows, row0, strace);
+    } else if (warp < 4 + 2 * TRM_NWG) {
+        trm_gradient_role<T, IKC, RKS, QA, IKC - QA, true, 2>(a, ctl, sF12, stageX0, stageT0, cnt, cid, crank, nrows, row0, strace);
+    } else if (warp == 4 + 2 * TRM_NWG) {
         // ================================== TMA producer ==================================
         if (lane == 0) {
             const unsigned my_bytes = (unsigned)nrows * (unsigned)IK * (unsigned)sizeof(T);
@@ -486,7 +541,7 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
                 if (++s == NS) { s = 0; if (j >= NS) ph ^= 1u; }
             }
         }
-    } else if (warp == TRM_NWF + 2 * TRM_NWG + 1) {
+    } else if (warp == 4 + 2 * TRM_NWG + 1) {
         // ===================== reducer: CTA partial of u[n,:] -> owner CTA =====================
         int s = 0, owner = 0, slot = 0;
         unsigned ph = 0;
@@ -508,7 +563,7 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
             if (++s == NS) { s = 0; ph ^= 1u; }
             if (++owner == CL) { owner = 0; if (++slot == TRM_QO) slot = 0; }
         }
-    } else if (warp == TRM_NWF + 2 * TRM_NWG + 2) {
+    } else if (warp == 4 + 2 * TRM_NWG + 2) {
         // ============== epilogue of the samples this CTA owns; v[n,:] -> every CTA ==============
         EpiMnArgs<T> ea;
         ea.partial = nullptr; ea.WT = 0; ea.RKs = RKS; ea.N = a.N; ea.R = R; ea.C = C;
@@ -547,13 +602,14 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
                 }
             }
             if (lane == 0) TRM_STAMP(6, i);
+            T eP = (T)0, eqs = (T)1, edZ = (T)0;
             if (TRM_DBG(4)) {
 #pragma unroll
                 for (int r = 0; r < RKS; ++r) vv[r] = u[r];
             } else if (C <= 16) {
-                trm_epilogue<T, RKS, 4>(ea, n, u, lane, sFCw, yn, omega, loss, vv);
+                trm_epilogue<T, RKS, 4>(ea, n, u, lane, sFCw, yn, omega, vv, eP, eqs, edZ);
             } else {
-                trm_epilogue<T, RKS, 5>(ea, n, u, lane, sFCw, yn, omega, loss, vv);
+                trm_epilogue<T, RKS, 5>(ea, n, u, lane, sFCw, yn, omega, vv, eP, eqs, edZ);
             }
             if (lane == 0) TRM_STAMP(7, i);
             if (lane < CL) {
@@ -562,6 +618,7 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
                     trf::st_async_val(trf::mapa(trf::smem_u32(&ctl->vbuf[s][r]), (unsigned)lane), vv[r],
                                       trf::mapa(trf::smem_u32(&ctl->rready[s]), (unsigned)lane));
             }
+            trm_epilogue_tail<T, RKS>(ea, n, u, lane, yn, omega, eP, eqs, edZ, loss);
             __syncwarp();
             if (++slot == TRM_QO) { slot = 0; phc ^= 1u; }
             s += sstep;
@@ -579,6 +636,15 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
     if (a.trace && cid == 0 && crank == 0)
         for (int i = threadIdx.x; i < TRM_TRACE_N * TRM_TRACE_EV; i += TRM_NT) a.trace[i] = strace[i];
 #endif
+}
+
+// F3 in the layout of the constant buffer: (I_k, RKS), channels r >= R zero
+template <typename T>
+__global__ void k_pack_f3(const T* __restrict__ F3, int IK, int R, int RKS, T* __restrict__ out) {
+    for (int idx = threadIdx.x; idx < IK * RKS; idx += blockDim.x) {
+        const int i3 = idx / RKS, r = idx % RKS;
+        out[idx] = r < R ? F3[i3 * R + r] : (T)0;
+    }
 }
 
 // dFt_k[i_k, r] = sum over (slot, CTA, warp) of the flushed A partials, in double; one block per (i_k, r)

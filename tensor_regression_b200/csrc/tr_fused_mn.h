@@ -5,6 +5,7 @@
 struct TrmEntry {
     int IKC, RKS;
     const void* kern;       // void (*)(FusedMnArgs<T>)
+    const void* f3_symbol;  // the translation unit's constant buffer trm_c_f3 (cudaGetSymbolAddress / cudaMemcpyToSymbol)
 };
 
 const TrmEntry* trm_entries_f32_0(int* n);

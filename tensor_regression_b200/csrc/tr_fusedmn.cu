@@ -8,7 +8,7 @@
 #error "compile with -DTR_MPART=0..3"
 #endif
 
-#define TRM_K(T, IKC, RKS) { IKC, RKS, (const void*)k_fused_mn<T, IKC, RKS, (IKC + 1) / 2> }
+#define TRM_K(T, IKC, RKS) { IKC, RKS, (const void*)k_fused_mn<T, IKC, RKS, (IKC + 1) / 2>, (const void*)trm_c_f3 }
 
 #if TR_MPART == 0
 static const TrmEntry tab[] = {TRM_K(float, 5, 6), TRM_K(float, 5, 4), TRM_K(float, 2, 2), TRM_K(float, 3, 2), TRM_K(float, 4, 2),
