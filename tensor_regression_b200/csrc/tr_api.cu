@@ -988,6 +988,8 @@ int mn_t(tr_handle* h, const void* X, const long long* y, const void* class_w, l
     const size_t esmem = (size_t)(g.C * g.R + g.R) * sizeof(double);
     // loop bounds of the epilogue sized to the model (same arithmetic, fewer dead iterations and registers)
     if (g.C <= 32 && g.R <= 8) k_epi_mn<T, 8, 1><<<egrid, TR_TPB, esmem, st>>>(ea);
+    else if (g.C <= 32 && g.R <= 16) k_epi_mn<T, 16, 1><<<egrid, TR_TPB, esmem, st>>>(ea);
+    else if (g.R <= 16) k_epi_mn<T, 16, TR_JC><<<egrid, TR_TPB, esmem, st>>>(ea);
     else if (g.C <= 32) k_epi_mn<T, TR_MAX_RANK_MN, 1><<<egrid, TR_TPB, esmem, st>>>(ea);
     else k_epi_mn<T, TR_MAX_RANK_MN, TR_JC><<<egrid, TR_TPB, esmem, st>>>(ea);
     TR_LAUNCH_CHECK(h);

@@ -30,6 +30,11 @@ struct KEntry {
       k_grad<T, RK, E, UG, VN<T>::v>, k_grad<T, RK, E * VN<T>::v, UG, 1>,                           \
       TR_FLOW_ENTRY(T, RK, E, UF, UG) }
 
+// channel counts whose coefficients / accumulators need more than 128 registers: one resident block per SM
+#define TR_ENTRY_WIDE(T, RK, E, UF, UG)                                                             \
+    { RK, E, UF, UG, k_fwd<T, RK, E, UF, VN<T>::v, 1>, k_fwd<T, RK, E * VN<T>::v, UF, 1, 1>,        \
+      k_grad<T, RK, E, UG, VN<T>::v, 1>, k_grad<T, RK, E * VN<T>::v, UG, 1, 1>, nullptr }
+
 const KEntry<float>* tr_entries_f32_0(int* n);
 const KEntry<float>* tr_entries_f32_1(int* n);
 const KEntry<float>* tr_entries_f32_2(int* n);

@@ -7,7 +7,7 @@
 #include "tr_kernels.cuh"
 
 #define TR_JC (TR_MAX_CLASSES / 32)
-#define TR_MAX_RANK_MN 16
+#define TR_MAX_RANK_MN 32
 
 // Gradient weights are stored with NaNs canonicalised: the dataflow kernel (tr_flow.cuh) uses the all-ones
 // bit pattern — also a NaN — as "not written yet".

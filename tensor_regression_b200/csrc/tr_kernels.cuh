@@ -239,8 +239,8 @@ __device__ __noinline__ void tr_coef_at(const T* sF, const T* sW, const int* sDi
     }
 }
 
-template <typename T, int RK, int E, int U, int VEC>
-__global__ void __launch_bounds__(TR_TPB, TR_MINB) k_fwd(const FwdArgs<T> a) {
+template <typename T, int RK, int E, int U, int VEC, int MINB = TR_MINB>
+__global__ void __launch_bounds__(TR_TPB, MINB) k_fwd(const FwdArgs<T> a) {
     extern __shared__ __align__(16) unsigned char tr_smem[];
     __shared__ int sDims[TR_MAX_MODES], sOff[TR_MAX_MODES + 2];
     T* sF = reinterpret_cast<T*>(tr_smem);
@@ -354,8 +354,8 @@ struct GradArgs {
     long long spc;     // samples per chunk
 };
 
-template <typename T, int RK, int E, int U, int VEC>
-__global__ void __launch_bounds__(TR_TPB, TR_MINB) k_grad(const GradArgs<T> a) {
+template <typename T, int RK, int E, int U, int VEC, int MINB = TR_MINB>
+__global__ void __launch_bounds__(TR_TPB, MINB) k_grad(const GradArgs<T> a) {
     constexpr int TILE = 32 * E * VEC;
     const int lane = threadIdx.x & 31;
     const long long warp_global = (long long)blockIdx.x * TR_WPB + (threadIdx.x >> 5);

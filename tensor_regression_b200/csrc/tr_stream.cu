@@ -54,7 +54,8 @@ TR_DEFINE(tr_entries_f32_1, float, TR_ENTRY(float, 4, TR_E4, TR_UF4, TR_UG4), TR
 #elif TR_PART == 2
 TR_DEFINE(tr_entries_f32_2, float, TR_ENTRY(float, 8, 2, 2, 2))
 #elif TR_PART == 3
-TR_DEFINE(tr_entries_f32_3, float, TR_ENTRY(float, 12, 1, 2, 2), TR_ENTRY(float, 16, 1, 2, 2))
+TR_DEFINE(tr_entries_f32_3, float, TR_ENTRY(float, 12, 1, 2, 2), TR_ENTRY(float, 16, 1, 2, 2), TR_ENTRY_WIDE(float, 24, 1, 1, 1),
+          TR_ENTRY_WIDE(float, 32, 1, 1, 1))
 #elif TR_PART == 4
 TR_DEFINE(tr_entries_f64_0, double, TR_ENTRY(double, 1, 4, 4, 4), TR_ENTRY(double, 2, 4, 2, 2))
 #elif TR_PART == 5
@@ -62,5 +63,6 @@ TR_DEFINE(tr_entries_f64_1, double, TR_ENTRY(double, 4, 2, 2, 2), TR_ENTRY(doubl
 #elif TR_PART == 6
 TR_DEFINE(tr_entries_f64_2, double, TR_ENTRY(double, 8, 1, 2, 2))
 #elif TR_PART == 7
-TR_DEFINE(tr_entries_f64_3, double, TR_ENTRY(double, 12, 1, 1, 1), TR_ENTRY(double, 16, 1, 1, 1))
+TR_DEFINE(tr_entries_f64_3, double, TR_ENTRY(double, 12, 1, 1, 1), TR_ENTRY(double, 16, 1, 1, 1), TR_ENTRY_WIDE(double, 24, 1, 1, 1),
+          TR_ENTRY_WIDE(double, 32, 1, 1, 1))
 #endif

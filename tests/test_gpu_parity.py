@@ -752,6 +752,7 @@ def test_cfg3_full_size_properties():
     Fs = [0.3 * torch.randn(d, R, generator=gc) for d in list(dims) + [C]]
     B0 = O.init_mn(list(dims) + [C], R, nn, scale=0.2)
     eng = engine_for(dims, R, C, torch.float32)
+    eng.set_option('fused', 0)      # the two-pass kernels (fp64 epilogue); the single-pass kernel has its own full-size test
     w = dev(torch.ones(R))
     theta_star, theta = dev(O.pack(Fs)), dev(O.pack(B0))
     P, y = eng.forward_mn(X, theta_star, w, 0, 50.0, 1.0)

@@ -199,6 +199,27 @@ def test_allreduce_through_the_c_abi_one_rank_communicator():
         eng.allreduce(buf, 0)
 
 
+@pytest.mark.parametrize('R', [20, 32])
+def test_mn_rank_above_16_runs_on_the_wide_channel_kernels(R):
+    """VERDICT r1 #12: multinomial rank 17..32 (24- and 32-channel streaming kernels, one block per SM)."""
+    from tensor_regression_b200 import engine
+    N, dims, C = 70, (9, 6, 8), 5
+    X, y, _ = O.synth_mn(N, dims, R, C, 55)
+    nn = [False, True, False, False]
+    B = O.init_mn(list(dims) + [C], R, nn, scale=0.4)
+    cw = torch.tensor([1.0, 0.5, 2.0, 1.5, 0.8])
+    for dt in (torch.float32, torch.float64):
+        want = O.closed_form_mn(X.double(), y, [b.double() for b in B], torch.ones(R, dtype=torch.float64), nn,
+                                cw.double().numpy())
+        eng = engine.Engine(dims, R, C, dt, DEV)
+        P = torch.empty((N, C), dtype=dt, device=DEV)
+        gs = eng.fwd_grad_mn(dev(X.to(dt)), dev(y), dev(cw.to(dt)), dev(O.pack([b.to(dt) for b in B])),
+                             dev(torch.ones(R, dtype=dt)), 2, 50.0, 1.0, P=P)
+        assert eng.launch_info()['channels'] in (24, 32)
+        assert rel(P, want['P']) < TOL[dt] and rel(gs, want['gradsum']) < TOL[dt]
+        eng.close()
+
+
 def test_labels_outside_the_class_range_raise():
     from tensor_regression_b200 import multinomial_tensor_regression as MTR
     X = np.random.default_rng(0).standard_normal((12, 4, 3)).astype(np.float32)
@@ -307,6 +328,7 @@ def test_cfg5_full_size_properties():
     w = dev(torch.ones(R))
     theta_star, theta = dev(O.pack(Fs)), dev(O.pack(B0))
     P, y = eng.forward_mn(X, theta_star, w, 0, 50.0, 1.0)
+    paths = set()
     for sl in (slice(0, 200), slice(N - 200, N)):
         want = O.mn_model(X[sl].cpu().double(), [f.double() for f in Fs], torch.ones(R, dtype=torch.float64), nn)
         assert rel(P[sl], want) < 1e-5
@@ -318,13 +340,20 @@ def test_cfg5_full_size_properties():
     want = O.closed_form_mn(X[sub].cpu().double(), y[sub].cpu(), [b.double() for b in B0],
                             torch.ones(R, dtype=torch.float64), nn, cw.cpu().double().numpy())['gradsum']
     assert rel(eng.fwd_grad_mn(X[sub], y[sub], cw, theta, w, 0, 50.0, 1.0), want) < 1e-5
-    full = eng.fwd_grad_mn(X, y, cw, theta, w, 0, 50.0, 1.0).clone()
-    assert torch.equal(eng.fwd_grad_mn(X, y, cw, theta, w, 0, 50.0, 1.0), full)
-    parts = torch.zeros_like(full)
-    for r in range(3):
-        lo, hi = engine.shard_bounds(N, r, 3)
-        parts += eng.fwd_grad_mn(X[lo:hi], y[lo:hi], cw, theta, w, 0, 50.0, 1.0)
-    assert rel(parts, full) < 1e-5
+    fulls = {}
+    for fused in (0, 1):
+        eng.set_option('fused', fused)
+        full = eng.fwd_grad_mn(X, y, cw, theta, w, 0, 50.0, 1.0).clone()
+        paths.add(eng.launch_info()['path'])
+        assert torch.equal(eng.fwd_grad_mn(X, y, cw, theta, w, 0, 50.0, 1.0), full)      # deterministic
+        parts = torch.zeros_like(full)
+        for r in range(3):
+            lo, hi = engine.shard_bounds(N, r, 3)
+            parts += eng.fwd_grad_mn(X[lo:hi], y[lo:hi], cw, theta, w, 0, 50.0, 1.0)
+        assert rel(parts, full) < 1e-5
+        fulls[fused] = full
+    assert rel(fulls[1], fulls[0]) < 1e-5 and len(paths) == 2, paths         # single-pass == two-pass at 125 GB
+    eng.set_option('fused', -1)
     ones = dev(torch.ones(C))
     gs = eng.fwd_grad_mn(X, y, ones, theta, w, 0, 50.0, 1.0)
     ce = float(gs[-1]) / N

@@ -199,7 +199,7 @@ def test_create_rejects_unsupported_geometry_loudly():
     assert rc == 3 and 'feature modes' in msg
     rc, msg = create(0, [4, 4], 2, 129)
     assert rc == 3 and 'n_classes' in msg
-    rc, msg = create(0, [4, 4], 17, 3)
+    rc, msg = create(0, [4, 4], 33, 3)
     assert rc == 3 and 'multinomial rank' in msg
     rc, msg = create(7, [4, 4], 2, 0)
     assert rc == 1 and 'dtype' in msg
