@@ -98,6 +98,7 @@ struct tr_handle {
     int fused_pace = 0;                 // cycles between TMA issues (tuning knob, option "fused_pace")
     int fused_piece = 32768;            // bytes per bulk-copy instruction (option "fused_piece")
     int last_fused = 0;
+    int fused_ns = 0;                   // testing knob (option "fused_ns", env TR_B200_FUSED_NS): cap on the shared-memory stages of k_fused_mn
     int fused_cl = 0;                   // testing knob (option "fused_cl"): force the cluster size of the single-pass multinomial kernel
     std::map<const void*, int> occ_clusters;
     int flow_mode = 0;                  // dataflow kernel (tr_flow.cuh), experimental: 0 never (default), 1 always (error when
@@ -524,6 +525,8 @@ int plan_fused_mn(tr_handle* h, long long N, const void* X, FusedMnPlan* fp) {
     head += (size_t)TRM_F12_ROWS * RKS * sizeof(T);
     head = (head + 15) / 16 * 16;
     head += (size_t)g.C * (RKS + 1) * sizeof(T);
+    head = (head + 15) / 16 * 16;
+    head += (size_t)2 * TRM_NFT * RKS * sizeof(T);          // the forward threads' partials of u, two samples deep
     head = (head + 127) / 128 * 128;
     #ifdef TRM_TRACE
     const size_t budget = 218 * 1024;       // room for the timeline stamps
@@ -537,10 +540,15 @@ int plan_fused_mn(tr_handle* h, long long N, const void* X, FusedMnPlan* fp) {
         const int rows_max = (NR + CL - 1) / CL;
         if (rows_max > TRM_GMAX * TRM_NCT || NR < CL) continue;    // every CTA of the cluster needs at least one row
         const size_t sx = ((size_t)rows_max * IK * sizeof(T) + 127) / 128 * 128;
+#if TRM_TMEM
+        const size_t st = 0;                                             // t[row,:] waits in tensor memory
+#else
         const size_t st = ((size_t)rows_max * RKS * sizeof(T) + 15) / 16 * 16;
+#endif
         if (head + 4 * (sx + st) > budget) continue;
         int NS = (int)((budget - head) / (sx + st));
         if (NS > TRM_MAX_NS) NS = TRM_MAX_NS;
+        if (h->fused_ns >= 4 && NS > h->fused_ns) NS = h->fused_ns;
         // the smallest cluster that still gives a deep pipeline (>= 6 stages); otherwise the deepest one
         const bool better = bestCL == 0 || (bestNS < 6 && NS > bestNS);
         if (better) { bestCL = CL; bestNS = NS; best_sx = (unsigned)sx; best_st = (unsigned)st; }
@@ -1065,6 +1073,7 @@ int tr_create(tr_handle** out, int dtype, int k, const int64_t* dims, int R, int
     h->sms = prop.multiProcessorCount;
     h->l2_bytes = (size_t)prop.l2CacheSize;
     if (const char* ev = getenv("TR_B200_FUSED")) h->fused_mode = atoi(ev) < 0 ? -1 : (atoi(ev) > 0 ? 1 : 0);
+    if (const char* ev = getenv("TR_B200_FUSED_NS")) h->fused_ns = atoi(ev);
     if (const char* ev = getenv("TR_B200_FUSED_PACE")) h->fused_pace = atoi(ev);
     if (const char* ev = getenv("TR_B200_FUSED_PIECE")) { const int v = atoi(ev); if (v >= 16 && v % 16 == 0) h->fused_piece = v; }
     *out = h;
@@ -1404,6 +1413,7 @@ int tr_set_option(tr_handle* h, const char* name, int64_t value) {
         return TR_OK;
     }
     if (strcmp(name, "fused_pace") == 0) { h->fused_pace = (int)value; return TR_OK; }
+    if (strcmp(name, "fused_ns") == 0) { h->fused_ns = (int)value; h->occ_clusters.clear(); return TR_OK; }
     if (strcmp(name, "fused_cl") == 0) {
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
             return fail(h, TR_ERR_INVALID, "fused_cl must be 0 (auto), 1, 2, 4, 8 or 16");

@@ -16,12 +16,20 @@
 // arithmetic per element as the two-pass kernels.  t[row,:] stays in shared memory next to the sample until the
 // gradient phase has used it.
 //
+// Build option -DTRM_T_IN_TMEM (make TR_NVCC_EXTRA=-DTRM_T_IN_TMEM): t[row,:] waits in TENSOR MEMORY instead — the
+// forward thread parks it with tcgen05.st in its own TMEM lane and the gradient-B thread with the same warp % 4 and
+// lane (the only TMEM lanes a warp may touch) fetches it with tcgen05.ld, so the X stage is the only per-sample
+// shared-memory buffer and cfg 3 gets 8 stages instead of 6.  Parity-green and MEASURED SLOWER on cfg 3 (6.53 ms
+// against 6.00 ms; cfg 5: 24.1-24.6 against 25.0 ms): the tcgen05.st on the forward warps — the role that bounds the
+// pipeline — costs more than the two extra stages return (without the stores, wrong results: 5.69 ms; nine x2 stores
+// or one x16 + one x2 make no difference).  Kept as an option with its tests; the default build does not use it.
+//
 // One CLUSTER holds one sample: CTA c owns a contiguous range of rows, NS stages deep.  512 threads per CTA:
-//   warps 0-3    forward          (wait full[s]; t, u partial -> pA, arrive redA[s])
+//   warps 0-3    forward          (wait full[s]; t -> t stage, thread partials of u -> sUp, arrive redA[s])
 //   warps 4-7    gradient A       (chunks [0,QA) of every row -> A;              wait rready[s], arrive empty[s])
 //   warps 8-11   gradient B       (chunks [QA,IKC) of every row -> A, and S;     wait rready[s], arrive empty[s])
 //   warp 12      TMA producer     (cp.async.bulk of the CTA's rows of sample j into stage j % NS)
-//   warp 13      reducer          (sums the 4 warp partials, sends the CTA partial to the sample's OWNER CTA)
+//   warp 13      reducer          (sums the 128 forward threads' partials, sends the CTA partial to the sample's OWNER CTA)
 //   warp 14      epilogue         (for the samples this CTA owns, i mod CL == rank: sums the CL partials, runs the
 //                                  per-sample epilogue in fp64, broadcasts v[n,:] to every CTA of the cluster)
 // All hand-offs are mbarriers; partials and v travel through DSMEM with st.async (data + complete_tx together).
@@ -86,7 +94,9 @@ struct FusedMnCtl {
     uint64_t redA[TRM_MAX_NS];
     uint64_t rready[TRM_MAX_NS];
     uint64_t cready[TRM_QO];
-    T pA[TRM_MAX_NS][TRM_NWF][TRM_RKMAX];
+    uint64_t pfree[2];                           // the reducer is done with slot (i & 1) of the forward threads' partials
+    uint32_t tmem_base;                          // tcgen05.alloc result
+    uint32_t pad_;
     T vbuf[TRM_MAX_NS][TRM_RKMAX];               // written remotely (owner -> every CTA)
     T cpart[TRM_QO][TRM_MAX_CL][TRM_RKMAX];      // written remotely (every CTA -> owner)
     int dims[TR_MAX_MODES];
@@ -155,6 +165,140 @@ template <int RKS> struct SVec<double, RKS> {
     static __device__ __forceinline__ void st(double* p, const double (&o)[RKS]) {
 #pragma unroll
         for (int r = 0; r < RKS; ++r) p[r] = o[r];
+    }
+};
+}  // namespace trf
+
+#ifdef TRM_T_IN_TMEM
+#define TRM_TMEM 1
+#else
+#define TRM_TMEM 0
+#endif
+#define TRM_TMEM_COLS 512
+#ifndef TRM_ROTB
+#define TRM_ROTB 2                      // row rotation of gradient group B (warps) for its X part
+#endif
+#ifndef TRM_ROTA
+#define TRM_ROTA 2
+#endif
+
+namespace trf {
+// Tensor memory as per-thread scratch: shape 32x32b = thread i of the warp accesses TMEM lane (32 * (warp % 4) + i),
+// xN = N consecutive 32-bit columns.  All tcgen05 instructions are warp-wide (.sync.aligned): call them convergently.
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(TRM_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(TRM_TMEM_COLS) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& a, uint32_t& b) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
+}
+// wide variants: one instruction moves 4 / 8 / 16 consecutive columns (a tcgen05.st / ld costs about the same issue
+// time whatever its width: measured, nine x2 stores per sample cost the forward warps 15 % of their time)
+__device__ __forceinline__ void tmem_st4(uint32_t t, const uint32_t* w) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t t, const uint32_t* w) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(t), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t t, const uint32_t* w) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(t), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]),
+                   "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t t, uint32_t* w) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(t) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t t, uint32_t* w) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(t) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t t, uint32_t* w) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]),
+                   "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]) : "r"(t) : "memory");
+}
+// N (even) consecutive columns of the calling thread's lane, in as few instructions as the power-of-two widths allow
+template <int N>
+__device__ __forceinline__ void tmem_st_words(uint32_t t, const uint32_t* w) {
+    static_assert(N >= 0 && N % 2 == 0, "even word counts only");
+    if constexpr (N >= 16) { tmem_st16(t, w); tmem_st_words<N - 16>(t + 16, w + 16); }
+    else if constexpr (N >= 8) { tmem_st8(t, w); tmem_st_words<N - 8>(t + 8, w + 8); }
+    else if constexpr (N >= 4) { tmem_st4(t, w); tmem_st_words<N - 4>(t + 4, w + 4); }
+    else if constexpr (N >= 2) { tmem_st2(t, w[0], w[1]); }
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_words(uint32_t t, uint32_t* w) {
+    static_assert(N >= 0 && N % 2 == 0, "even word counts only");
+    if constexpr (N >= 16) { tmem_ld16(t, w); tmem_ld_words<N - 16>(t + 16, w + 16); }
+    else if constexpr (N >= 8) { tmem_ld8(t, w); tmem_ld_words<N - 8>(t + 8, w + 8); }
+    else if constexpr (N >= 4) { tmem_ld4(t, w); tmem_ld_words<N - 4>(t + 4, w + 4); }
+    else if constexpr (N >= 2) { tmem_ld2(t, w[0], w[1]); }
+}
+__device__ __forceinline__ void tmem_tie(uint32_t& x) { asm volatile("" : "+r"(x)); }
+// bit casts between NV values of T and 32-bit words
+template <int NV> __device__ __forceinline__ void to_words(const float (&v)[NV], uint32_t (&w)[NV]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) w[i] = __float_as_uint(v[i]);
+}
+template <int NV> __device__ __forceinline__ void to_words(const double (&v)[NV], uint32_t (&w)[2 * NV]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const long long b = __double_as_longlong(v[i]);
+        w[2 * i] = (uint32_t)b; w[2 * i + 1] = (uint32_t)(b >> 32);
+    }
+}
+__device__ __forceinline__ float from_words(const uint32_t* w, float) { return __uint_as_float(w[0]); }
+__device__ __forceinline__ double from_words(const uint32_t* w, double) {
+    return __longlong_as_double((long long)(((unsigned long long)w[1] << 32) | w[0]));
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers written by tcgen05.ld are defined only after tcgen05.wait::ld: re-defining them in an (empty) volatile asm
+// placed after the wait keeps the compiler from scheduling a consumer above it
+__device__ __forceinline__ void tmem_tie(float& x) { asm volatile("" : "+f"(x)); }
+__device__ __forceinline__ void tmem_tie(double& x) { asm volatile("" : "+d"(x)); }
+__device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// RKS values of T <-> consecutive TMEM columns of the calling thread's lane (RKS even; a double takes two columns)
+template <typename T, int RKS> struct TVec;
+template <int RKS> struct TVec<float, RKS> {
+    static constexpr int COLS = RKS;
+    static __device__ __forceinline__ void st(uint32_t taddr, const float (&o)[RKS]) {
+#pragma unroll
+        for (int r = 0; r < RKS; r += 2) tmem_st2(taddr + r, __float_as_uint(o[r]), __float_as_uint(o[r + 1]));
+    }
+    static __device__ __forceinline__ void ld(uint32_t taddr, float (&o)[RKS]) {
+#pragma unroll
+        for (int r = 0; r < RKS; r += 2) {
+            uint32_t a, b;
+            tmem_ld2(taddr + r, a, b);
+            o[r] = __uint_as_float(a); o[r + 1] = __uint_as_float(b);
+        }
+    }
+};
+template <int RKS> struct TVec<double, RKS> {
+    static constexpr int COLS = 2 * RKS;
+    static __device__ __forceinline__ void st(uint32_t taddr, const double (&o)[RKS]) {
+#pragma unroll
+        for (int r = 0; r < RKS; ++r) {
+            const long long b = __double_as_longlong(o[r]);
+            tmem_st2(taddr + 2 * r, (uint32_t)b, (uint32_t)(b >> 32));
+        }
+    }
+    static __device__ __forceinline__ void ld(uint32_t taddr, double (&o)[RKS]) {
+#pragma unroll
+        for (int r = 0; r < RKS; ++r) {
+            uint32_t a, b;
+            tmem_ld2(taddr + 2 * r, a, b);
+            o[r] = __longlong_as_double((long long)(((unsigned long long)b << 32) | a));
+        }
     }
 };
 }  // namespace trf
@@ -237,12 +381,37 @@ __device__ __forceinline__ void trm_epilogue_tail(const EpiMnArgs<T>& a, long lo
     }
 }
 
+// S[row,r] += v[r] t[row,r] over the rows of the FORWARD thread that shares this thread's TMEM lane (threadIdx & 127 +
+// j * 128; njs row iterations, warp-uniform), whatever rotation the X part of the gradient group uses
+template <typename T, int RKS, int NJS>
+__device__ __forceinline__ void trm_s_rows(T (&S)[TRM_GMAX][RKS], const T (&v)[RKS], uint32_t tt) {
+#if TRM_TMEM
+    constexpr int WPT = (int)sizeof(T) / 4;
+    uint32_t w[NJS * RKS * WPT];
+    trf::tmem_ld_words<NJS * RKS * WPT>(tt, w);
+    trf::tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < NJS * RKS * WPT; ++i) trf::tmem_tie(w[i]);
+#pragma unroll
+    for (int j = 0; j < NJS; ++j)
+#pragma unroll
+        for (int r = 0; r < RKS; ++r) S[j][r] = tr_fma<T>(v[r], trf::from_words(&w[(j * RKS + r) * WPT], (T)0), S[j][r]);
+#endif
+}
+template <typename T, int RKS>
+__device__ __forceinline__ void trm_s_only(T (&S)[TRM_GMAX][RKS], const T (&v)[RKS], uint32_t tt, int njs) {
+    static_assert(TRM_GMAX == 3, "row iterations are dispatched explicitly");
+    if (njs == 3) trm_s_rows<T, RKS, 3>(S, v, tt);
+    else if (njs == 2) trm_s_rows<T, RKS, 2>(S, v, tt);
+    else if (njs == 1) trm_s_rows<T, RKS, 1>(S, v, tt);
+}
+
 // One gradient group: chunks [Q0, Q0 + QN) of every row of this CTA (and the row sums S when WITH_S).
 // One sample of the forward role for a warp with NJ row iterations (rows tid + j * TRM_NFT): t[row,:] to shared memory,
 // the lane's partial of u[n,:] in vals.  Branch-free like trm_gradient_sample.
 template <typename T, int IKC, int RKS, int NJ>
 __device__ __forceinline__ void trm_forward_sample(T (&vals)[TRM_RKMAX], const T* cF3, const T (&f12)[TRM_GMAX][RKS], const T* xs,
-                                                   T* ts, int tid, int nrows, const int (&rlc)[TRM_GMAX], bool store_t) {
+                                                   T* ts, uint32_t tt, int tid, int nrows, const int (&rlc)[TRM_GMAX], bool store_t) {
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int IK = IKC * VEC;
     T t[NJ][RKS];
@@ -267,10 +436,27 @@ __device__ __forceinline__ void trm_forward_sample(T (&vals)[TRM_RKMAX], const T
     }
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
+#if !TRM_TMEM
         if (tid + j * TRM_NFT < nrows && store_t) trf::SVec<T, RKS>::st(ts + (size_t)(tid + j * TRM_NFT) * RKS, t[j]);
+#endif
 #pragma unroll
         for (int r = 0; r < RKS; ++r) vals[r] = tr_fma<T>(t[j][r], f12[j][r], vals[r]);     // f12 = 0 past nrows
     }
+#if TRM_TMEM
+    {
+        // t of the thread's NJ rows -> NJ * RKS consecutive TMEM columns of its lane, in one or two wide stores; every
+        // lane stores (warp-wide instruction), rows past nrows are never read back
+        constexpr int WPT = (int)sizeof(T) / 4;
+        T flat[NJ * RKS];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int r = 0; r < RKS; ++r) flat[j * RKS + r] = t[j][r];
+        uint32_t w[NJ * RKS * WPT];
+        trf::to_words<NJ * RKS>(flat, w);
+        trf::tmem_st_words<NJ * RKS * WPT>(tt, w);
+    }
+#endif
 }
 
 // One sample of a gradient group for a warp with NJ row iterations.  No branches: lanes whose row of iteration j lies
@@ -279,8 +465,8 @@ __device__ __forceinline__ void trm_forward_sample(T (&vals)[TRM_RKMAX], const T
 // hides the LDS latency).
 template <typename T, int IKC, int RKS, int Q0, int QN, bool WITH_S, int NJ>
 __device__ __forceinline__ void trm_gradient_sample(T (&acc)[QN * (16 / (int)sizeof(T))][RKS], T (&S)[WITH_S ? TRM_GMAX : 1][RKS],
-                                                    const T (&v)[RKS], const T* sF12, const T* xs, const T* ts, int tb,
-                                                    const int (&rlc)[TRM_GMAX]) {
+                                                    const T (&v)[RKS], const T* sF12, const T* xs, const T* ts, uint32_t tt, int tb,
+                                                    const int (&rlc)[TRM_GMAX], int njs) {
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int IK = IKC * VEC;
     T c[NJ][RKS];
@@ -290,15 +476,19 @@ __device__ __forceinline__ void trm_gradient_sample(T (&acc)[QN * (16 / (int)siz
 #pragma unroll
         for (int r = 0; r < RKS; ++r) c[j][r] *= v[r];
     }
+#if TRM_TMEM
+
+#else
     if (WITH_S) {
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            T tt[RKS];
-            trf::SVec<T, RKS>::ld(ts + (size_t)rlc[j] * RKS, tt);
+            T tv[RKS];
+            trf::SVec<T, RKS>::ld(ts + (size_t)rlc[j] * RKS, tv);
 #pragma unroll
-            for (int r = 0; r < RKS; ++r) S[j][r] = tr_fma<T>(v[r], tt[r], S[j][r]);
+            for (int r = 0; r < RKS; ++r) S[j][r] = tr_fma<T>(v[r], tv[r], S[j][r]);
         }
     }
+#endif
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
 #pragma unroll
@@ -309,6 +499,12 @@ __device__ __forceinline__ void trm_gradient_sample(T (&acc)[QN * (16 / (int)siz
             for (int vv = 0; vv < VEC; ++vv) trf::fma_row(acc[qq * VEC + vv], x[vv], c[j]);
         }
     }
+#if TRM_TMEM
+    // S runs over the rows of the FORWARD thread with this thread's TMEM lane (threadIdx & 127 + j * 128; njs row
+    // iterations, warp-uniform), whatever rotation the X part above uses: t[row,:] comes from that lane with
+    // tcgen05.ld.  After the X loop, when the registers of c and x are free again.
+    if constexpr (WITH_S) trm_s_only<T, RKS>(S, v, tt, njs);
+#endif
 }
 
 // ROT rotates the thread -> row assignment by ROT warps: with nrows between 2 and 3 rows per thread the first warps of
@@ -321,6 +517,8 @@ __device__ __forceinline__ void trm_gradient_role(const FusedMnArgs<T>& a, Fused
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int IK = IKC * VEC;
     const int lane = threadIdx.x & 31;
+    // TMEM address of this thread's lane quarter (lanes 32 * (warp % 4) ..): bits 31..16 lane, 15..0 column
+    const uint32_t tmem_lane = ctl->tmem_base + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16);
     const int gw = (threadIdx.x & (TRM_NCT - 1)) >> 5;                          // physical warp of the role: flush slot
     const int tb = (threadIdx.x + ROT * 32) & (TRM_NCT - 1);                    // role-relative thread id for the row assignment
     const int NS = a.NS;
@@ -341,6 +539,11 @@ __device__ __forceinline__ void trm_gradient_role(const FusedMnArgs<T>& a, Fused
     int nj = 0;
 #pragma unroll
     for (int j = 0; j < TRM_GMAX; ++j) nj += ((tb & ~31) + j * TRM_NCT < nrows) ? 1 : 0;
+    // rows of the S sums: with t in TMEM those of the forward thread that shares this thread's TMEM lane
+    const int ts_id = TRM_TMEM ? (int)(threadIdx.x & (TRM_NCT - 1)) : tb;
+    int njs = 0;
+#pragma unroll
+    for (int j = 0; j < TRM_GMAX; ++j) njs += ((ts_id & ~31) + j * TRM_NCT < nrows) ? 1 : 0;
     int s = 0;
     unsigned ph = 0;
     int left = (int)(a.spc < cnt ? a.spc : cnt);
@@ -349,6 +552,12 @@ __device__ __forceinline__ void trm_gradient_role(const FusedMnArgs<T>& a, Fused
         trf::mbar_wait(&ctl->rready[s], ph);                       // v[n,:] of this sample arrived (all lanes wait)
         if (WITH_S) trf::mbar_wait(&ctl->redA[s], ph);             // acquire the forward warps' t[row,:] stores
         __syncwarp();
+#if TRM_TMEM
+        if (WITH_S) trf::tmem_fence_after();
+        const uint32_t tt = tmem_lane + (uint32_t)(s * TRM_GMAX) * trf::TVec<T, RKS>::COLS;
+#else
+        const uint32_t tt = 0;
+#endif
         if (tb == 0) TRM_STAMP(WITH_S ? 10 : 8, i);
         T v[RKS];
         trf::SVec<T, RKS>::ld(&ctl->vbuf[s][0], v);
@@ -359,12 +568,16 @@ __device__ __forceinline__ void trm_gradient_role(const FusedMnArgs<T>& a, Fused
         // sample can be issued ahead of the FMAs (one warp per role and sub-partition: nothing else hides LDS latency).
         // row iterations this WARP really has (warp-uniform): a warp whose rows of iteration j all lie past nrows skips it
         if (!TRM_DBG(1)) {
-            if (nj == 3) trm_gradient_sample<T, IKC, RKS, Q0, QN, WITH_S, 3>(acc, S, v, sF12, xs, ts, tb, rlc);
-            else if (nj == 2) trm_gradient_sample<T, IKC, RKS, Q0, QN, WITH_S, 2>(acc, S, v, sF12, xs, ts, tb, rlc);
-            else if (nj == 1) trm_gradient_sample<T, IKC, RKS, Q0, QN, WITH_S, 1>(acc, S, v, sF12, xs, ts, tb, rlc);
+            if (nj == 3) trm_gradient_sample<T, IKC, RKS, Q0, QN, WITH_S, 3>(acc, S, v, sF12, xs, ts, tt, tb, rlc, njs);
+            else if (nj == 2) trm_gradient_sample<T, IKC, RKS, Q0, QN, WITH_S, 2>(acc, S, v, sF12, xs, ts, tt, tb, rlc, njs);
+            else if (nj == 1) trm_gradient_sample<T, IKC, RKS, Q0, QN, WITH_S, 1>(acc, S, v, sF12, xs, ts, tt, tb, rlc, njs);
+            else if constexpr (WITH_S) { if (njs > 0) trm_s_only<T, RKS>(S, v, tt, njs); }
         }
         __syncwarp();
         if (tb == 0) TRM_STAMP(WITH_S ? 11 : 9, i);
+#if TRM_TMEM
+        if (WITH_S) trf::tmem_fence_before();                      // the TMEM reads above are ordered before the stage's release
+#endif
         if (lane == 0) trf::mbar_arrive(&ctl->empty[s]);           // this warp's reads of the stage are done
         if (++s == NS) { s = 0; ph ^= 1u; }
         if (--left == 0) {
@@ -385,7 +598,7 @@ __device__ __forceinline__ void trm_gradient_role(const FusedMnArgs<T>& a, Fused
                 T* sp = a.Spart + slot * (size_t)RKS * a.NR;
 #pragma unroll
                 for (int j = 0; j < TRM_GMAX; ++j) {
-                    const int rl = tb + j * TRM_NCT;
+                    const int rl = ts_id + j * TRM_NCT;
                     if (rl < nrows) {
 #pragma unroll
                         for (int r = 0; r < RKS; ++r) {
@@ -424,6 +637,8 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
     off = (off + 15) / 16 * 16;
     T* sFCw = reinterpret_cast<T*>(trm_smem + off);                 // (C, RKS): w_r * FC[c,r], zero-padded channels
     T* sCW = sFCw + (size_t)C * RKS;                                // (C): class weights omega[c]
+    // (2, 128, RKS): the forward threads' partials of u[n,:] of samples i and i+1 (summed by the reducer warp)
+    T* sUp = reinterpret_cast<T*>(trm_smem + (off + (size_t)C * (RKS + 1) * sizeof(T) + 15) / 16 * 16);
     const unsigned char* stageX0 = trm_smem + a.head_bytes;
     const unsigned char* stageT0 = stageX0 + (size_t)NS * a.stage_x_bytes;
 #ifdef TRM_TRACE
@@ -468,9 +683,19 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
             trf::mbar_init(&ctl->rready[s], 1);
         }
         for (int q = 0; q < TRM_QO; ++q) trf::mbar_init(&ctl->cready[q], 1);
+        trf::mbar_init(&ctl->pfree[0], 1);
+        trf::mbar_init(&ctl->pfree[1], 1);
         trf::fence_mbar_init();
     }
+#if TRM_TMEM
+    static_assert(TRM_MAX_NS * TRM_GMAX * TRM_RKMAX * (int)(sizeof(T) / 4) <= TRM_TMEM_COLS, "t does not fit the TMEM columns");
+    if (warp == TRM_NT / 32 - 1) trf::tmem_alloc(&ctl->tmem_base);      // one warp allocates (1 CTA per SM: never contended)
+    trf::tmem_fence_before();
+#endif
     __syncthreads();
+#if TRM_TMEM
+    trf::tmem_fence_after();
+#endif
     trf::cluster_arrive();
     trf::cluster_wait();
 
@@ -496,30 +721,48 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
         unsigned ph = 0;
         for (int i = 0; i < cnt; ++i) {
             trf::mbar_wait(&ctl->full[s], ph);                     // every lane waits on the barrier itself (tr_fused.cuh)
+            // slot i & 1 of the partial buffer was last used by sample i - 2: its use number is (i >> 1) - 1
+            if (i >= 2) trf::mbar_wait(&ctl->pfree[i & 1], (unsigned)(((i >> 1) - 1) & 1));
             __syncwarp();
             if (tid == 0) TRM_STAMP(1, i);
             const T* xs = reinterpret_cast<const T*>(stageX0 + (size_t)s * a.stage_x_bytes);
             T* ts = reinterpret_cast<T*>(const_cast<unsigned char*>(stageT0) + (size_t)s * a.stage_t_bytes);
+#if TRM_TMEM
+            const uint32_t tt = ctl->tmem_base + ((uint32_t)(fw * 32) << 16) + (uint32_t)(s * TRM_GMAX) * trf::TVec<T, RKS>::COLS;
+#else
+            const uint32_t tt = 0;
+#endif
             T vals[TRM_RKMAX];
 #pragma unroll
             for (int r = 0; r < TRM_RKMAX; ++r) vals[r] = (T)0;
             if (!TRM_DBG(2)) {
-                if (nj == 3) trm_forward_sample<T, IKC, RKS, 3>(vals, cF3, f12, xs, ts, tid, nrows, rlc, !TRM_DBG(16));
-                else if (nj == 2) trm_forward_sample<T, IKC, RKS, 2>(vals, cF3, f12, xs, ts, tid, nrows, rlc, !TRM_DBG(16));
-                else if (nj == 1) trm_forward_sample<T, IKC, RKS, 1>(vals, cF3, f12, xs, ts, tid, nrows, rlc, !TRM_DBG(16));
+                if (nj == 3) trm_forward_sample<T, IKC, RKS, 3>(vals, cF3, f12, xs, ts, tt, tid, nrows, rlc, !TRM_DBG(16));
+                else if (nj == 2) trm_forward_sample<T, IKC, RKS, 2>(vals, cF3, f12, xs, ts, tt, tid, nrows, rlc, !TRM_DBG(16));
+                else if (nj == 1) trm_forward_sample<T, IKC, RKS, 1>(vals, cF3, f12, xs, ts, tt, tid, nrows, rlc, !TRM_DBG(16));
             }
             if (tid == 0) TRM_STAMP(13, i);
-            warp_reduce_transpose<T, TRM_RKMAX, 0>(vals, lane);   // lane l: total of channel l >> 2
-            if ((lane & 3) == 0) ctl->pA[s][fw][lane >> 2] = vals[0];
+            // the thread's partial of u[n,:] goes to shared memory as it is: the cross-thread sum is the reducer warp's
+            // job (a shuffle reduction here would sit on the forward warps, the busiest role of the pipeline)
+            {
+                T pv[RKS];
+#pragma unroll
+                for (int r = 0; r < RKS; ++r) pv[r] = vals[r];
+                trf::SVec<T, RKS>::st(sUp + ((size_t)(i & 1) * TRM_NFT + tid) * RKS, pv);
+            }
+#if TRM_TMEM
+            trf::tmem_wait_st();                                   // t is in TMEM ...
+            trf::tmem_fence_before();                              // ... and ordered before the arrival below
+#endif
             __syncwarp();
             if (tid == 0) TRM_STAMP(2, i);
             if (lane == 0) trf::mbar_arrive(&ctl->redA[s]);
             if (++s == NS) { s = 0; ph ^= 1u; }
         }
     } else if (warp < 4 + TRM_NWG) {
-        trm_gradient_role<T, IKC, RKS, 0, QA, false, 2>(a, ctl, sF12, stageX0, stageT0, cnt, cid, crank, nrows, row0, strace);
+        trm_gradient_role<T, IKC, RKS, 0, QA, false, TRM_ROTA>(a, ctl, sF12, stageX0, stageT0, cnt, cid, crank, nrows, row0, strace);
     } else if (warp < 4 + 2 * TRM_NWG) {
-        trm_gradient_role<T, IKC, RKS, QA, IKC - QA, true, 2>(a, ctl, sF12, stageX0, stageT0, cnt, cid, crank, nrows, row0, strace);
+        // group B: X part on rotated rows like group A; its S sums run over the rows of the forward thread it shares TMEM lanes with
+        trm_gradient_role<T, IKC, RKS, QA, IKC - QA, true, TRM_ROTB>(a, ctl, sF12, stageX0, stageT0, cnt, cid, crank, nrows, row0, strace);
     } else if (warp == 4 + 2 * TRM_NWG) {
         // ================================== TMA producer ==================================
         if (lane == 0) {
@@ -552,14 +795,27 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
             // the previous use of rready[s] (sample i - NS) has completed: its gradient phase released the stage
             // before this sample could be loaded.  Arm it for v[n,:] of this sample.
             if (lane == 0) trf::mbar_arrive_expect_tx(&ctl->rready[s], (unsigned)(RKS * sizeof(T)));
-            if (lane < RKS) {
-                T pc = (T)0;
+            {
+                // lane l sums the partials of forward threads l, l + 32, l + 64, l + 96 (fixed order), then a transposed
+                // butterfly leaves the total of channel c in lane 4 c
+                T pc[TRM_RKMAX];
 #pragma unroll
-                for (int w4 = 0; w4 < TRM_NWF; ++w4) pc += ctl->pA[s][w4][lane];          // fixed order
-                trf::st_async_val(trf::mapa(trf::smem_u32(&ctl->cpart[slot][crank][lane]), (unsigned)owner), pc,
-                                  trf::mapa(trf::smem_u32(&ctl->cready[slot]), (unsigned)owner));
+                for (int r = 0; r < TRM_RKMAX; ++r) pc[r] = (T)0;
+                const T* up = sUp + ((size_t)(i & 1) * TRM_NFT + lane) * RKS;
+#pragma unroll
+                for (int w4 = 0; w4 < TRM_NWF; ++w4) {
+                    T pv[RKS];
+                    trf::SVec<T, RKS>::ld(up + (size_t)w4 * 32 * RKS, pv);
+#pragma unroll
+                    for (int r = 0; r < RKS; ++r) pc[r] += pv[r];
+                }
+                warp_reduce_transpose<T, TRM_RKMAX, 0>(pc, lane);
+                if ((lane & 3) == 0 && (lane >> 2) < RKS)
+                    trf::st_async_val(trf::mapa(trf::smem_u32(&ctl->cpart[slot][crank][lane >> 2]), (unsigned)owner), pc[0],
+                                      trf::mapa(trf::smem_u32(&ctl->cready[slot]), (unsigned)owner));
             }
             __syncwarp();
+            if (lane == 0) trf::mbar_arrive(&ctl->pfree[i & 1]);        // the partial slot may be rewritten (sample i + 2)
             if (++s == NS) { s = 0; ph ^= 1u; }
             if (++owner == CL) { owner = 0; if (++slot == TRM_QO) slot = 0; }
         }
@@ -627,10 +883,31 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
         loss = warp_sum(loss);
         if (lane == 0) a.losspart[(size_t)cid * CL + crank] = loss;
     }
+#ifdef TRM_TRACE
+    else if (warp == 4 + 2 * TRM_NWG + 3) {
+        // trace builds only: an observer on the otherwise idle warp 15 stamps the moment a sample's bytes have landed
+        if (lane == 0) {
+            int s = 0;
+            unsigned ph = 0;
+            for (int i = 0; i < cnt; ++i) {
+                trf::mbar_wait(&ctl->full[s], ph);
+                TRM_STAMP(14, i);
+                if (++s == NS) { s = 0; ph ^= 1u; }
+            }
+        }
+    }
+#endif
     // no CTA may exit while a peer can still write into its shared memory
     __syncwarp();
+#if TRM_TMEM
+    trf::tmem_fence_before();
+#endif
     trf::cluster_arrive();
     trf::cluster_wait();
+#if TRM_TMEM
+    trf::tmem_fence_after();
+    if (warp == TRM_NT / 32 - 1) trf::tmem_dealloc(ctl->tmem_base);     // every thread of the cluster is past its last TMEM access
+#endif
 #ifdef TRM_TRACE
     __syncthreads();
     if (a.trace && cid == 0 && crank == 0)

@@ -50,6 +50,7 @@ for i in range(NS):
 d = lambda a, b: np.median((t[:, b] - t[:, a])[(t[:, a] > 0) & (t[:, b] > 0)])  # noqa: E731
 print('median cycles: tma->fwd0 %d | fwd %d | fwd1->red %d | red->gA0 %d | gradA %d | gradB %d | tma->gB1 (stage residency) %d'
       % (d(0, 1), d(1, 2), d(2, 3), d(3, 8), d(8, 9), d(10, 11), d(0, 11)))
+print('TMA issue -> bytes landed (observer warp) %d | landed -> forward start %d' % (d(0, 14), d(14, 1)))
 print('forward: compute %d | warp reduce + pA %d' % (d(1, 13), d(13, 2)))
 own = t[:, 5] > 0
 if own.any():
