@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define TR_B200_VERSION 200
+#define TR_B200_VERSION 210
 
 enum { TR_F32 = 0, TR_F64 = 1 };
 enum { TR_OK = 0, TR_ERR_INVALID = 1, TR_ERR_CUDA = 2, TR_ERR_UNSUPPORTED = 3, TR_ERR_NOMEM = 4 };
@@ -111,6 +111,40 @@ int tr_backward_std(tr_handle* h, const void* X, const void* dyhat, int64_t N, c
  * gradients incl. the class factor.  gradsum = [ dFt | 0 ]. */
 int tr_backward_mn(tr_handle* h, const void* X, const void* dP, int64_t N, const void* theta, const void* w,
                    uint32_t nn_mask, double sp_beta, double sp_thr, double* gradsum, void* stream);
+
+/* ---- spectral_tensor_regression.py: X (T, W, D), y (T, n_out) ---------------------------------
+ * The model of that file's fit / fit_Adam closures (spectral:573-586 / 727-731):
+ *     yhat = lin_model(X, Bcp_n, weights[:rank_normal], ...) + stepwise_spectral_model(X, Bcp_c, ...)
+ * lin_model (spectral:118-165) is the standard CP model with n_out outputs; stepwise_spectral_model
+ * (spectral:339-390) contracts the window axis with a (W, rank_spectral, complex_dim) factor, takes the NORM over
+ * the complex axis, then contracts D and maps to the outputs.  Loss = MSE over (T, n_out) (spectral:581).
+ *
+ * Parameter vector (the reference's optimizer parameter list Bcp_n + Bcp_c + [bias], laid end to end, row-major):
+ *     theta = [ Fn0 (W,Rn) | Fn1 (D,Rn) | Fn2 (n_out,Rn) | Fc0 (W,Rs,CC) | Fc1 (D,Rs) | Fc2 (n_out,Rs) | bias (n_out) ]
+ * P = Pf + n_out.  nn_mask bit i (i < 6) = softplus on the i-th block (the reference applies non_negative[m] to
+ * block m of both lists: bits m and m + 3).  w = rank weights (Rn + Rs values; only the first Rn are used, as in the
+ * reference).  gradsum = [ dFt (Pf) | nb * sum_t res[t,n] (n_out) | sum res^2 ]  (P + 1 doubles; nb = number of
+ * non-empty parts, because both parts add the bias), to be summed across GPUs and passed to tr_finish_grad with
+ * grad_scale = 2 / (T_total * n_out), loss_scale = 1 / (T_total * n_out).  tr_param_count, tr_gradsum_count,
+ * tr_finish_grad, tr_adam_step, tr_lbfgs_*, tr_allreduce, tr_destroy work on these handles as on the others. */
+int tr_spec_create(tr_handle** out, int dtype, int64_t W, int64_t D, int64_t n_out, int rank_normal,
+                   int rank_spectral, int complex_dim, int device);
+
+/* One closure evaluation without penalty and normalisation (spectral:573-586): two streaming passes over X.
+ * y: (N, n_out) of dtype; yhat (N, n_out) may be NULL. */
+int tr_spec_fwd_grad(tr_handle* h, const void* X, const void* y, int64_t N, const void* theta, const void* w,
+                     uint32_t nn_mask, double sp_beta, double sp_thr, double* gradsum, void* yhat, void* stream);
+
+/* Forward only; every output may be NULL:
+ *   yhat     (N, n_out)  the model of the fit closures (above)
+ *   yhat_lin (N, n_out)  lin_model alone, bias once                               (spectral:118-165)
+ *   spec_pred (N, n_out) spectral_model (spectral:168-221): sqrt(sum_c z_c^2) + bias with z_c the complete CP
+ *                        contraction of X with the c-th complex slice of Fc0 (rank weights w[Rn:] applied) — what the
+ *                        reference's predict adds to lin_model (spectral:960-961); NOT the model of the fit
+ *   latents  (N, Rn)     stepwise_latents_model: s_n without rank weights          (spectral:284-337, predict_latents) */
+int tr_spec_forward(tr_handle* h, const void* X, int64_t N, const void* theta, const void* w, uint32_t nn_mask,
+                    double sp_beta, double sp_thr, void* yhat, void* yhat_lin, void* spec_pred, void* latents,
+                    void* stream);
 
 /* gradsum (after the cross-GPU sum, if any) -> gradient wrt the RAW parameters and the losses:
  *   grad[F_m] = grad_scale * dFt_m * softplus'(F_m) + lambda_L2 * F_m / ||F_m||_F   (L2_penalty, std:180-196)

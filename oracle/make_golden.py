@@ -150,7 +150,82 @@ def gen_hier(HTR):
     print('wrote', name, 'final loss', out['adam_loss_running'][-1])
 
 
+SPEC_CASES = [
+    # name, T, W, D, n_out, rank_normal, rank_spectral, n_complex_dim, dtype, non_negative, weights, lambda, seed
+    ('spec_f32', 48, 10, 12, 3, 2, 2, 1, torch.float32, [False, False, False], None, 0.01, 31),
+    ('spec_f64_nn', 40, 9, 8, 2, 1, 3, 2, torch.float64, [True, False, False], [0.7, 1.0, 1.0, 1.0], 0.02, 32),
+    ('spec_only_f64', 36, 7, 5, 4, 0, 2, 1, torch.float64, [False, False, False], None, 0.01, 33),
+    ('spec_normal_only_f32', 40, 8, 16, 2, 3, 0, 0, torch.float32, [False, True, False], [1.0, 0.5, 2.0], 0.01, 34),
+]
+
+
+def gen_spec(SPR):
+    """spectral_tensor_regression.py: one closure evaluation with the module-level functions, fit_Adam, fit (fp64),
+    predict / predict_latents through the reference's estimator class."""
+    from . import tr_oracle_spectral as OS
+    for name, T, W, D, NO, rn, rs, ncd, dtype, nn, w, lam, seed in SPEC_CASES:
+        cc = ncd + 1
+        X, y = OS.synth(T, W, D, NO, max(rn, 1), max(rs, 1), cc, 1234 + seed, dtype=dtype)
+        Bn0, Bc0 = OS.init(W, D, NO, rn, rs, cc, dtype=dtype, seed=321 + seed)
+        weights = torch.ones(rn + rs, dtype=dtype) if w is None else torch.tensor(w, dtype=dtype)
+        Bn = [b.clone().requires_grad_(True) for b in Bn0]
+        Bc = [b.clone().requires_grad_(True) for b in Bc0]
+        bias = torch.zeros(NO, dtype=dtype, requires_grad=True)
+        y_hat = SPR.lin_model(X, Bn, weights[:rn], nn, bias) + SPR.stepwise_spectral_model(X, Bc, weights[rn:], nn, bias)
+        mse = torch.nn.MSELoss()(y_hat, y)
+        loss = mse + lam * (SPR.L2_penalty(Bn) + SPR.L2_penalty(Bc))
+        loss.backward()
+        out = {'X': X.numpy(), 'y': y.numpy(), 'weights': weights.numpy(), 'non_negative': np.array(nn), 'lambda_L2': lam,
+               'rank_normal': rn, 'rank_spectral': rs, 'n_complex_dim': ncd,
+               'y_hat': y_hat.detach().numpy(), 'loss_data': mse.item(), 'loss': loss.item(), 'dbias': bias.grad.numpy()}
+        for i in range(3):
+            out[f'Bn_init_{i}'] = Bn0[i].numpy()
+            out[f'Bc_init_{i}'] = Bc0[i].numpy()
+            out[f'grad_n_{i}'] = (Bn[i].grad if Bn[i].grad is not None else torch.zeros_like(Bn[i])).numpy()
+            out[f'grad_c_{i}'] = (Bc[i].grad if Bc[i].grad is not None else torch.zeros_like(Bc[i])).numpy()
+
+        def fresh():
+            return SPR.CP_linear_regression(X.shape, y.shape, dtype=dtype, rank_normal=rn, rank_spectral=rs,
+                                            non_negative=nn, weights=None if w is None else np.array(w),
+                                            Bcp_init=[[b.clone().requires_grad_(True) for b in Bn0],
+                                                      [b.clone().requires_grad_(True) for b in Bc0]],
+                                            n_complex_dim=ncd, device='cpu')
+        m = fresh()
+        m.fit_Adam(X, y, lambda_L2=lam, max_iter=20, tol=1e-50, patience=100, verbose=False, Adam_kwargs=ADAM)
+        out['adam_loss_running'] = np.array(m.loss_running)
+        out['adam_bias'] = m.bias.detach().numpy()
+        for i in range(3):
+            out[f'adam_Bn_{i}'] = m.Bcp_n[i].detach().numpy()
+            out[f'adam_Bc_{i}'] = m.Bcp_c[i].detach().numpy()
+        # the reference's predict adds spectral_model's (T, rank_spectral) output to the (T, n_out) normal part:
+        # only defined when torch can broadcast the two (stored when it can)
+        try:
+            out['adam_predict'] = m.predict(X).numpy()
+        except RuntimeError:
+            pass
+        if rn > 0:
+            out['adam_latents'] = np.asarray(m.predict_latents(X))
+        if dtype == torch.float64:
+            m2 = fresh()
+            conv = m2.fit(X, y, lambda_L2=lam, max_iter=6, tol=1e-50, patience=10, verbose=False,
+                          running_loss_logging_interval=1, LBFGS_kwargs=LBFGS)
+            out['lbfgs_loss_running'] = np.array(m2.loss_running)
+            out['lbfgs_bias'] = m2.bias.detach().numpy()
+            out['lbfgs_converged'] = conv
+            for i in range(3):
+                out[f'lbfgs_Bn_{i}'] = m2.Bcp_n[i].detach().numpy()
+                out[f'lbfgs_Bc_{i}'] = m2.Bcp_c[i].detach().numpy()
+        np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+        print('wrote', name, 'loss', out['loss'], 'adam', out['adam_loss_running'][[0, -1]])
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'spec':        # only the spectral fixtures (the others stay as committed)
+        if not ref_loader.available():
+            sys.exit('reference not found at ' + ref_loader.REFERENCE_DIR)
+        torch.set_num_threads(1)
+        gen_spec(ref_loader.spectral())
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'hier':        # only the hierarchical fixture (the others stay as committed)
         if not ref_loader.available():
             sys.exit('reference not found at ' + ref_loader.REFERENCE_DIR)
@@ -164,6 +239,7 @@ def main():
     gen_std(ref_loader.standard())
     gen_mn(ref_loader.multinomial())
     gen_hier(ref_loader.hierarchical())
+    gen_spec(ref_loader.spectral())
 
 
 if __name__ == '__main__':

@@ -44,3 +44,9 @@ def hierarchical():
     if 'hier' not in _cache:
         _cache['hier'] = _load('multinomial_tensor_regression_hierarchical')
     return _cache['hier']
+
+
+def spectral():
+    if 'spec' not in _cache:
+        _cache['spec'] = _load('spectral_tensor_regression')
+    return _cache['spec']

@@ -15,6 +15,7 @@ SYMBOLS = [
     'tr_profile_read', 'tr_set_option', 'tr_lbfgs_direction', 'tr_lbfgs_point', 'tr_lbfgs_gtd',
     'tr_adam_step_groups', 'tr_allreduce', 'tr_comm_unique_id', 'tr_comm_create', 'tr_comm_destroy',
     'tr_upload', 'tr_upload_stats', 'tr_host_last_error',
+    'tr_spec_create', 'tr_spec_fwd_grad', 'tr_spec_forward',
 ]
 
 
@@ -62,6 +63,9 @@ def _load():
     lib.tr_lbfgs_direction.argtypes = [vp, vp, vp, vp, dbl, i32, vp, vp, vp, i32, vp, vp]
     lib.tr_lbfgs_point.argtypes = [vp, vp, vp, dbl, vp, vp]
     lib.tr_lbfgs_gtd.argtypes = [vp, vp, vp, vp, vp]
+    lib.tr_spec_create.argtypes = [ctypes.POINTER(vp), i32, i64, i64, i64, i32, i32, i32, i32]
+    lib.tr_spec_fwd_grad.argtypes = [vp, vp, vp, i64, vp, vp, u32, dbl, dbl, vp, vp, vp]
+    lib.tr_spec_forward.argtypes = [vp, vp, i64, vp, vp, u32, dbl, dbl, vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ('tr_last_error', 'tr_host_last_error'):

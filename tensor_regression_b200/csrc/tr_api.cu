@@ -14,6 +14,7 @@
 #include "tr_kernels.cuh"
 #include "tr_dispatch.h"
 #include "tr_small.cuh"
+#include "tr_spectral.cuh"
 #include "tr_fused.cuh"
 #include "tr_fused_mn.h"
 
@@ -109,7 +110,14 @@ struct tr_handle {
     Buf trace;                          // debug timeline of k_fused_mn (builds with -DTRM_TRACE only)
     Buf f3_stage;                       // last-mode factor in the constant buffer's layout (copied to the constant bank per launch)
     int flow_debug = 0;
+    // spectral_tensor_regression.py handles (tr_spec_create): kind 2, geo describes the six factor blocks of theta
+    int kind = 0;
+    SpecGeo sg;
+    Buf spA, spDA, spMc, spU, spDS, spRes, spPart, spDf1;
 };
+
+// trainable scalars after the factor entries: the scalar bias of the standard model, the (n_out) bias of the spectral one
+static inline int tr_nbias(const tr_handle* h) { return h->kind == 2 ? h->sg.NO : (h->geo.C == 0 ? 1 : 0); }
 
 namespace {
 
@@ -1015,8 +1023,192 @@ int mn_t(tr_handle* h, const void* X, const long long* y, const void* class_w, l
     return TR_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// spectral model (tr_spectral.cuh): plan + launch
+// ---------------------------------------------------------------------------------------------
+template <typename T, int VEC> using SpecFwdKern = void (*)(SpecFwdArgs<T>);
+template <typename T, int VEC> using SpecGradKern = void (*)(SpecGradArgs<T>);
+
+template <typename T, int VEC>
+SpecFwdKern<T, VEC> spec_fwd_kernel(int QT) {
+    switch (QT) {
+        case 1: return k_spec_fwd<T, 1, VEC, 8>;
+        case 2: return k_spec_fwd<T, 2, VEC, 8>;
+        case 3: return k_spec_fwd<T, 3, VEC, 4>;
+        case 4: return k_spec_fwd<T, 4, VEC, 4>;
+        case 5: return k_spec_fwd<T, 5, VEC, 4>;
+        case 6: return k_spec_fwd<T, 6, VEC, 4>;
+        case 7: return k_spec_fwd<T, 7, VEC, 4>;
+        case 8: return k_spec_fwd<T, 8, VEC, 4>;
+    }
+    return nullptr;
+}
+template <typename T, int VEC>
+SpecGradKern<T, VEC> spec_grad_kernel(int QT) {
+    switch (QT) {
+        case 1: return k_spec_grad<T, 1, VEC>;
+        case 2: return k_spec_grad<T, 2, VEC>;
+        case 3: return k_spec_grad<T, 3, VEC>;
+        case 4: return k_spec_grad<T, 4, VEC>;
+        case 5: return k_spec_grad<T, 5, VEC>;
+        case 6: return k_spec_grad<T, 6, VEC>;
+        case 7: return k_spec_grad<T, 7, VEC>;
+        case 8: return k_spec_grad<T, 8, VEC>;
+    }
+    return nullptr;
+}
+
+// channels are processed in groups of at most TRS_MAXQ per pass over X, the groups as equal as possible
+static inline void spec_groups(int Q, int* ngroups, int* qt) {
+    *ngroups = (Q + TRS_MAXQ - 1) / TRS_MAXQ;
+    *qt = (Q + *ngroups - 1) / *ngroups;
+}
+
+template <typename T, int VEC>
+int spec_pass1(tr_handle* h, const T* X, long long N, cudaStream_t st) {
+    const SpecGeo& sg = h->sg;
+    int ng, QT;
+    spec_groups(sg.Q, &ng, &QT);
+    auto kern = spec_fwd_kernel<T, VEC>(QT);
+    const size_t smem = (size_t)sg.W * QT * sizeof(T);
+    if (smem > 200 * 1024) return fail(h, TR_ERR_UNSUPPORTED, "first-mode factor rows (%zu bytes) do not fit in shared memory", smem);
+    int rc, occ = 0;
+    if ((rc = occupancy(h, kern, smem, &occ))) return rc;
+    const long long DT = (sg.D + 32 * VEC - 1) / (32 * VEC);
+    const long long items = N * DT;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((items + TR_WPB - 1) / TR_WPB, (long long)h->sms * occ));
+    for (int gi = 0; gi < ng; ++gi) {
+        SpecFwdArgs<T> fa;
+        fa.X = X; fa.N = N; fa.FtT = (const T*)h->FtT.p; fa.A = (T*)h->spA.p; fa.g = sg; fa.q0 = gi * QT;
+        if ((rc = raise_smem_limit(h, kern, smem))) return rc;
+        if (h->prof && gi == 0) { rc = prof_fold(h, false); if (rc) return rc; TR_CUDA(h, cudaEventRecord(h->ev[0], st)); }
+        kern<<<grid, TR_TPB, smem, st>>>(fa);
+        TR_LAUNCH_CHECK(h);
+        if (h->prof && gi == ng - 1) { TR_CUDA(h, cudaEventRecord(h->ev[1], st)); h->ev_set[0] = true; }
+    }
+    h->info[1] = grid; h->info[3] = (long long)DT; h->info[6] = QT; h->info[7] = VEC;
+    return TR_OK;
+}
+
+template <typename T, int VEC>
+int spec_pass2(tr_handle* h, const T* X, long long N, double* gradsum, cudaStream_t st) {
+    const SpecGeo& sg = h->sg;
+    int ng, QT;
+    spec_groups(sg.Q, &ng, &QT);
+    auto kern = spec_grad_kernel<T, VEC>(QT);
+    int rc, occ = 0;
+    if ((rc = occupancy(h, kern, 0, &occ))) return rc;
+    const int WTN = (sg.W + TRS_WT - 1) / TRS_WT;
+    const long long wtot = (long long)h->sms * occ * TR_WPB;
+    long long Gn = std::max<long long>(1, wtot / WTN);
+    if (Gn > N) Gn = N;
+    const long long items = (long long)WTN * Gn;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((items + TR_WPB - 1) / TR_WPB, (long long)h->sms * occ));
+    if ((rc = ensure(h, h->spPart, (size_t)items * TRS_WT * QT * sizeof(double)))) return rc;
+    const long long per = (N + Gn - 1) / Gn;
+    const long long DT = (sg.D + 32 * VEC - 1) / (32 * VEC);
+    // at most ~2048 (sample, tile) steps between two folds of the fp32 sums into the double slots
+    const long long spc = sizeof(T) == 4 ? std::max<long long>(1, std::min<long long>(per, 2048 / std::max<long long>(1, DT))) : per;
+    for (int gi = 0; gi < ng; ++gi) {
+        SpecGradArgs<T> ga;
+        ga.X = X; ga.DA = (const T*)h->spDA.p; ga.N = N; ga.g = sg; ga.q0 = gi * QT; ga.WTN = WTN; ga.Gn = (int)Gn;
+        ga.spc = spc; ga.part = (double*)h->spPart.p;
+        if (h->prof && gi == 0) { rc = prof_fold(h, false); if (rc) return rc; TR_CUDA(h, cudaEventRecord(h->ev[2], st)); }
+        kern<<<grid, TR_TPB, 0, st>>>(ga);
+        TR_LAUNCH_CHECK(h);
+        if (h->prof && gi == ng - 1) { TR_CUDA(h, cudaEventRecord(h->ev[3], st)); h->ev_set[1] = true; }
+        k_spec_dg_reduce<<<std::max(1, std::min(64, (sg.W * QT + 255) / 256)), 256, 0, st>>>((const double*)h->spPart.p, WTN, (int)Gn, QT,
+                                                                                         gi * QT, sg, gradsum);
+        TR_LAUNCH_CHECK(h);
+    }
+    h->info[2] = grid; h->info[5] = Gn;
+    return TR_OK;
+}
+
+// forward (+ gradient when y and gradsum are given) of the spectral model
+template <typename T>
+int run_spec(tr_handle* h, const T* X, const T* y, long long N, const T* theta, const T* w, uint32_t nn_mask, double beta,
+             double thr, double* gradsum, T* yhat, T* yhat_lin, T* spec_pred, T* latents, cudaStream_t st) {
+    const SpecGeo& sg = h->sg;
+    const Geo& g = h->geo;
+    const bool grad = gradsum != nullptr;
+    int rc;
+    h->launches = 0;
+    if ((rc = ensure(h, h->FtT, (size_t)g.pf * sizeof(T)))) return rc;
+    if ((rc = ensure(h, h->Ft64, (size_t)g.pf * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->spA, (size_t)N * sg.Q * sg.D * sizeof(T)))) return rc;
+    const int egrid = (int)std::max<long long>(1, std::min<long long>((N + TR_WPB - 1) / TR_WPB, (long long)h->sms * 8));
+    const int dgrid = (int)std::max<long long>(1, std::min<long long>(N / 64 + 1, (long long)h->sms * 2));
+    const int CR = sg.NO * (sg.RT + 1);
+    const int slabs = (int)std::max<long long>(1, std::min<long long>(N / 32 + 1, std::max<long long>(1, (long long)h->sms * 4 / ((sg.D + TR_TPB - 1) / TR_TPB))));
+    if (grad) {
+        if ((rc = ensure(h, h->spDA, (size_t)N * sg.Q * sg.D * sizeof(T)))) return rc;
+        if ((rc = ensure(h, h->spMc, (size_t)N * std::max(1, sg.Rs) * sg.D * sizeof(T)))) return rc;
+        if ((rc = ensure(h, h->spU, (size_t)N * (sg.RT + 1) * sizeof(T) + (size_t)(sg.RT + 1) * sizeof(T)))) return rc;
+        if ((rc = ensure(h, h->spDS, (size_t)N * sg.RT * sizeof(T)))) return rc;
+        if ((rc = ensure(h, h->spRes, (size_t)N * sg.NO * sizeof(T)))) return rc;
+        if ((rc = ensure(h, h->epi_part, (size_t)egrid * sizeof(double)))) return rc;
+        if ((rc = ensure(h, h->dfc_part, ((size_t)dgrid + 1) * CR * sizeof(double)))) return rc;
+        if ((rc = ensure(h, h->spDf1, (size_t)slabs * sg.RT * sg.D * sizeof(double)))) return rc;
+    }
+    k_prep<T><<<std::max(1, std::min(64, (g.pf + 255) / 256)), 256, 0, st>>>(theta, g, nn_mask, beta, thr, (T*)h->FtT.p, (double*)h->Ft64.p);
+    TR_LAUNCH_CHECK(h);
+    const bool vec = vec_ok(X, sg.D, sizeof(T));
+    constexpr int VEC = 16 / (int)sizeof(T);
+    if ((rc = vec ? spec_pass1<T, VEC>(h, X, N, st) : spec_pass1<T, 1>(h, X, N, st))) return rc;
+    SpecEpiArgs<T> ea;
+    memset(&ea, 0, sizeof(ea));
+    ea.A = (const T*)h->spA.p; ea.Ft64 = (const double*)h->Ft64.p; ea.theta = theta; ea.w = w; ea.y = y; ea.N = N; ea.g = sg;
+    ea.nb = (double)((sg.Rn > 0 ? 1 : 0) + (sg.Rs > 0 ? 1 : 0));
+    ea.yhat = yhat;
+    if (grad) {
+        ea.res = (T*)h->spRes.p; ea.U = (T*)h->spU.p; ea.dS = (T*)h->spDS.p; ea.Mc = (T*)h->spMc.p; ea.DA = (T*)h->spDA.p;
+        ea.part = (double*)h->epi_part.p;
+    }
+    if (grad || yhat) {
+        k_spec_epi<T><<<egrid, TR_TPB, 0, st>>>(ea);
+        TR_LAUNCH_CHECK(h);
+    }
+    if (yhat_lin || spec_pred || latents) {
+        SpecPredArgs<T> pa;
+        pa.A = (const T*)h->spA.p; pa.Ft64 = (const double*)h->Ft64.p; pa.theta = theta; pa.w = w; pa.N = N; pa.g = sg;
+        pa.yhat_lin = yhat_lin; pa.spec_pred = spec_pred; pa.latents = latents;
+        k_spec_pred<T><<<egrid, TR_TPB, (size_t)TR_WPB * sg.Q * sizeof(double), st>>>(pa);
+        TR_LAUNCH_CHECK(h);
+    }
+    if (grad) {
+        // third-mode factors + bias:  M[n,c] = wcat_c sum_t res[t,n] U[t,c],  wcat = [w_normal | 1 ... 1 | 1]
+        T* wcat = (T*)h->spU.p + (size_t)N * (sg.RT + 1);
+        k_spec_wcat<T><<<1, 32, 0, st>>>(w, sg.Rn, sg.RT + 1, wcat);
+        TR_LAUNCH_CHECK(h);
+        const size_t smem = (size_t)4 * CR * sizeof(double);
+        if ((rc = raise_smem_limit(h, k_dfc<T>, smem))) return rc;
+        k_dfc<T><<<dgrid, TR_TPB, smem, st>>>((const T*)h->spRes.p, (const T*)h->spU.p, wcat, N, sg.NO, sg.RT + 1, (double*)h->dfc_part.p);
+        TR_LAUNCH_CHECK(h);
+        double* M = (double*)h->dfc_part.p + (size_t)dgrid * CR;
+        k_colsum<<<CR, 128, 0, st>>>((const double*)h->dfc_part.p, dgrid, CR, M);
+        TR_LAUNCH_CHECK(h);
+        k_spec_scatter<<<1, 256, 0, st>>>(M, (const double*)h->epi_part.p, egrid, sg, ea.nb, gradsum);
+        TR_LAUNCH_CHECK(h);
+        // second-mode factors
+        SpecDf1Args<T> da;
+        da.A = (const T*)h->spA.p; da.Mc = (const T*)h->spMc.p; da.dS = (const T*)h->spDS.p; da.N = N; da.g = sg; da.slabs = slabs;
+        da.part = (double*)h->spDf1.p;
+        k_spec_df1<T><<<dim3((sg.D + TR_TPB - 1) / TR_TPB, slabs), TR_TPB, 0, st>>>(da);
+        TR_LAUNCH_CHECK(h);
+        k_spec_df1_reduce<<<std::max(1, std::min(128, (sg.RT * sg.D + 255) / 256)), 256, 0, st>>>((const double*)h->spDf1.p, slabs, sg, gradsum);
+        TR_LAUNCH_CHECK(h);
+        // first-mode factors: the second pass over X
+        if ((rc = vec ? spec_pass2<T, VEC>(h, X, N, gradsum, st) : spec_pass2<T, 1>(h, X, N, gradsum, st))) return rc;
+    }
+    h->info[0] = h->launches; h->info[4] = slabs;
+    return TR_OK;
+}
+
 int check_common(tr_handle* h, const void* X, long long N, const void* theta, const void* w) {
     if (!h) return TR_ERR_INVALID;
+    if (h->kind != 0) return fail(h, TR_ERR_INVALID, "this entry point does not take a spectral handle (use tr_spec_*)");
     if (N < 0) return fail(h, TR_ERR_INVALID, "N must be >= 0 (got %lld)", N);
     if ((N > 0 && !X) || !theta || !w) return fail(h, TR_ERR_INVALID, "null X / theta / w pointer");
     if ((uintptr_t)X % h->elt != 0) return fail(h, TR_ERR_INVALID, "X is not aligned to its element size");
@@ -1085,7 +1277,8 @@ int tr_destroy(tr_handle* h) {
     DeviceGuard dg(h->device);
     cudaDeviceSynchronize();
     Buf* bufs[] = {&h->FtT, &h->Ft64, &h->partial, &h->V, &h->u_ws, &h->dZ_ws, &h->Gpart, &h->Gred, &h->epi_part, &h->dfc_part,
-                   &h->flow_ring, &h->flow_sync, &h->Apart, &h->Spart, &h->trace, &h->f3_stage};
+                   &h->flow_ring, &h->flow_sync, &h->Apart, &h->Spart, &h->trace, &h->f3_stage,
+                   &h->spA, &h->spDA, &h->spMc, &h->spU, &h->spDS, &h->spRes, &h->spPart, &h->spDf1};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
@@ -1096,14 +1289,14 @@ const char* tr_last_error(tr_handle* h) { return h ? h->err.c_str() : g_create_e
 
 int tr_param_count(tr_handle* h, int64_t* P, int64_t* Pf) {
     if (!h) return TR_ERR_INVALID;
-    if (P) *P = h->geo.pf + (h->geo.C == 0 ? 1 : 0);
+    if (P) *P = h->geo.pf + tr_nbias(h);
     if (Pf) *Pf = h->geo.pf;
     return TR_OK;
 }
 
 int tr_gradsum_count(tr_handle* h, int64_t* count) {
     if (!h || !count) return TR_ERR_INVALID;
-    *count = h->geo.pf + (h->geo.C == 0 ? 2 : 1);
+    *count = h->geo.pf + tr_nbias(h) + 1;
     return TR_OK;
 }
 
@@ -1156,7 +1349,7 @@ int tr_forward_mn(tr_handle* h, const void* X, int64_t N, const void* theta, con
 }
 
 static int zero_gradsum(tr_handle* h, double* gradsum, cudaStream_t st) {
-    const size_t n = (size_t)h->geo.pf + (h->geo.C == 0 ? 2 : 1);
+    const size_t n = (size_t)h->geo.pf + tr_nbias(h) + 1;
     TR_CUDA(h, cudaMemsetAsync(gradsum, 0, n * sizeof(double), st));
     return TR_OK;
 }
@@ -1218,6 +1411,85 @@ int tr_backward_mn(tr_handle* h, const void* X, const void* dP, int64_t N, const
                : mn_t<double>(h, X, nullptr, nullptr, N, theta, w, nn_mask, sp_beta, sp_thr, gradsum, nullptr, nullptr, st, dP);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// spectral_tensor_regression.py (tr_spectral.cuh)
+// ---------------------------------------------------------------------------------------------
+int tr_spec_create(tr_handle** out, int dtype, int64_t W, int64_t D, int64_t n_out, int rank_normal, int rank_spectral,
+                   int complex_dim, int device) {
+    if (!out) return fail(nullptr, TR_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (W < 1 || D < 1 || n_out < 1 || W > (1 << 20) || D > (1 << 24))
+        return fail(nullptr, TR_ERR_INVALID, "invalid geometry W=%lld D=%lld n_out=%lld", (long long)W, (long long)D, (long long)n_out);
+    if (n_out > TR_MAX_CLASSES) return fail(nullptr, TR_ERR_UNSUPPORTED, "n_out=%lld outputs (supported: up to %d)", (long long)n_out, TR_MAX_CLASSES);
+    if (rank_normal < 0 || rank_spectral < 0 || rank_normal + rank_spectral < 1 || rank_normal + rank_spectral > TRS_MAXR)
+        return fail(nullptr, TR_ERR_UNSUPPORTED, "rank_normal=%d rank_spectral=%d (supported: 1 <= sum <= %d)", rank_normal, rank_spectral, TRS_MAXR);
+    if (complex_dim < 1 || complex_dim > 16) return fail(nullptr, TR_ERR_UNSUPPORTED, "complex_dim=%d (supported: 1..16)", complex_dim);
+    const int64_t one = 1;
+    tr_handle* h = nullptr;
+    int rc = tr_create(&h, dtype, 1, &one, 1, 0, device);       // device / dtype checks, SM count
+    if (rc) return rc;
+    h->kind = 2;
+    SpecGeo& sg = h->sg;
+    sg.W = (int)W; sg.D = (int)D; sg.NO = (int)n_out; sg.Rn = rank_normal; sg.Rs = rank_spectral; sg.CC = complex_dim;
+    sg.Q = rank_normal + rank_spectral * complex_dim; sg.RT = rank_normal + rank_spectral;
+    const long long sizes[6] = {W * rank_normal, D * rank_normal, n_out * rank_normal,
+                                W * rank_spectral * complex_dim, D * rank_spectral, n_out * rank_spectral};
+    long long off = 0;
+    Geo& g = h->geo;
+    memset(&g, 0, sizeof(g));
+    g.k = 6; g.R = 1; g.C = 0; g.D = W * D;
+    for (int i = 0; i < 6; ++i) {
+        sg.off[i] = (int)off; g.foff[i] = (int)off; g.dims[i] = (int)sizes[i];
+        off += sizes[i];
+        if (off > (1LL << 30)) { tr_destroy(h); return fail(nullptr, TR_ERR_UNSUPPORTED, "too many parameters"); }
+    }
+    sg.off[6] = (int)off;
+    g.foff[6] = (int)off; g.foff[7] = (int)off;
+    g.pfeat = (int)off; g.pf = (int)off;
+    *out = h;
+    return TR_OK;
+}
+
+static int spec_check(tr_handle* h, const void* X, int64_t N, const void* theta, const void* w) {
+    if (!h) return TR_ERR_INVALID;
+    if (h->kind != 2) return fail(h, TR_ERR_INVALID, "tr_spec_* needs a handle made by tr_spec_create");
+    if (N < 0) return fail(h, TR_ERR_INVALID, "N must be >= 0 (got %lld)", (long long)N);
+    if ((N > 0 && !X) || !theta || !w) return fail(h, TR_ERR_INVALID, "null X / theta / w pointer");
+    if ((uintptr_t)X % h->elt != 0) return fail(h, TR_ERR_INVALID, "X is not aligned to its element size");
+    return TR_OK;
+}
+
+int tr_spec_forward(tr_handle* h, const void* X, int64_t N, const void* theta, const void* w, uint32_t nn_mask,
+                    double sp_beta, double sp_thr, void* yhat, void* yhat_lin, void* spec_pred, void* latents, void* stream) {
+    int rc = spec_check(h, X, N, theta, w);
+    if (rc) return rc;
+    if (N == 0) return TR_OK;
+    DeviceGuard dg(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->dtype == TR_F32)
+        return run_spec<float>(h, (const float*)X, nullptr, N, (const float*)theta, (const float*)w, nn_mask, sp_beta, sp_thr,
+                               nullptr, (float*)yhat, (float*)yhat_lin, (float*)spec_pred, (float*)latents, st);
+    return run_spec<double>(h, (const double*)X, nullptr, N, (const double*)theta, (const double*)w, nn_mask, sp_beta, sp_thr,
+                            nullptr, (double*)yhat, (double*)yhat_lin, (double*)spec_pred, (double*)latents, st);
+}
+
+int tr_spec_fwd_grad(tr_handle* h, const void* X, const void* y, int64_t N, const void* theta, const void* w,
+                     uint32_t nn_mask, double sp_beta, double sp_thr, double* gradsum, void* yhat, void* stream) {
+    int rc = spec_check(h, X, N, theta, w);
+    if (rc) return rc;
+    if (!gradsum || (N > 0 && !y)) return fail(h, TR_ERR_INVALID, "null y / gradsum pointer");
+    DeviceGuard dg(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = zero_gradsum(h, gradsum, st))) return rc;
+    if (N == 0) return TR_OK;
+    if (h->dtype == TR_F32)
+        return run_spec<float>(h, (const float*)X, (const float*)y, N, (const float*)theta, (const float*)w, nn_mask, sp_beta,
+                               sp_thr, gradsum, (float*)yhat, nullptr, nullptr, nullptr, st);
+    return run_spec<double>(h, (const double*)X, (const double*)y, N, (const double*)theta, (const double*)w, nn_mask, sp_beta,
+                            sp_thr, gradsum, (double*)yhat, nullptr, nullptr, nullptr, st);
+}
+
 int tr_finish_grad(tr_handle* h, const double* gradsum, double grad_scale, double loss_scale, const void* theta,
                    double lambda_L2, uint32_t nn_mask, double sp_beta, double sp_thr, void* grad, double* loss,
                    void* stream) {
@@ -1225,12 +1497,12 @@ int tr_finish_grad(tr_handle* h, const double* gradsum, double grad_scale, doubl
     if (!gradsum || !theta || !grad || !loss) return fail(h, TR_ERR_INVALID, "null pointer argument");
     DeviceGuard dg(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    const int n_gs = h->geo.pf + (h->geo.C == 0 ? 2 : 1);
+    const int n_gs = h->geo.pf + tr_nbias(h) + 1;
     if (h->dtype == TR_F32)
-        k_finish<float><<<1, 1024, 0, st>>>(gradsum, n_gs, grad_scale, loss_scale, (const float*)theta, h->geo,
+        k_finish<float><<<1, 1024, 0, st>>>(gradsum, n_gs, tr_nbias(h), grad_scale, loss_scale, (const float*)theta, h->geo,
                                             lambda_L2, nn_mask, sp_beta, sp_thr, (float*)grad, loss);
     else
-        k_finish<double><<<1, 1024, 0, st>>>(gradsum, n_gs, grad_scale, loss_scale, (const double*)theta, h->geo,
+        k_finish<double><<<1, 1024, 0, st>>>(gradsum, n_gs, tr_nbias(h), grad_scale, loss_scale, (const double*)theta, h->geo,
                                              lambda_L2, nn_mask, sp_beta, sp_thr, (double*)grad, loss);
     TR_LAUNCH_CHECK(h);
     return TR_OK;
@@ -1245,12 +1517,13 @@ static int adam_launch(tr_handle* h, void* theta, const void* grad, void* m, voi
     DeviceGuard dg(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const Geo& g = h->geo;
-    const long long P = g.pf + (g.C == 0 ? 1 : 0);
+    const long long P = g.pf + tr_nbias(h);
     const double bc1 = 1.0 - pow(beta1, (double)step);
     const double bc2 = 1.0 - pow(beta2, (double)step);
     const double bc2_sqrt = sqrt(bc2);
     AdamGroups ag;
     memset(&ag, 0, sizeof(ag));
+    if (lr_groups && h->kind != 0) return fail(h, TR_ERR_UNSUPPORTED, "tr_adam_step_groups: not available for spectral handles");
     if (lr_groups) {
         // one group per factor in theta order (feature factors, class factor) and, standard model, the bias
         const int nfac = g.k + (g.C > 0 ? 1 : 0);
@@ -1436,7 +1709,7 @@ int tr_lbfgs_direction(tr_handle* h, const void* g, void* prev_g, void* d, doubl
         return fail(h, TR_ERR_UNSUPPORTED, "history_size %d (supported: 1..%d)", history, TR_LBFGS_MAX_HIST);
     DeviceGuard dg(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    const long long P = h->geo.pf + (h->geo.C == 0 ? 1 : 0);
+    const long long P = h->geo.pf + tr_nbias(h);
     if (h->dtype == TR_F32)
         k_lbfgs_direction<float><<<1, 1024, 0, st>>>((const float*)g, (float*)prev_g, (float*)d, t, first, (float*)S,
                                                      (float*)Y, lstate, history, P, scal4);
@@ -1452,7 +1725,7 @@ int tr_lbfgs_point(tr_handle* h, void* out, const void* x, double t, const void*
     if (!out || !x || !d) return fail(h, TR_ERR_INVALID, "null pointer argument");
     DeviceGuard dg(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    const long long P = h->geo.pf + (h->geo.C == 0 ? 1 : 0);
+    const long long P = h->geo.pf + tr_nbias(h);
     const int grid = (int)std::min<long long>((P + 255) / 256, 1024);
     if (h->dtype == TR_F32) k_axpy_out<float><<<grid, 256, 0, st>>>((float*)out, (const float*)x, t, (const float*)d, P);
     else k_axpy_out<double><<<grid, 256, 0, st>>>((double*)out, (const double*)x, t, (const double*)d, P);
@@ -1465,7 +1738,7 @@ int tr_lbfgs_gtd(tr_handle* h, const void* g, const void* d, double* scal2, void
     if (!g || !scal2) return fail(h, TR_ERR_INVALID, "null pointer argument");
     DeviceGuard dg(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    const long long P = h->geo.pf + (h->geo.C == 0 ? 1 : 0);
+    const long long P = h->geo.pf + tr_nbias(h);
     if (h->dtype == TR_F32) k_lbfgs_gtd<float><<<1, 1024, 0, st>>>((const float*)g, (const float*)d, P, scal2);
     else k_lbfgs_gtd<double><<<1, 1024, 0, st>>>((const double*)g, (const double*)d, P, scal2);
     TR_LAUNCH_CHECK(h);

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(TR_TPB) k_mttkrp(const MtArgs a) {
 // L2_penalty std:180-196 (sum of un-squared Frobenius norms of the RAW factors; bias excluded).
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(1024) k_finish(const double* __restrict__ gradsum, int n_gs, double grad_scale,
+__global__ void __launch_bounds__(1024) k_finish(const double* __restrict__ gradsum, int n_gs, int nbias, double grad_scale,
                                                  double loss_scale, const T* __restrict__ theta, Geo g,
                                                  double lambda, uint32_t nn_mask, double beta, double thr,
                                                  T* __restrict__ grad, double* __restrict__ loss) {
@@ -210,8 +210,9 @@ __global__ void __launch_bounds__(1024) k_finish(const double* __restrict__ grad
         if (lambda != 0.0) d += lambda * x / snorm[m];   // lambda == 0: no penalty term (also keeps the VJP path finite at F == 0)
         grad[p] = (T)d;
     }
+    // bias entries (one for the standard model, n_out for the spectral one; none for the multinomial model)
+    for (int b = threadIdx.x; b < nbias; b += blockDim.x) grad[g.pf + b] = (T)(gradsum[g.pf + b] * grad_scale);
     if (threadIdx.x == 0) {
-        if (g.C == 0) grad[g.pf] = (T)(gradsum[g.pf] * grad_scale);
         double pen = 0.0;
         for (int m = 0; m < nfac; ++m) pen += snorm[m];
         const double ld = gradsum[n_gs - 1] * loss_scale;

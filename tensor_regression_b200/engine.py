@@ -273,6 +273,83 @@ class Engine:
         self.launches += 1
 
 
+class SpectralEngine(Engine):
+    """Plan + workspace for the model of spectral_tensor_regression.py: X (T, W, D), y (T, n_out), ``rank_normal``
+    ordinary CP components and ``rank_spectral`` components whose first-mode factor has ``complex_dim`` columns
+    (tr_spec_* entry points).  The optimizer / all-reduce methods of ``Engine`` work on this handle unchanged."""
+
+    def __init__(self, W, D, n_out, rank_normal, rank_spectral, complex_dim, dtype=torch.float32, device='cuda'):
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise TRError(f"device '{device}': tensor_regression_b200 runs on CUDA devices only (no CPU path)")
+        if not torch.cuda.is_available():
+            raise TRError('no CUDA device available (tensor_regression_b200 has no CPU path)')
+        if dtype not in _DT:
+            raise TRError(f'dtype {dtype} not supported (float32 / float64)')
+        if device.index is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device, self.dtype = device, dtype
+        self.W, self.Dm, self.n_out = int(W), int(D), int(n_out)
+        self.rank_normal, self.rank_spectral, self.complex_dim = int(rank_normal), int(rank_spectral), int(complex_dim)
+        self.dims = [self.W, self.Dm]
+        self.rank = self.rank_normal + self.rank_spectral
+        self.n_classes = 0
+        h = ctypes.c_void_p()
+        rc = _lib.lib.tr_spec_create(ctypes.byref(h), _DT[dtype], self.W, self.Dm, self.n_out, self.rank_normal,
+                                     self.rank_spectral, self.complex_dim, device.index)
+        if rc != 0:
+            raise TRError(f'tr_spec_create failed ({rc}): {_lib.lib.tr_last_error(None).decode()}')
+        self._h = h
+        P, Pf, ngs = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        self._ck(_lib.lib.tr_param_count(h, ctypes.byref(P), ctypes.byref(Pf)))
+        self._ck(_lib.lib.tr_gradsum_count(h, ctypes.byref(ngs)))
+        self.P, self.Pf, self.n_gradsum = P.value, Pf.value, ngs.value
+        self.launches = 0
+
+    def block_shapes(self):
+        """Shapes of the six factor blocks of theta in order (Bcp_n then Bcp_c, spectral:518-523)."""
+        rn, rs, cc = self.rank_normal, self.rank_spectral, self.complex_dim
+        return [(self.W, rn, 1), (self.Dm, rn, 1), (self.n_out, rn, 1),
+                (self.W, rs, cc), (self.Dm, rs, 1), (self.n_out, rs, 1)]
+
+    def fwd_grad(self, X, y, theta, w, nn_mask, beta, thr, gradsum=None, yhat=None):
+        X = self._x(X)
+        N = X.shape[0]
+        if gradsum is None:
+            gradsum = torch.empty(self.n_gradsum, dtype=torch.float64, device=self.device)
+        self._ck(_lib.lib.tr_spec_fwd_grad(self._h, X.data_ptr(), self._vec(y, N * self.n_out, 'y').data_ptr(), N,
+                                           self._vec(theta, self.P, 'theta').data_ptr(),
+                                           self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
+                                           self._vec(gradsum, self.n_gradsum, 'gradsum', torch.float64).data_ptr(),
+                                           yhat.data_ptr() if yhat is not None else None, self._stream()))
+        self._count()
+        return gradsum
+
+    def forward(self, X, theta, w, nn_mask, beta, thr, want=('yhat',)):
+        """Returns a dict with the requested outputs among 'yhat' (the model of the fit), 'yhat_lin' (lin_model),
+        'spec_pred' (spectral_model, (N, n_out)) and 'latents' ((N, rank_normal))."""
+        X = self._x(X)
+        N = X.shape[0]
+        shapes = {'yhat': (N, self.n_out), 'yhat_lin': (N, self.n_out), 'spec_pred': (N, self.n_out),
+                  'latents': (N, self.rank_normal)}
+        out = {k: torch.empty(shapes[k], dtype=self.dtype, device=self.device) for k in want}
+        ptr = lambda k: out[k].data_ptr() if k in out and out[k].numel() > 0 else None   # noqa: E731
+        self._ck(_lib.lib.tr_spec_forward(self._h, X.data_ptr(), N, self._vec(theta, self.P, 'theta').data_ptr(),
+                                          self._vec(w, self.rank, 'weights').data_ptr(), nn_mask, beta, thr,
+                                          ptr('yhat'), ptr('yhat_lin'), ptr('spec_pred'), ptr('latents'), self._stream()))
+        self._count()
+        return out
+
+    def launch_info(self):
+        info = (ctypes.c_int64 * 8)()
+        _lib.lib.tr_last_launch_info(self._h, info)
+        keys = ['launches', 'grid_fwd', 'grid_grad', 'tiles_per_sample', 'df1_slabs', 'groups_grad', 'channels_per_pass',
+                'vector_width']
+        d = dict(zip(keys, [int(v) for v in info]))
+        d['path'] = 'two-pass (window contraction, norm epilogue)'
+        return d
+
+
 class ShardedSum:
     """Sums the packed ``gradsum`` vector over the ranks that each hold a slice of the sample
     axis: one all-reduce of P+2 doubles per closure evaluation.  With

@@ -1,0 +1,224 @@
+"""GPU parity of the spectral variant (tensor_regression_b200/spectral_tensor_regression.py, tr_spec_* in the C ABI)
+against the outputs of the UNMODIFIED reference stored in tests/golden/spec_*.npz and against the oracle port
+(oracle/tr_oracle_spectral.py) on seeded inputs.  Tolerances: the north star's 1e-5 (fp32) / 1e-10 (fp64), norm-relative;
+fitted factors after 20 Adam iterations 1e-4 / 1e-9; L-BFGS (fp64) logged losses 1e-7."""
+import ctypes
+import glob
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tr_oracle_spectral as OS
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+SPEC = sorted(glob.glob(os.path.join(GOLDEN, 'spec_*.npz')))
+ADAM = {'lr': 0.01, 'amsgrad': True}
+LBFGS = {'lr': 1, 'max_iter': 20, 'max_eval': None, 'tolerance_grad': 1e-07, 'tolerance_change': 1e-09,
+         'history_size': 100, 'line_search_fn': 'strong_wolfe'}
+DEV = 'cuda:0'
+
+
+def rel(a, b):
+    a = np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a, dtype=np.float64)
+    b = np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b, dtype=np.float64)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300) if b.size else 0.0
+
+
+def case(path):
+    z = np.load(path)
+    X, y = torch.from_numpy(z['X']), torch.from_numpy(z['y'])
+    Bn = [torch.from_numpy(z[f'Bn_init_{i}']) for i in range(3)]
+    Bc = [torch.from_numpy(z[f'Bc_init_{i}']) for i in range(3)]
+    w = z['weights']
+    nn = [bool(v) for v in z['non_negative']]
+    return z, X, y, Bn, Bc, w, nn, float(z['lambda_L2'])
+
+
+def model_of(z, X, y, Bn, Bc, w, nn):
+    from tensor_regression_b200 import spectral_tensor_regression as SPR
+    return SPR.CP_linear_regression(X.shape, y.shape, dtype=X.dtype, rank_normal=int(z['rank_normal']),
+                                    rank_spectral=int(z['rank_spectral']), non_negative=nn, weights=w,
+                                    Bcp_init=[[b.clone() for b in Bn], [b.clone() for b in Bc]],
+                                    n_complex_dim=int(z['n_complex_dim']), device=DEV)
+
+
+@pytest.mark.parametrize('path', SPEC, ids=[os.path.basename(p)[:-4] for p in SPEC])
+def test_spectral_closure_vs_reference_golden(path):
+    """One closure evaluation through the C ABI: prediction, losses and the gradient wrt every raw parameter."""
+    z, X, y, Bn, Bc, w, nn, lam = case(path)
+    tol = 1e-10 if X.dtype == torch.float64 else 1e-5
+    m = model_of(z, X, y, Bn, Bc, w, nn)
+    eng = m._engine()
+    Xd, yd = X.to(DEV), y.to(DEV)
+    beta, thr = m._sp()
+    yhat = torch.empty_like(yd)
+    gs = eng.fwd_grad(Xd, yd, m.theta, m.weights, m._mask(), beta, thr, yhat=yhat)
+    n_total = y.numel()
+    grad, loss = eng.finish(gs, 2.0 / n_total, 1.0 / n_total, m.theta, lam, m._mask(), beta, thr)
+    assert rel(yhat, z['y_hat']) < tol
+    assert abs(loss[0].item() - float(z['loss_data'])) < tol * abs(float(z['loss_data']))
+    assert abs(loss[1].item() - float(z['loss'])) < tol * abs(float(z['loss']))
+    want = np.concatenate([z[f'grad_n_{i}'].reshape(-1) for i in range(3)] + [z[f'grad_c_{i}'].reshape(-1) for i in range(3)]
+                          + [z['dbias'].reshape(-1)])
+    assert rel(grad, want) < tol
+    # block by block as well (a small block must not hide behind a large one)
+    off = 0
+    for name in [f'grad_n_{i}' for i in range(3)] + [f'grad_c_{i}' for i in range(3)] + ['dbias']:
+        n = z[name].size
+        if n:
+            assert rel(grad[off:off + n], z[name].reshape(-1)) < 10 * tol, name
+        off += n
+    # forward-only entry point gives the same prediction
+    out = eng.forward(Xd, m.theta, m.weights, m._mask(), beta, thr, want=('yhat',))
+    assert torch.equal(out['yhat'], yhat)
+
+
+@pytest.mark.parametrize('path', SPEC, ids=[os.path.basename(p)[:-4] for p in SPEC])
+def test_spectral_fit_adam_vs_reference_golden(path):
+    z, X, y, Bn, Bc, w, nn, lam = case(path)
+    f64 = X.dtype == torch.float64
+    m = model_of(z, X, y, Bn, Bc, w, nn)
+    conv = m.fit_Adam(X.to(DEV), y.to(DEV), lambda_L2=lam, max_iter=20, tol=1e-50, patience=100, verbose=False,
+                      Adam_kwargs=ADAM)
+    assert conv is False
+    assert rel(m.loss_running, z['adam_loss_running']) < (1e-9 if f64 else 1e-5)
+    ftol = 1e-9 if f64 else 1e-4
+    for i in range(3):
+        assert rel(m.Bcp_n[i], z[f'adam_Bn_{i}']) < ftol
+        assert rel(m.Bcp_c[i], z[f'adam_Bc_{i}']) < ftol
+    assert rel(m.bias, z['adam_bias']) < ftol
+    # the reference's predict (lin_model + spectral_model) and predict_latents on the fitted model
+    if 'adam_predict' in z.files:
+        p = m.predict(X.to(DEV))
+        assert isinstance(p, torch.Tensor) and p.device.type == 'cpu'
+        assert rel(p, z['adam_predict']) < (1e-8 if f64 else 2e-4)
+        assert rel(m.predict(X.numpy()), z['adam_predict']) < (1e-8 if f64 else 2e-4)       # host array, streamed
+    if 'adam_latents' in z.files:
+        assert rel(m.predict_latents(X.to(DEV)), z['adam_latents']) < (1e-8 if f64 else 2e-4)
+
+
+@pytest.mark.parametrize('path', [p for p in SPEC if 'f64' in p], ids=lambda p: os.path.basename(p)[:-4])
+def test_spectral_fit_lbfgs_vs_reference_golden(path):
+    z, X, y, Bn, Bc, w, nn, lam = case(path)
+    m = model_of(z, X, y, Bn, Bc, w, nn)
+    conv = m.fit(X.to(DEV), y.to(DEV), lambda_L2=lam, max_iter=6, tol=1e-50, patience=10, verbose=False,
+                 running_loss_logging_interval=1, LBFGS_kwargs=LBFGS)
+    assert bool(conv) == bool(z['lbfgs_converged'])
+    # The norm makes this objective much less forgiving than the other models': perturbing X by 1e-15 (relative) moves
+    # the REFERENCE's own logged losses by 2e-14, 3e-12, 2e-8 / 5e-7, 3e-6 / 5e-4, 1e-4 at logged iterations 1..5
+    # (tools/README: measured with the oracle port, the same torch.optim.LBFGS).  The first four logged losses pin
+    # the path; the last two only have to stay on the same descent.
+    want = z['lbfgs_loss_running']
+    assert len(m.loss_running) == len(want)
+    assert rel(m.loss_running[:3], want[:3]) < 1e-9
+    assert abs(m.loss_running[3] - want[3]) < 2e-5 * abs(want[3])
+    assert rel(m.loss_running[4:], want[4:]) < 2e-2
+
+
+@pytest.mark.parametrize('shape', [
+    # T, W, D, n_out, rank_normal, rank_spectral, complex, dtype
+    (37, 13, 21, 3, 2, 2, 2, torch.float32),       # D = 21: element loads, ragged tiles
+    (64, 50, 128, 4, 2, 2, 2, torch.float32),      # 16-byte rows, one full warp tile
+    (50, 9, 260, 2, 3, 3, 3, torch.float32),       # 12 channels: two passes over X per direction; D spans three tiles
+    (33, 17, 36, 5, 4, 1, 1, torch.float64),
+    (20, 5, 8, 2, 1, 1, 4, torch.float64),         # four complex columns
+], ids=lambda s: 'x'.join(str(v) for v in s[:7]) + ('_f64' if s[7] == torch.float64 else '_f32'))
+def test_spectral_kernels_vs_oracle(shape):
+    """Seeded geometry sweep against the oracle port's autograd (fp64 truth for the fp32 cases as well)."""
+    from tensor_regression_b200 import spectral_tensor_regression as SPR
+    T, W, D, NO, rn, rs, cc, dtype = shape
+    X, y = OS.synth(T, W, D, NO, rn, rs, cc, 4242, dtype=dtype)
+    Bn, Bc = OS.init(W, D, NO, rn, rs, cc, dtype=dtype, seed=99)
+    nn = [True, False, False]
+    w = np.linspace(0.5, 1.5, rn + rs)
+    lam = 0.01
+    bias = 0.1 * torch.arange(1, NO + 1, dtype=dtype)
+    r = OS.loss_grad(X.double(), y.double(), [b.double() for b in Bn], [b.double() for b in Bc], bias.double(),
+                     torch.tensor(w, dtype=torch.float64), nn, lam)
+    m = SPR.CP_linear_regression(X.shape, y.shape, dtype=dtype, rank_normal=rn, rank_spectral=rs, non_negative=nn,
+                                 weights=w, Bcp_init=[Bn, Bc], n_complex_dim=cc - 1, device=DEV)
+    m.bias.copy_(bias.to(DEV))
+    eng = m._engine()
+    beta, thr = m._sp()
+    Xd, yd = X.to(DEV), y.to(DEV)
+    yhat = torch.empty_like(yd)
+    gs = eng.fwd_grad(Xd, yd, m.theta, m.weights, m._mask(), beta, thr, yhat=yhat)
+    grad, loss = eng.finish(gs, 2.0 / y.numel(), 1.0 / y.numel(), m.theta, lam, m._mask(), beta, thr)
+    tol = 1e-10 if dtype == torch.float64 else 1e-5
+    assert rel(yhat.reshape(-1), r['y_hat'].reshape(-1)) < tol
+    assert abs(loss[1].item() - r['loss']) < tol * abs(r['loss'])
+    want = torch.cat([g.reshape(-1) for g in r['grad_n'] + r['grad_c']] + [r['dbias'].reshape(-1)])
+    assert rel(grad, want) < tol
+    # relaunch: bit-identical (fixed summation orders, no atomics)
+    gs2 = eng.fwd_grad(Xd, yd, m.theta, m.weights, m._mask(), beta, thr)
+    assert torch.equal(gs, gs2)
+    # shard sums add up: the gradsum of two halves of the sample axis sums to the whole (what the all-reduce relies on)
+    h = T // 2
+    ga = eng.fwd_grad(Xd[:h].contiguous(), yd[:h].contiguous(), m.theta, m.weights, m._mask(), beta, thr).clone()
+    gb = eng.fwd_grad(Xd[h:].contiguous(), yd[h:].contiguous(), m.theta, m.weights, m._mask(), beta, thr)
+    assert rel(ga + gb, gs) < 1e-12 if dtype == torch.float64 else rel(ga + gb, gs) < 1e-6
+    # module-level functions
+    got = SPR.lin_model(Xd, [b.to(DEV) for b in Bn], m.weights[:rn], nn, m.bias) + \
+        SPR.stepwise_spectral_model(Xd, [b.to(DEV) for b in Bc], m.weights[rn:], nn, m.bias)
+    assert rel(got.reshape(-1), r['y_hat'].reshape(-1)) < tol
+    sp = OS.spectral_model(X.double(), [b.double() for b in Bc], torch.tensor(w[rn:], dtype=torch.float64), nn, bias.double())
+    assert rel(SPR.spectral_model(Xd, [b.to(DEV) for b in Bc], m.weights[rn:], nn, m.bias).reshape(-1), sp.reshape(-1)) < tol
+
+
+def test_spectral_api_surface_and_errors():
+    from tensor_regression_b200 import spectral_tensor_regression as SPR
+    from tensor_regression_b200._lib import TRError
+    m = SPR.CP_linear_regression((10, 6, 8), (10, 2), rank_normal=2, rank_spectral=1, n_complex_dim=1, device=DEV)
+    assert [tuple(b.shape) for b in m.Bcp_n] == [(6, 2, 1), (8, 2, 1), (2, 2, 1)]
+    assert [tuple(b.shape) for b in m.Bcp_c] == [(6, 1, 2), (8, 1, 1), (2, 1, 1)]
+    assert tuple(m.bias.shape) == (2,) and float(m.bias.abs().sum()) == 0.0
+    assert m.theta.numel() == 2 * (6 + 8 + 2) + (12 + 8 + 2) + 2
+    X = torch.randn(10, 6, 8, device=DEV)
+    y = torch.randn(10, 2, device=DEV)
+    with pytest.raises(TypeError):
+        m.fit_Adam(X, y)                      # Adam_kwargs=None raises, as in the reference (spectral:705-712)
+    with pytest.raises(TypeError):
+        m.fit(X, y)
+    with pytest.raises(ValueError):
+        m.fit_Adam(torch.randn(10, 6, 9, device=DEV), y, Adam_kwargs=ADAM)
+    with pytest.raises(ValueError):
+        SPR.CP_linear_regression((10, 6, 8, 3), (10, 2), device=DEV)
+    with pytest.raises(TRError):
+        SPR.CP_linear_regression((10, 6, 8), (10, 2), device='cpu')
+    m.fit_Adam(X, y, max_iter=3, Adam_kwargs=ADAM)
+    assert len(m.loss_running) == 3
+    p = m.get_params()
+    assert set(p) == {'weights', 'Bcp_n', 'Bcp_c', 'non_negative', 'softplus_kwargs', 'rank', 'device', 'loss_running'}
+    m2 = pickle.loads(pickle.dumps(m))
+    assert torch.equal(m2.theta, m.theta)
+    assert rel(m2.predict(X), m.predict(X)) == 0.0
+    m3 = SPR.CP_linear_regression((10, 6, 8), (10, 2), rank_normal=2, rank_spectral=1, n_complex_dim=1, device=DEV)
+    m3.set_params(p)
+    assert all(torch.equal(a, b) for a, b in zip(m3.Bcp_n + m3.Bcp_c, m.Bcp_n + m.Bcp_c))
+    fin_n, fin_c = m.return_Bcp_final()
+    assert len(fin_n) == 3 and fin_c[0].shape == (6, 1, 2)
+    # a standard-model entry point refuses a spectral handle
+    from tensor_regression_b200 import _lib
+    rc = _lib.lib.tr_forward_std(m._engine()._h, X.data_ptr(), 10, m.theta.data_ptr(), m.weights.data_ptr(), 0, 50.0, 1.0,
+                                 y.data_ptr(), None)
+    assert rc != 0 and b'spectral' in _lib.lib.tr_last_error(m._engine()._h)
+
+
+def test_spectral_convergence_rule_and_nan_stop(capsys):
+    """fit_Adam stops on the reference's rule (spectral:743-745) and both fits report a NaN loss like the reference."""
+    from tensor_regression_b200 import spectral_tensor_regression as SPR
+    X, y = OS.synth(40, 6, 8, 2, 1, 1, 2, 7)
+    m = SPR.CP_linear_regression(X.shape, y.shape, rank_normal=1, rank_spectral=1, n_complex_dim=1, device=DEV)
+    conv = m.fit_Adam(X.to(DEV), y.to(DEV), lambda_L2=0.0, max_iter=400, tol=1e3, patience=5, Adam_kwargs={'lr': 1e-3})
+    assert conv is True and len(m.loss_running) == 7          # first test at ii = patience + 1
+    m2 = SPR.CP_linear_regression(X.shape, y.shape, rank_normal=1, rank_spectral=1, n_complex_dim=1, device=DEV)
+    Xn = X.clone()
+    Xn[0, 0, 0] = float('nan')
+    conv = m2.fit_Adam(Xn.to(DEV), y.to(DEV), max_iter=50, Adam_kwargs={'lr': 1e-3})
+    assert conv is False and len(m2.loss_running) == 1
+    assert 'Loss is NaN. Stopping.' in capsys.readouterr().out

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(_lib.lib, name), name
-    assert _lib.lib.tr_version() == 200
+    assert _lib.lib.tr_version() == 210
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-device failure mode')
