@@ -37,6 +37,9 @@ WORKLOADS = {
     'cfg3': ('mn', 62500, (100, 50, 20), 6, 10, torch.float32),
     'cfg4': ('std', 100000, (16, 16, 16, 32), 12, 0, torch.float64),
     'cfg5': ('mn', 312500, (100, 50, 20), 4, 4, torch.float32),
+    # the spectral variant (spectral_tensor_regression.py); dims = (W, D), R = (rank_normal, rank_spectral,
+    # complex columns), C = outputs.  Not a BASELINE config: measured as a secondary record.
+    'spec1': ('spec', 200000, (64, 128), (2, 2, 2), 4, torch.float32),
     # diagnostic only (not a BASELINE config): the standard model on the cfg3 sample shape
     'dbg3': ('std', 62500, (100, 50, 20), 6, 0, torch.float32),
 }
@@ -46,6 +49,7 @@ DESCR = {
     'cfg3': 'multinomial CP regression, X (N=62500 per GPU, 100,50,20), n_classes=10, rank 6, fp32',
     'cfg4': '5-mode standard CP regression, X (N=100000, 16,16,16,32), rank 12, fp64',
     'cfg5': 'multinomial CP regression, X (N=312500 per GPU, 100,50,20), n_classes=4, rank 4, fp32',
+    'spec1': 'spectral CP regression (spectral_tensor_regression.py), X (T=200000 per GPU, 64,128), 4 outputs, rank_normal 2, rank_spectral 2, 2 complex columns, fp32',
     'dbg3': 'diagnostic: standard CP regression on the cfg3 sample shape, X (N=62500, 100,50,20), rank 6, fp32',
 }
 ADAM = {'lr': 0.01, 'amsgrad': True}
@@ -187,7 +191,12 @@ def make_device_data(wl, n_local, rank, device):
     for lo in range(0, n_local, step):
         X[lo:lo + step].normal_(generator=g)
     gc = torch.Generator().manual_seed(4321)
-    Fstar = [0.3 * torch.randn((d, R), generator=gc, dtype=dt) for d in list(dims) + ([C] if C else [])]
+    if kind == 'spec':
+        rn, rs, cc = R
+        shapes = [(dims[0], rn), (dims[1], rn), (C, rn), (dims[0], rs * cc), (dims[1], rs), (C, rs)]
+        Fstar = [0.1 * torch.randn(shp, generator=gc, dtype=dt) for shp in shapes]
+    else:
+        Fstar = [0.3 * torch.randn((d, R), generator=gc, dtype=dt) for d in list(dims) + ([C] if C else [])]
     return X, Fstar
 
 
@@ -369,7 +378,18 @@ class Workload:
         self.sharder = None
         nn = [False] * (len(dims) + 1)
         torch.manual_seed(321)
-        if kind == 'std':
+        if kind == 'spec':
+            rn, rs, cc = R
+            self.eng = E.SpectralEngine(dims[0], dims[1], C, rn, rs, cc, dt, device)
+            self.w = torch.ones(rn + rs, dtype=dt, device=device)
+            theta_star = torch.cat([f.reshape(-1) for f in Fstar] + [torch.zeros(C, dtype=dt)]).to(device)
+            self.y = self.eng.forward(self.X, theta_star, self.w, 0, 50.0, 1.0, want=('yhat',))['yhat']
+            self.y += 0.01 * torch.randn(self.y.shape, dtype=dt, device=device)
+            gi = torch.Generator().manual_seed(321)
+            self.theta = (0.2 * torch.rand(self.eng.P, generator=gi, dtype=dt) - 0.05).to(device).contiguous()
+            self.theta[-C:] = 0
+            self.cw = None
+        elif kind == 'std':
             self.eng = E.Engine(dims, R, 0, dt, device)
             self.w = torch.ones(R, dtype=dt, device=device)
             theta_star = torch.cat([f.reshape(-1) for f in Fstar] + [torch.tensor([0.1], dtype=dt)]).to(device)
@@ -387,9 +407,10 @@ class Workload:
             self.theta = torch.cat([b.reshape(-1) for b in self.B0]).to(device=device, dtype=torch.float32).contiguous()
             self.cw = torch.ones(C, device=device)
         self.sharder = E.ShardedSum(engine=self.eng) if world > 1 else E.ShardedSum(enabled=False)
-        self.eng.set_option('fused', fused)
-        if flow == 1:
-            self.eng.set_option('flow', 1)
+        if kind != 'spec':
+            self.eng.set_option('fused', fused)
+            if flow == 1:
+                self.eng.set_option('flow', 1)
         self.reset()
 
     def reset(self):
@@ -407,7 +428,12 @@ class Workload:
         y = self.y if y is None else y
         self.step_no += 1
         eng = self.eng
-        if self.kind == 'std':
+        if self.kind == 'spec':
+            eng.fwd_grad(X, y, self.th, self.w, 0, 50.0, 1.0, gradsum=self.gs)
+            self.sharder.sum_(self.gs)
+            nt = n_total * self.C                      # MSE over (T, n_out)
+            eng.finish(self.gs, 2.0 / nt, 1.0 / nt, self.th, LAMBDA, 0, 50.0, 1.0, grad=self.grad, loss=self.loss)
+        elif self.kind == 'std':
             eng.fwd_grad_std(X, y, self.th, self.w, 0, 50.0, 1.0, gradsum=self.gs)
             self.sharder.sum_(self.gs)
             eng.finish(self.gs, 2.0 / n_total, 1.0 / n_total, self.th, LAMBDA, 0, 50.0, 1.0, grad=self.grad, loss=self.loss)
@@ -486,6 +512,8 @@ def roofline_of(res, wk, x_bytes, ratios):
                  'share_of_step': {dom: fused_ms / ms_per_step}}
     else:
         dom = 'k_grad' if grad_ms >= fwd_ms else 'k_fwd'
+        if wk.kind == 'spec':
+            dom = 'k_spec_grad' if grad_ms >= fwd_ms else 'k_spec_fwd'
         dom_ms, alg, phys = max(grad_ms, fwd_ms), x_bytes, x_bytes
         extra = {'k_fwd_ms': fwd_ms, 'k_grad_ms': grad_ms,
                  'k_fwd_gbs': x_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None,
@@ -578,7 +606,7 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help="weak: every rank holds the workload's per-GPU N (default); strong: the workload's N is split over the ranks")
-    ap.add_argument('--secondary', default='cfg3,cfg4,cfg5', help='comma list of further workloads measured after the primary (device-timed only); "" = none')
+    ap.add_argument('--secondary', default='cfg3,cfg4,cfg5,spec1', help='comma list of further workloads measured after the primary (device-timed only); "" = none')
     ap.add_argument('--n-local', type=int, default=0, help='override samples per GPU (debug)')
     ap.add_argument('--secondary-n-local', type=int, default=0, help='override samples per GPU of the secondary workloads (debug)')
     ap.add_argument('--no-e2e', action='store_true')
@@ -676,7 +704,7 @@ def main():
 
     # ---- end to end through the public API with HOST buffers ------------------------------------------------
     e2e = None
-    X, y, B0 = wk.X, wk.y, wk.B0
+    X, y, B0 = wk.X, wk.y, getattr(wk, 'B0', None)
     if not args.no_e2e:
         pool_n = int(min(n_local, max(256, (2 << 30) // (D * elt))))
         pool = torch.empty((pool_n, *dims), dtype=dt, pin_memory=True)

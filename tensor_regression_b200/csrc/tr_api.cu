@@ -1059,6 +1059,22 @@ SpecGradKern<T, VEC> spec_grad_kernel(int QT) {
     return nullptr;
 }
 
+template <typename T, int VEC> using SpecFusedKern = void (*)(SpecFusedArgs<T>);
+template <typename T, int VEC>
+SpecFusedKern<T, VEC> spec_fused_kernel(int QT) {
+    switch (QT) {
+        case 1: return k_spec_fused<T, 1, VEC, 8>;
+        case 2: return k_spec_fused<T, 2, VEC, 8>;
+        case 3: return k_spec_fused<T, 3, VEC, 8>;
+        case 4: return k_spec_fused<T, 4, VEC, 8>;
+        case 5: return k_spec_fused<T, 5, VEC, 8>;
+        case 6: return k_spec_fused<T, 6, VEC, 8>;
+        case 7: return k_spec_fused<T, 7, VEC, 4>;
+        case 8: return k_spec_fused<T, 8, VEC, 4>;
+    }
+    return nullptr;
+}
+
 // channels are processed in groups of at most TRS_MAXQ per pass over X, the groups as equal as possible
 static inline void spec_groups(int Q, int* ngroups, int* qt) {
     *ngroups = (Q + TRS_MAXQ - 1) / TRS_MAXQ;
@@ -1118,11 +1134,45 @@ int spec_pass2(tr_handle* h, const T* X, long long N, double* gradsum, cudaStrea
         kern<<<grid, TR_TPB, 0, st>>>(ga);
         TR_LAUNCH_CHECK(h);
         if (h->prof && gi == ng - 1) { TR_CUDA(h, cudaEventRecord(h->ev[3], st)); h->ev_set[1] = true; }
-        k_spec_dg_reduce<<<std::max(1, std::min(64, (sg.W * QT + 255) / 256)), 256, 0, st>>>((const double*)h->spPart.p, WTN, (int)Gn, QT,
-                                                                                         gi * QT, sg, gradsum);
+        k_spec_dg_fold<<<sg.W * QT, 128, 0, st>>>((const double*)h->spPart.p, WTN, (int)Gn, QT, gi * QT, sg, gradsum);
         TR_LAUNCH_CHECK(h);
     }
     h->info[2] = grid; h->info[5] = Gn;
+    return TR_OK;
+}
+
+// pass 1 + epilogue + second-mode gradient in one kernel (samples of one warp tile); fills DA, res, U, gradsum[F*1], loss parts
+template <typename T, int VEC>
+int spec_fused_pass1(tr_handle* h, const T* X, const T* y, long long N, const T* theta, const T* w, double nb,
+                     double* gradsum, T* yhat, int* nloss, cudaStream_t st) {
+    const SpecGeo& sg = h->sg;
+    const int QT = sg.Q;
+    auto kern = spec_fused_kernel<T, VEC>(QT);
+    constexpr int CH = 16 / (int)sizeof(T);
+    const int QP = (QT + CH - 1) / CH * CH;                                   // row stride of the G table (whole 16-byte chunks)
+    const size_t smem = ((size_t)sg.W * QP + (size_t)sg.NO * QT + sg.NO) * sizeof(T);
+    int rc, occ = 0;
+    if ((rc = occupancy(h, kern, smem, &occ))) return rc;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((N + TR_WPB - 1) / TR_WPB, (long long)h->sms * occ));
+    const size_t nslots = (size_t)grid * TR_WPB;
+    const int TILE = 32 * VEC;
+    if ((rc = ensure(h, h->spDf1, nslots * QT * TILE * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->epi_part, (size_t)grid * sizeof(double)))) return rc;
+    SpecFusedArgs<T> fa;
+    fa.X = X; fa.y = y; fa.N = N; fa.FtT = (const T*)h->FtT.p; fa.theta = theta; fa.w = w; fa.g = sg; fa.nb = nb;
+    fa.DA = (T*)h->spDA.p; fa.res = (T*)h->spRes.p; fa.U = (T*)h->spU.p; fa.yhat = yhat;
+    fa.df1part = (double*)h->spDf1.p; fa.losspart = (double*)h->epi_part.p;
+    const long long per = (N + (long long)nslots - 1) / (long long)nslots;
+    fa.spc = sizeof(T) == 4 ? std::max<long long>(1, std::min<long long>(per, 2048)) : std::max<long long>(1, per);
+    if ((rc = raise_smem_limit(h, kern, smem))) return rc;
+    if (h->prof) { rc = prof_fold(h, false); if (rc) return rc; TR_CUDA(h, cudaEventRecord(h->ev[0], st)); }
+    kern<<<grid, TR_TPB, smem, st>>>(fa);
+    TR_LAUNCH_CHECK(h);
+    if (h->prof) { TR_CUDA(h, cudaEventRecord(h->ev[1], st)); h->ev_set[0] = true; }
+    k_spec_df1_fold<<<sg.RT * sg.D, 128, 0, st>>>((const double*)h->spDf1.p, (int)nslots, QT, TILE, sg, gradsum);
+    TR_LAUNCH_CHECK(h);
+    *nloss = grid;
+    h->info[1] = grid; h->info[3] = 1; h->info[6] = QT; h->info[7] = VEC;
     return TR_OK;
 }
 
@@ -1137,36 +1187,52 @@ int run_spec(tr_handle* h, const T* X, const T* y, long long N, const T* theta, 
     h->launches = 0;
     if ((rc = ensure(h, h->FtT, (size_t)g.pf * sizeof(T)))) return rc;
     if ((rc = ensure(h, h->Ft64, (size_t)g.pf * sizeof(double)))) return rc;
-    if ((rc = ensure(h, h->spA, (size_t)N * sg.Q * sg.D * sizeof(T)))) return rc;
     const int egrid = (int)std::max<long long>(1, std::min<long long>((N + TR_WPB - 1) / TR_WPB, (long long)h->sms * 8));
     const int dgrid = (int)std::max<long long>(1, std::min<long long>(N / 64 + 1, (long long)h->sms * 2));
     const int CR = sg.NO * (sg.RT + 1);
     const int slabs = (int)std::max<long long>(1, std::min<long long>(N / 32 + 1, std::max<long long>(1, (long long)h->sms * 4 / ((sg.D + TR_TPB - 1) / TR_TPB))));
     if (grad) {
         if ((rc = ensure(h, h->spDA, (size_t)N * sg.Q * sg.D * sizeof(T)))) return rc;
-        if ((rc = ensure(h, h->spMc, (size_t)N * std::max(1, sg.Rs) * sg.D * sizeof(T)))) return rc;
         if ((rc = ensure(h, h->spU, (size_t)N * (sg.RT + 1) * sizeof(T) + (size_t)(sg.RT + 1) * sizeof(T)))) return rc;
-        if ((rc = ensure(h, h->spDS, (size_t)N * sg.RT * sizeof(T)))) return rc;
         if ((rc = ensure(h, h->spRes, (size_t)N * sg.NO * sizeof(T)))) return rc;
         if ((rc = ensure(h, h->epi_part, (size_t)egrid * sizeof(double)))) return rc;
         if ((rc = ensure(h, h->dfc_part, ((size_t)dgrid + 1) * CR * sizeof(double)))) return rc;
-        if ((rc = ensure(h, h->spDf1, (size_t)slabs * sg.RT * sg.D * sizeof(double)))) return rc;
     }
     k_prep<T><<<std::max(1, std::min(64, (g.pf + 255) / 256)), 256, 0, st>>>(theta, g, nn_mask, beta, thr, (T*)h->FtT.p, (double*)h->Ft64.p);
     TR_LAUNCH_CHECK(h);
     const bool vec = vec_ok(X, sg.D, sizeof(T));
     constexpr int VEC = 16 / (int)sizeof(T);
-    if ((rc = vec ? spec_pass1<T, VEC>(h, X, N, st) : spec_pass1<T, 1>(h, X, N, st))) return rc;
+    const double nbias_mult = (double)((sg.Rn > 0 ? 1 : 0) + (sg.Rs > 0 ? 1 : 0));
+    // fit iterations of samples that fit one warp tile: window contraction, epilogue and second-mode gradient in ONE kernel
+    const bool can_fuse = grad && sg.Q <= TRS_MAXQ && sg.D <= 32 * (vec ? VEC : 1);
+    if (h->fused_mode == 1 && grad && !can_fuse)
+        return fail(h, TR_ERR_UNSUPPORTED, "option fused=1: the fused spectral pass needs Q <= %d channels and D <= %d features", TRS_MAXQ, 32 * (vec ? VEC : 1));
+    const bool fuse = can_fuse && h->fused_mode != 0;
+    if (!fuse) {
+        if ((rc = ensure(h, h->spA, (size_t)N * sg.Q * sg.D * sizeof(T)))) return rc;
+        if (grad) {
+            if ((rc = ensure(h, h->spMc, (size_t)N * std::max(1, sg.Rs) * sg.D * sizeof(T)))) return rc;
+            if ((rc = ensure(h, h->spDS, (size_t)N * sg.RT * sizeof(T)))) return rc;
+            if ((rc = ensure(h, h->spDf1, (size_t)slabs * sg.RT * sg.D * sizeof(double)))) return rc;
+        }
+    }
+    int nloss = egrid;
+    if (fuse) {
+        if ((rc = vec ? spec_fused_pass1<T, VEC>(h, X, y, N, theta, w, nbias_mult, gradsum, yhat, &nloss, st)
+                      : spec_fused_pass1<T, 1>(h, X, y, N, theta, w, nbias_mult, gradsum, yhat, &nloss, st))) return rc;
+    } else {
+        if ((rc = vec ? spec_pass1<T, VEC>(h, X, N, st) : spec_pass1<T, 1>(h, X, N, st))) return rc;
+    }
     SpecEpiArgs<T> ea;
     memset(&ea, 0, sizeof(ea));
     ea.A = (const T*)h->spA.p; ea.Ft64 = (const double*)h->Ft64.p; ea.theta = theta; ea.w = w; ea.y = y; ea.N = N; ea.g = sg;
-    ea.nb = (double)((sg.Rn > 0 ? 1 : 0) + (sg.Rs > 0 ? 1 : 0));
+    ea.nb = nbias_mult;
     ea.yhat = yhat;
     if (grad) {
         ea.res = (T*)h->spRes.p; ea.U = (T*)h->spU.p; ea.dS = (T*)h->spDS.p; ea.Mc = (T*)h->spMc.p; ea.DA = (T*)h->spDA.p;
         ea.part = (double*)h->epi_part.p;
     }
-    if (grad || yhat) {
+    if (!fuse && (grad || yhat)) {
         k_spec_epi<T><<<egrid, TR_TPB, 0, st>>>(ea);
         TR_LAUNCH_CHECK(h);
     }
@@ -1189,20 +1255,22 @@ int run_spec(tr_handle* h, const T* X, const T* y, long long N, const T* theta, 
         double* M = (double*)h->dfc_part.p + (size_t)dgrid * CR;
         k_colsum<<<CR, 128, 0, st>>>((const double*)h->dfc_part.p, dgrid, CR, M);
         TR_LAUNCH_CHECK(h);
-        k_spec_scatter<<<1, 256, 0, st>>>(M, (const double*)h->epi_part.p, egrid, sg, ea.nb, gradsum);
+        k_spec_scatter<<<1, 256, 0, st>>>(M, (const double*)h->epi_part.p, nloss, sg, ea.nb, gradsum);
         TR_LAUNCH_CHECK(h);
-        // second-mode factors
-        SpecDf1Args<T> da;
-        da.A = (const T*)h->spA.p; da.Mc = (const T*)h->spMc.p; da.dS = (const T*)h->spDS.p; da.N = N; da.g = sg; da.slabs = slabs;
-        da.part = (double*)h->spDf1.p;
-        k_spec_df1<T><<<dim3((sg.D + TR_TPB - 1) / TR_TPB, slabs), TR_TPB, 0, st>>>(da);
-        TR_LAUNCH_CHECK(h);
-        k_spec_df1_reduce<<<std::max(1, std::min(128, (sg.RT * sg.D + 255) / 256)), 256, 0, st>>>((const double*)h->spDf1.p, slabs, sg, gradsum);
-        TR_LAUNCH_CHECK(h);
+        if (!fuse) {
+            // second-mode factors
+            SpecDf1Args<T> da;
+            da.A = (const T*)h->spA.p; da.Mc = (const T*)h->spMc.p; da.dS = (const T*)h->spDS.p; da.N = N; da.g = sg; da.slabs = slabs;
+            da.part = (double*)h->spDf1.p;
+            k_spec_df1<T><<<dim3((sg.D + TR_TPB - 1) / TR_TPB, slabs), TR_TPB, 0, st>>>(da);
+            TR_LAUNCH_CHECK(h);
+            k_spec_df1_fold<<<sg.RT * sg.D, 128, 0, st>>>((const double*)h->spDf1.p, slabs, sg.RT, sg.D, sg, gradsum);
+            TR_LAUNCH_CHECK(h);
+        }
         // first-mode factors: the second pass over X
         if ((rc = vec ? spec_pass2<T, VEC>(h, X, N, gradsum, st) : spec_pass2<T, 1>(h, X, N, gradsum, st))) return rc;
     }
-    h->info[0] = h->launches; h->info[4] = slabs;
+    h->info[0] = h->launches; h->info[4] = fuse ? 0 : slabs;
     return TR_OK;
 }
 

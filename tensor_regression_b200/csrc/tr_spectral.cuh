@@ -60,6 +60,29 @@ template <typename T> struct SpecVec<T, 1> {
     static __device__ __forceinline__ void ld(const T* p, T (&v)[1]) { v[0] = __ldg(p); }
 };
 
+// a row of QP values (QP a multiple of the 16-byte chunk) from shared memory with 16-byte loads (warp-uniform address: broadcast)
+template <typename T> struct VECG;
+template <> struct VECG<float> {
+    static constexpr int v = 4;
+    template <int QP> static __device__ __forceinline__ void ld(const float* p, float (&o)[QP]) {
+#pragma unroll
+        for (int i = 0; i < QP; i += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(p + i);
+            o[i] = t.x; o[i + 1] = t.y; o[i + 2] = t.z; o[i + 3] = t.w;
+        }
+    }
+};
+template <> struct VECG<double> {
+    static constexpr int v = 2;
+    template <int QP> static __device__ __forceinline__ void ld(const double* p, double (&o)[QP]) {
+#pragma unroll
+        for (int i = 0; i < QP; i += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(p + i);
+            o[i] = t.x; o[i + 1] = t.y;
+        }
+    }
+};
+
 template <typename T>
 __device__ __forceinline__ T spec_G(const T* FtT, const SpecGeo& g, int w, int q) {
     return q < g.Rn ? FtT[g.off[0] + w * g.Rn + q] : FtT[g.off[3] + w * (g.Rs * g.CC) + (q - g.Rn)];
@@ -297,18 +320,6 @@ __global__ void __launch_bounds__(TR_TPB) k_spec_df1(const SpecDf1Args<T> a) {
         if (r < g.RT) a.part[((size_t)slab * g.RT + r) * g.D + d] = acc[r];
 }
 
-// gradsum[Fn1 | Fc1] (row-major (D, Rn) / (D, Rs)) = sum over slabs of part (slabs, RT, D)
-__global__ void k_spec_df1_reduce(const double* __restrict__ part, int slabs, SpecGeo g, double* __restrict__ gradsum) {
-    const int total = g.RT * g.D;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const int r = e / g.D, d = e % g.D;
-        double s = 0.0;
-        for (int b = 0; b < slabs; ++b) s += part[((size_t)b * g.RT + r) * g.D + d];
-        if (r < g.Rn) gradsum[g.off[1] + d * g.Rn + r] = s;
-        else gradsum[g.off[4] + d * g.Rs + (r - g.Rn)] = s;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // pass 2: dG[w,q] = sum_t sum_d X[t,w,d] da[t,q,d] for the channels [q0, q0 + QT).
 // Warp (wt, grp) owns the TRS_WT window rows [wt*8, wt*8+8) and the samples grp, grp + G, ...: per (sample, d-tile) a
@@ -397,21 +408,6 @@ __global__ void __launch_bounds__(TR_TPB) k_spec_grad(const SpecGradArgs<T> a) {
     }
 }
 
-// gradsum[Fn0 | Fc0] = sum over sample groups of part (WTN*Gn, TRS_WT, QT); one thread per (w, q)
-__global__ void k_spec_dg_reduce(const double* __restrict__ part, int WTN, int Gn, int QT, int q0, SpecGeo g,
-                                 double* __restrict__ gradsum) {
-    const int total = g.W * QT;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const int w = e / QT, ql = e % QT, q = q0 + ql;
-        if (q >= g.Q) continue;
-        const int wt = w / TRS_WT, i = w % TRS_WT;
-        double s = 0.0;
-        for (int grp = 0; grp < Gn; ++grp) s += part[(((size_t)grp * WTN + wt) * TRS_WT + i) * QT + ql];
-        if (q < g.Rn) gradsum[g.off[0] + w * g.Rn + q] = s;
-        else gradsum[g.off[3] + w * (g.Rs * g.CC) + (q - g.Rn)] = s;
-    }
-}
-
 // third-mode factors and bias from the (NO, RT + 1) matrix  M[n, c] = wcat_c sum_t res[t,n] U[t,c]  (k_dfc + k_colsum):
 // c < Rn -> dFn2[n,c], c < RT -> dFc2[n, c - Rn], c = RT -> nb * sum_t res[t,n] (bias), and the loss sum
 __global__ void k_spec_scatter(const double* __restrict__ M, const double* __restrict__ losspart, int nloss, SpecGeo g,
@@ -491,5 +487,266 @@ __global__ void __launch_bounds__(TR_TPB) k_spec_pred(const SpecPredArgs<T> a) {
                 a.spec_pred[t * g.NO + n] = (T)(sqrt(acc) + b);
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1 with the per-sample epilogue fused in, for samples whose D features fit ONE warp tile (D <= 32 * VEC) and
+// Q <= TRS_MAXQ channels: the warp that contracted the window axis holds a[t,:,d] of its sample in registers, so the
+// second contraction, the outputs, the residual, ds and da = d loss / d a follow in the same warp — a, m and the
+// second-mode gradient never go through memory.  Per sample the kernel reads X[t] (and y[t]) and writes da[t] (Q / W
+// of the sample), res[t], [s_n | s_s | 1]; the second-mode gradient sum_t ds[t,r] m[t,r,d] accumulates in registers
+// (the lane owns the same d for every sample it sees) and is folded into the warp's double slot every `spc` samples.
+// Channel -> component mapping (rq) is a run-time, warp-uniform table: every register array is indexed statically.
+// ---------------------------------------------------------------------------------------------
+// sqrt(ss) and 1 / sqrt(ss) (0 at ss = 0) with one reciprocal square root: for float the hardware rsqrt (2 ulp) plus one
+// Newton step on the product — well inside the 1e-5 tolerance and an order of magnitude fewer instructions than
+// sqrtf + an IEEE division; exact operations for double
+__device__ __forceinline__ void spec_norm(float ss, float& nrm, float& ri) {
+    float r = ss > 0.0f ? rsqrtf(ss) : 0.0f;
+    r = r * fmaf(-0.5f * ss * r, r, 1.5f);                 // one Newton step: relative error ~1e-7 -> ~1e-14 (then fp32 rounding)
+    ri = r;
+    nrm = ss * r;
+}
+__device__ __forceinline__ void spec_norm(double ss, double& nrm, double& ri) {
+    nrm = sqrt(ss);
+    ri = nrm > 0.0 ? 1.0 / nrm : 0.0;
+}
+
+template <typename T>
+struct SpecFusedArgs {
+    const T* X; const T* y; long long N;
+    const T* FtT; const T* theta; const T* w;
+    SpecGeo g; double nb;
+    T* DA; T* res; T* U; T* yhat;
+    double* df1part;       // (warps, QT, 32 * VEC) doubles: slot of warp (blockIdx * TR_WPB + wid)
+    double* losspart;      // (blocks)
+    long long spc;
+};
+
+template <typename T, int QT, int VEC, int UW>
+__global__ void __launch_bounds__(TR_TPB, 2) k_spec_fused(const SpecFusedArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char tr_smem[];
+    __shared__ double sloss[TR_WPB];
+    const SpecGeo& g = a.g;
+    constexpr int QP = (QT + VECG<T>::v - 1) / VECG<T>::v * VECG<T>::v;      // row stride of sG: whole 16-byte chunks
+    T* sG = reinterpret_cast<T*>(tr_smem);                                   // (W, QP)
+    T* sF2 = sG + (size_t)g.W * QP;                                          // (NO, QT): w_r Fn2[n,r] | Fc2[n,r]
+    T* sB = sF2 + (size_t)g.NO * QT;                                         // (NO): nb * bias
+    for (int i = threadIdx.x; i < g.W * QP; i += TR_TPB) {
+        const int w = i / QP, q = i % QP;
+        sG[i] = q < g.Q ? spec_G(a.FtT, g, w, q) : (T)0;
+    }
+    for (int i = threadIdx.x; i < g.NO * QT; i += TR_TPB) {
+        const int n = i / QT, r = i % QT;
+        T v = (T)0;
+        if (r < g.Rn) v = a.w[r] * a.FtT[g.off[2] + n * g.Rn + r];
+        else if (r < g.RT) v = a.FtT[g.off[5] + n * g.Rs + (r - g.Rn)];
+        sF2[i] = v;
+    }
+    for (int i = threadIdx.x; i < g.NO; i += TR_TPB) sB[i] = (T)(a.nb * (double)a.theta[g.off[6] + i]);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int d0 = lane * VEC;
+    const bool act = d0 < g.D;
+    int rq[QT];                                                              // component of channel q (warp-uniform)
+#pragma unroll
+    for (int q = 0; q < QT; ++q) rq[q] = q < g.Rn ? q : g.Rn + (q - g.Rn) / g.CC;
+    T f1[VEC][QT];                                                           // second-mode factor of component r at the lane's d
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+#pragma unroll
+        for (int r = 0; r < QT; ++r) {
+            T val = (T)0;
+            if (act && r < g.Rn) val = a.FtT[g.off[1] + (d0 + v) * g.Rn + r];
+            else if (act && r < g.RT) val = a.FtT[g.off[4] + (d0 + v) * g.Rs + (r - g.Rn)];
+            f1[v][r] = val;
+        }
+    T accF[VEC][QT];                                                         // sum_t ds[t,r] m[t,r,d] since the last fold
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+#pragma unroll
+        for (int r = 0; r < QT; ++r) accF[v][r] = (T)0;
+    const long long wslot = (long long)blockIdx.x * TR_WPB + wid;
+    double* slot = a.df1part + (size_t)wslot * QT * 32 * VEC;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+#pragma unroll
+        for (int r = 0; r < QT; ++r) slot[(size_t)r * 32 * VEC + d0 + v] = 0.0;
+    double loss = 0.0;
+    long long left = a.spc;
+    const long long wtot = (long long)gridDim.x * TR_WPB;
+    const size_t WD = (size_t)g.W * g.D;
+    for (long long t = wslot; t < a.N; t += wtot) {
+        // targets of this sample: one per lane and round, fetched before the window loop
+        T yv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) yv[k] = (lane + 32 * k < g.NO) ? __ldg(a.y + t * g.NO + lane + 32 * k) : (T)0;
+        T acc[VEC][QT];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+#pragma unroll
+            for (int q = 0; q < QT; ++q) acc[v][q] = (T)0;
+        const T* xp = a.X + (size_t)t * WD + (act ? d0 : 0);
+        for (int w = 0; w < g.W; w += UW) {
+            T x[UW][VEC];
+#pragma unroll
+            for (int u = 0; u < UW; ++u) {
+                if (act && w + u < g.W) XLoad<T, VEC>::ld(xp + (size_t)(w + u) * g.D, x[u]);
+                else {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) x[u][v] = (T)0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UW; ++u) {
+                T gq[QP];
+                VECG<T>::template ld<QP>(sG + (size_t)(w + u < g.W ? w + u : 0) * QP, gq);
+#pragma unroll
+                for (int q = 0; q < QT; ++q) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) acc[v][q] = tr_fma<T>(x[u][v], gq[q], acc[v][q]);
+                }
+            }
+        }
+        // m[v][r]: a itself (normal component) or the norm over the component's complex channels; rinv = 1 / m (0 at 0)
+        T m[VEC][QT], rinv[VEC][QT];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+#pragma unroll
+            for (int r = 0; r < QT; ++r) {
+                T ss = (T)0;
+#pragma unroll
+                for (int q = 0; q < QT; ++q) ss = (rq[q] == r) ? tr_fma<T>(acc[v][q], acc[v][q], ss) : ss;
+                T nrm, ri;
+                spec_norm(ss, nrm, ri);
+                m[v][r] = r < g.Rn ? acc[v][r] : nrm;
+                rinv[v][r] = r < g.Rn ? (T)1 : ri;
+            }
+        // second contraction: s[r] = sum_d m[d,r] F1[d,r]  (lane partial, then an all-reduce over the warp)
+        T s[QT];
+#pragma unroll
+        for (int r = 0; r < QT; ++r) {
+            T p = (T)0;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) p = tr_fma<T>(m[v][r], f1[v][r], p);
+            s[r] = p;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+            for (int r = 0; r < QT; ++r) s[r] += __shfl_xor_sync(TR_FULL, s[r], off);
+        if (a.U && lane <= g.RT) {
+            T uv = (T)1;
+#pragma unroll
+            for (int r = 0; r < QT; ++r) if (r == lane && r < g.RT) uv = s[r];
+            a.U[t * (g.RT + 1) + lane] = uv;
+        }
+        // outputs and residuals: lanes along n; ds[r] = sum_n res[n] F2[n,r]
+        T ds[QT];
+#pragma unroll
+        for (int r = 0; r < QT; ++r) ds[r] = (T)0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int n = lane + 32 * k;
+            if (n < g.NO) {
+                const T* f2 = sF2 + (size_t)n * QT;
+                T yh = sB[n];
+#pragma unroll
+                for (int r = 0; r < QT; ++r) yh = tr_fma<T>(s[r], f2[r], yh);
+                const T rr = yh - yv[k];
+                if (a.yhat) a.yhat[t * g.NO + n] = yh;
+                a.res[t * g.NO + n] = rr;
+                loss += (double)rr * (double)rr;
+#pragma unroll
+                for (int r = 0; r < QT; ++r) ds[r] = tr_fma<T>(rr, f2[r], ds[r]);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+            for (int r = 0; r < QT; ++r) ds[r] += __shfl_xor_sync(TR_FULL, ds[r], off);
+        // second-mode gradient (registers) and da (global)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+#pragma unroll
+            for (int r = 0; r < QT; ++r) accF[v][r] = tr_fma<T>(ds[r], m[v][r], accF[v][r]);
+        // kf[v][r] = ds[r] F1[d,r] (normal) or ds[r] F1[d,r] / m[d,r] (spectral; 0 at m = 0: torch.norm's subgradient);
+        // da of channel q = kf[.][rq[q]] (normal) or kf[.][rq[q]] * a[q] (spectral)
+        T kf[VEC][QT];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+#pragma unroll
+            for (int r = 0; r < QT; ++r) {
+                kf[v][r] = ds[r] * f1[v][r] * rinv[v][r];
+            }
+        if (act) {
+#pragma unroll
+            for (int q = 0; q < QT; ++q) {
+                if (q < g.Q) {
+                    T out[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        T kk = (T)0;
+#pragma unroll
+                        for (int r = 0; r < QT; ++r) kk = (rq[q] == r) ? kf[v][r] : kk;
+                        out[v] = q < g.Rn ? kk : kk * acc[v][q];
+                    }
+                    SpecVec<T, VEC>::st(a.DA + ((size_t)t * g.Q + q) * g.D + d0, out);
+                }
+            }
+        }
+        if (--left == 0) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                for (int r = 0; r < QT; ++r) {
+                    slot[(size_t)r * 32 * VEC + d0 + v] += (double)accF[v][r];
+                    accF[v][r] = (T)0;
+                }
+            left = a.spc;
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+#pragma unroll
+        for (int r = 0; r < QT; ++r) slot[(size_t)r * 32 * VEC + d0 + v] += (double)accF[v][r];
+    loss = warp_sum(loss);
+    if (lane == 0) sloss[wid] = loss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < TR_WPB; ++i) tot += sloss[i];
+        a.losspart[blockIdx.x] = tot;
+    }
+}
+
+// gradsum[Fn1 | Fc1] = sum over the warps' slots of df1part (warps, QT, TILE); one block per (r, d)
+__global__ void __launch_bounds__(128) k_spec_df1_fold(const double* __restrict__ part, int nslots, int QT, int TILE, SpecGeo g,
+                                                       double* __restrict__ gradsum) {
+    __shared__ double sbuf[32];
+    const int r = blockIdx.x / g.D, d = blockIdx.x % g.D;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nslots; b += blockDim.x) s += part[((size_t)b * QT + r) * TILE + d];
+    s = block_sum(s, sbuf);
+    if (threadIdx.x == 0) {
+        if (r < g.Rn) gradsum[g.off[1] + d * g.Rn + r] = s;
+        else gradsum[g.off[4] + d * g.Rs + (r - g.Rn)] = s;
+    }
+}
+
+// gradsum[Fn0 | Fc0] from the gradient pass's slots (WTN * Gn, TRS_WT, QT): one block per (w, q)
+__global__ void __launch_bounds__(128) k_spec_dg_fold(const double* __restrict__ part, int WTN, int Gn, int QT, int q0, SpecGeo g,
+                                                      double* __restrict__ gradsum) {
+    __shared__ double sbuf[32];
+    const int w = blockIdx.x / QT, ql = blockIdx.x % QT, q = q0 + ql;
+    if (q >= g.Q) return;
+    const int wt = w / TRS_WT, i = w % TRS_WT;
+    double s = 0.0;
+    for (int grp = threadIdx.x; grp < Gn; grp += blockDim.x) s += part[(((size_t)grp * WTN + wt) * TRS_WT + i) * QT + ql];
+    s = block_sum(s, sbuf);
+    if (threadIdx.x == 0) {
+        if (q < g.Rn) gradsum[g.off[0] + w * g.Rn + q] = s;
+        else gradsum[g.off[3] + w * (g.Rs * g.CC) + (q - g.Rn)] = s;
     }
 }

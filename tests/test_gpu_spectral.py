@@ -58,6 +58,9 @@ def test_spectral_closure_vs_reference_golden(path):
     beta, thr = m._sp()
     yhat = torch.empty_like(yd)
     gs = eng.fwd_grad(Xd, yd, m.theta, m.weights, m._mask(), beta, thr, yhat=yhat)
+    launches_fused = eng.launch_info()['launches']
+    q = int(z['rank_normal']) + int(z['rank_spectral']) * (int(z['n_complex_dim']) + 1)
+    assert (eng.launch_info()['df1_slabs'] == 0) == (q <= 8)           # fused first pass whenever the channels fit
     n_total = y.numel()
     grad, loss = eng.finish(gs, 2.0 / n_total, 1.0 / n_total, m.theta, lam, m._mask(), beta, thr)
     assert rel(yhat, z['y_hat']) < tol
@@ -73,9 +76,17 @@ def test_spectral_closure_vs_reference_golden(path):
         if n:
             assert rel(grad[off:off + n], z[name].reshape(-1)) < 10 * tol, name
         off += n
-    # forward-only entry point gives the same prediction
+    # forward-only entry point (separate epilogue kernel, sums in double) gives the same prediction
     out = eng.forward(Xd, m.theta, m.weights, m._mask(), beta, thr, want=('yhat',))
-    assert torch.equal(out['yhat'], yhat)
+    assert rel(out['yhat'], yhat) < tol
+    # ... and so does the unfused fit path (window contraction, epilogue and second-mode gradient as separate kernels)
+    eng.set_option('fused', 0)
+    yhat0 = torch.empty_like(yd)
+    gs0 = eng.fwd_grad(Xd, yd, m.theta, m.weights, m._mask(), beta, thr, yhat=yhat0)
+    grad0, loss0 = eng.finish(gs0, 2.0 / n_total, 1.0 / n_total, m.theta, lam, m._mask(), beta, thr)
+    assert eng.launch_info()['df1_slabs'] > 0 and eng.launch_info()['launches'] >= launches_fused
+    assert rel(yhat0, z['y_hat']) < tol and rel(grad0, want) < tol
+    assert abs(loss0[1].item() - float(z['loss'])) < tol * abs(float(z['loss']))
 
 
 @pytest.mark.parametrize('path', SPEC, ids=[os.path.basename(p)[:-4] for p in SPEC])
