@@ -49,6 +49,50 @@ def test_product_never_imports_oracle():
             assert 'oracle' not in src.replace('no CPU', ''), fn
 
 
+def test_spectral_signatures_match_reference():
+    """spectral_tensor_regression.py: names, positional order and defaults of everything the drop-in re-exposes —
+    hard-coded from the reference (spectral:17, 62, 118, 168, 284, 339, 393, 425-437, 541-550, 652-659, 895, 966)
+    and, where /root/reference is present, compared with the reference module itself."""
+    import inspect
+    from tensor_regression_b200 import spectral_tensor_regression as SPR
+
+    def names(f):
+        return [p.name for p in inspect.signature(f).parameters.values() if p.kind != p.KEYWORD_ONLY]
+
+    model_sig = ['X', 'Bcp', 'weights', 'non_negative', 'bias', 'softplus_kwargs']
+    assert names(SPR.make_BcpInit) == ['B_dims', 'rank', 'non_negative', 'complex_dims', 'scale', 'device', 'dtype']
+    for fn in (SPR.lin_model, SPR.spectral_model, SPR.stepwise_latents_model, SPR.stepwise_spectral_model):
+        assert names(fn) == model_sig
+    C = SPR.CP_linear_regression
+    assert names(C.__init__)[1:] == ['X_shape', 'y_shape', 'dtype', 'rank_normal', 'rank_spectral', 'non_negative', 'weights',
+                                     'Bcp_init', 'Bcp_init_scale', 'n_complex_dim', 'bias_init', 'device', 'softplus_kwargs']
+    assert names(C.fit)[1:] == ['X', 'y', 'lambda_L2', 'max_iter', 'tol', 'patience', 'verbose',
+                                'running_loss_logging_interval', 'LBFGS_kwargs']
+    assert names(C.fit_Adam)[1:] == ['X', 'y', 'lambda_L2', 'max_iter', 'tol', 'patience', 'verbose', 'plotting_interval',
+                                     'Adam_kwargs']
+    assert names(C.predict)[1:] == ['X', 'Bcp', 'device', 'plot_pref']
+    assert names(C.predict_latents)[1:] == ['X', 'Bcp', 'device', 'plot_pref']
+    d = inspect.signature(C.__init__).parameters
+    assert d['rank_normal'].default == 1 and d['rank_spectral'].default == 1 and d['n_complex_dim'].default == 0
+    d = inspect.signature(C.fit_Adam).parameters
+    assert d['lambda_L2'].default == 0.01 and d['max_iter'].default == 1000 and d['plotting_interval'].default == 100
+    for name in ['return_Bcp_final', 'detach_Bcp', 'get_params', 'set_params', 'display_params', 'plot_outputs']:
+        assert hasattr(C, name)
+    from oracle import ref_loader
+    if ref_loader.available():
+        R = ref_loader.spectral()
+        for fn in ['make_BcpInit', 'non_neg_fn', 'lin_model', 'spectral_model', 'stepwise_latents_model',
+                   'stepwise_spectral_model', 'L2_penalty']:
+            assert names(getattr(SPR, fn)) == names(getattr(R, fn)), fn
+        for meth in ['__init__', 'fit', 'fit_Adam', 'predict', 'predict_latents']:
+            ours, ref = getattr(C, meth), getattr(R.CP_linear_regression, meth)
+            assert names(ours) == names(ref), meth
+            po, pr = inspect.signature(ours).parameters, inspect.signature(ref).parameters
+            for k in pr:
+                if k not in ('self', 'device') and pr[k].default is not inspect.Parameter.empty:
+                    assert po[k].default == pr[k].default or (po[k].default is pr[k].default), (meth, k)
+
+
 def test_signatures_match_reference():
     import inspect
     from tensor_regression_b200 import standard_tensor_regression as STR
