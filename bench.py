@@ -513,7 +513,8 @@ def roofline_of(res, wk, x_bytes, ratios):
     else:
         dom = 'k_grad' if grad_ms >= fwd_ms else 'k_fwd'
         if wk.kind == 'spec':
-            dom = 'k_spec_grad' if grad_ms >= fwd_ms else 'k_spec_fwd'
+            first = 'k_spec_fused' if res['launch_info'].get('df1_slabs') == 0 else 'k_spec_fwd'
+            dom = 'k_spec_grad' if grad_ms >= fwd_ms else first
         dom_ms, alg, phys = max(grad_ms, fwd_ms), x_bytes, x_bytes
         extra = {'k_fwd_ms': fwd_ms, 'k_grad_ms': grad_ms,
                  'k_fwd_gbs': x_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None,

@@ -1150,7 +1150,8 @@ int spec_fused_pass1(tr_handle* h, const T* X, const T* y, long long N, const T*
     auto kern = spec_fused_kernel<T, VEC>(QT);
     constexpr int CH = 16 / (int)sizeof(T);
     const int QP = (QT + CH - 1) / CH * CH;                                   // row stride of the G table (whole 16-byte chunks)
-    const size_t smem = ((size_t)sg.W * QP + (size_t)sg.NO * QT + sg.NO) * sizeof(T);
+    const size_t smem = ((((size_t)sg.W * QP + (size_t)sg.NO * QT + sg.NO) * sizeof(T) + 15) / 16) * 16
+                        + (size_t)TR_WPB * QT * 32 * VEC * sizeof(T);                 // tables + the warps' scratch
     int rc, occ = 0;
     if ((rc = occupancy(h, kern, smem, &occ))) return rc;
     const int grid = (int)std::max<long long>(1, std::min<long long>((N + TR_WPB - 1) / TR_WPB, (long long)h->sms * occ));

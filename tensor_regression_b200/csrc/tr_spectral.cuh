@@ -83,6 +83,21 @@ template <> struct VECG<double> {
     }
 };
 
+// VEC consecutive, aligned elements of shared memory
+template <typename T, int VEC> struct SpecSm;
+template <> struct SpecSm<float, 4> {
+    static __device__ __forceinline__ void st(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+    static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+};
+template <> struct SpecSm<double, 2> {
+    static __device__ __forceinline__ void st(double* p, const double (&v)[2]) { *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]); }
+    static __device__ __forceinline__ void ld(const double* p, double (&v)[2]) { const double2 t = *reinterpret_cast<const double2*>(p); v[0] = t.x; v[1] = t.y; }
+};
+template <typename T> struct SpecSm<T, 1> {
+    static __device__ __forceinline__ void st(T* p, const T (&v)[1]) { p[0] = v[0]; }
+    static __device__ __forceinline__ void ld(const T* p, T (&v)[1]) { v[0] = p[0]; }
+};
+
 template <typename T>
 __device__ __forceinline__ T spec_G(const T* FtT, const SpecGeo& g, int w, int q) {
     return q < g.Rn ? FtT[g.off[0] + w * g.Rn + q] : FtT[g.off[3] + w * (g.Rs * g.CC) + (q - g.Rn)];
@@ -497,7 +512,8 @@ __global__ void __launch_bounds__(TR_TPB) k_spec_pred(const SpecPredArgs<T> a) {
 // second-mode gradient never go through memory.  Per sample the kernel reads X[t] (and y[t]) and writes da[t] (Q / W
 // of the sample), res[t], [s_n | s_s | 1]; the second-mode gradient sum_t ds[t,r] m[t,r,d] accumulates in registers
 // (the lane owns the same d for every sample it sees) and is folded into the warp's double slot every `spc` samples.
-// Channel -> component mapping (rq) is a run-time, warp-uniform table: every register array is indexed statically.
+// The channel sums go through a per-warp shared-memory scratch once, so the channels of a component are addressed at run
+// time (q = Rn + r CC + c) while every register array is indexed statically by the component r.
 // ---------------------------------------------------------------------------------------------
 // sqrt(ss) and 1 / sqrt(ss) (0 at ss = 0) with one reciprocal square root: for float the hardware rsqrt (2 ulp) plus one
 // Newton step on the product — well inside the 1e-5 tolerance and an order of magnitude fewer instructions than
@@ -533,6 +549,10 @@ __global__ void __launch_bounds__(TR_TPB, 2) k_spec_fused(const SpecFusedArgs<T>
     T* sG = reinterpret_cast<T*>(tr_smem);                                   // (W, QP)
     T* sF2 = sG + (size_t)g.W * QP;                                          // (NO, QT): w_r Fn2[n,r] | Fc2[n,r]
     T* sB = sF2 + (size_t)g.NO * QT;                                         // (NO): nb * bias
+    // per-warp scratch (QT, 32 * VEC): the window sums a[q][d] of the warp's current sample, so that the channels of a
+    // component can be addressed at run time (q = Rn + r * CC + c) while every register array stays statically indexed
+    T* sA = reinterpret_cast<T*>(tr_smem + ((((size_t)g.W * QP + (size_t)g.NO * QT + g.NO) * sizeof(T) + 15) / 16) * 16)
+            + (size_t)(threadIdx.x >> 5) * QT * 32 * VEC + (threadIdx.x & 31) * VEC;
     for (int i = threadIdx.x; i < g.W * QP; i += TR_TPB) {
         const int w = i / QP, q = i % QP;
         sG[i] = q < g.Q ? spec_G(a.FtT, g, w, q) : (T)0;
@@ -549,9 +569,6 @@ __global__ void __launch_bounds__(TR_TPB, 2) k_spec_fused(const SpecFusedArgs<T>
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int d0 = lane * VEC;
     const bool act = d0 < g.D;
-    int rq[QT];                                                              // component of channel q (warp-uniform)
-#pragma unroll
-    for (int q = 0; q < QT; ++q) rq[q] = q < g.Rn ? q : g.Rn + (q - g.Rn) / g.CC;
     T f1[VEC][QT];                                                           // second-mode factor of component r at the lane's d
 #pragma unroll
     for (int v = 0; v < VEC; ++v)
@@ -609,20 +626,40 @@ __global__ void __launch_bounds__(TR_TPB, 2) k_spec_fused(const SpecFusedArgs<T>
                 }
             }
         }
+        // window sums -> the warp's scratch (one 16-byte store per channel; read back only by the lane that wrote them)
+#pragma unroll
+        for (int q = 0; q < QT; ++q) {
+            T out[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) out[v] = acc[v][q];
+            SpecSm<T, VEC>::st(sA + (size_t)q * 32 * VEC, out);
+        }
+        __syncwarp();
         // m[v][r]: a itself (normal component) or the norm over the component's complex channels; rinv = 1 / m (0 at 0)
         T m[VEC][QT], rinv[VEC][QT];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v)
+        for (int r = 0; r < QT; ++r) {
+            if (r < g.Rn) {
 #pragma unroll
-            for (int r = 0; r < QT; ++r) {
-                T ss = (T)0;
+                for (int v = 0; v < VEC; ++v) { m[v][r] = acc[v][r]; rinv[v][r] = (T)1; }
+            } else if (r < g.RT) {
+                T ss[VEC];
 #pragma unroll
-                for (int q = 0; q < QT; ++q) ss = (rq[q] == r) ? tr_fma<T>(acc[v][q], acc[v][q], ss) : ss;
-                T nrm, ri;
-                spec_norm(ss, nrm, ri);
-                m[v][r] = r < g.Rn ? acc[v][r] : nrm;
-                rinv[v][r] = r < g.Rn ? (T)1 : ri;
+                for (int v = 0; v < VEC; ++v) ss[v] = (T)0;
+                const T* ap = sA + (size_t)(g.Rn + (r - g.Rn) * g.CC) * 32 * VEC;
+                for (int c = 0; c < g.CC; ++c) {
+                    T av[VEC];
+                    SpecSm<T, VEC>::ld(ap + (size_t)c * 32 * VEC, av);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) ss[v] = tr_fma<T>(av[v], av[v], ss[v]);
+                }
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) spec_norm(ss[v], m[v][r], rinv[v][r]);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { m[v][r] = (T)0; rinv[v][r] = (T)0; }
             }
+        }
         // second contraction: s[r] = sum_d m[d,r] F1[d,r]  (lane partial, then an all-reduce over the warp)
         T s[QT];
 #pragma unroll
@@ -666,36 +703,30 @@ __global__ void __launch_bounds__(TR_TPB, 2) k_spec_fused(const SpecFusedArgs<T>
         for (int off = 16; off >= 1; off >>= 1)
 #pragma unroll
             for (int r = 0; r < QT; ++r) ds[r] += __shfl_xor_sync(TR_FULL, ds[r], off);
-        // second-mode gradient (registers) and da (global)
+        // second-mode gradient (registers) and da (global):
+        // da of a normal channel r = ds[r] F1[d,r]; of the channels (r, c) of a spectral component = ds[r] F1[d,r] / m[d,r] * a
 #pragma unroll
-        for (int v = 0; v < VEC; ++v)
+        for (int r = 0; r < QT; ++r) {
+            T kf[VEC];
 #pragma unroll
-            for (int r = 0; r < QT; ++r) accF[v][r] = tr_fma<T>(ds[r], m[v][r], accF[v][r]);
-        // kf[v][r] = ds[r] F1[d,r] (normal) or ds[r] F1[d,r] / m[d,r] (spectral; 0 at m = 0: torch.norm's subgradient);
-        // da of channel q = kf[.][rq[q]] (normal) or kf[.][rq[q]] * a[q] (spectral)
-        T kf[VEC][QT];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v)
-#pragma unroll
-            for (int r = 0; r < QT; ++r) {
-                kf[v][r] = ds[r] * f1[v][r] * rinv[v][r];
+            for (int v = 0; v < VEC; ++v) {
+                accF[v][r] = tr_fma<T>(ds[r], m[v][r], accF[v][r]);
+                kf[v] = ds[r] * f1[v][r] * rinv[v][r];
             }
-        if (act) {
+            if (act && r < g.Rn) {
+                SpecVec<T, VEC>::st(a.DA + ((size_t)t * g.Q + r) * g.D + d0, kf);
+            } else if (act && r < g.RT) {
+                const int qb = g.Rn + (r - g.Rn) * g.CC;
+                for (int c = 0; c < g.CC; ++c) {
+                    T av[VEC];
+                    SpecSm<T, VEC>::ld(sA + (size_t)(qb + c) * 32 * VEC, av);
 #pragma unroll
-            for (int q = 0; q < QT; ++q) {
-                if (q < g.Q) {
-                    T out[VEC];
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        T kk = (T)0;
-#pragma unroll
-                        for (int r = 0; r < QT; ++r) kk = (rq[q] == r) ? kf[v][r] : kk;
-                        out[v] = q < g.Rn ? kk : kk * acc[v][q];
-                    }
-                    SpecVec<T, VEC>::st(a.DA + ((size_t)t * g.Q + q) * g.D + d0, out);
+                    for (int v = 0; v < VEC; ++v) av[v] *= kf[v];
+                    SpecVec<T, VEC>::st(a.DA + ((size_t)t * g.Q + qb + c) * g.D + d0, av);
                 }
             }
         }
+        __syncwarp();
         if (--left == 0) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v)
