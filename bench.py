@@ -546,11 +546,20 @@ def multi_gpu_check(rank, world, device, dist, E, STR, MTR):
     ok = True
     cases = [('std_f32_single_pass', 'std', (64, 64, 32), 8, 0, torch.float32, 1, 1e-6),
              ('std_f64_two_pass', 'std', (16, 16, 16, 32), 12, 0, torch.float64, 0, 1e-12),
-             ('mn_f32', 'mn', (100, 50, 20), 6, 10, torch.float32, -1, 1e-6)]
+             ('mn_f32', 'mn', (100, 50, 20), 6, 10, torch.float32, -1, 1e-6),
+             # spectral variant: dims = (W, D), R = (rank_normal, rank_spectral, complex columns), C = outputs
+             ('spec_f32', 'spec', (16, 128), (2, 2, 2), 3, torch.float32, -1, 1e-6),
+             ('spec_f64', 'spec', (12, 40), (1, 2, 3), 2, torch.float64, -1, 1e-12)]
     for name, kind, dims, R, C, dt, fused, tol in cases:
         n_glob = 24 * world + 5                         # uneven split on purpose
         nn = [False] * (len(dims) + 1)
-        if kind == 'std':
+        if kind == 'spec':
+            from oracle import tr_oracle_spectral as OS
+            from tensor_regression_b200 import spectral_tensor_regression as SPR
+            rn, rs, cc = R
+            X, y = OS.synth(n_glob, dims[0], dims[1], C, rn, rs, cc, 4244, dtype=dt)
+            B0 = OS.init(dims[0], dims[1], C, rn, rs, cc, dtype=dt, seed=11)
+        elif kind == 'std':
             X, y, _ = O.synth_std(n_glob, dims, R, 4242, dtype=dt)
             B0 = O.init_std(dims, R, nn, dtype=dt)
         else:
@@ -559,7 +568,14 @@ def multi_gpu_check(rank, world, device, dist, E, STR, MTR):
         lo, hi = E.shard_bounds(n_glob, rank, world)
 
         def fit(Xs, ys, group):
-            if kind == 'std':
+            if kind == 'spec':
+                m = SPR.CP_linear_regression((Xs.shape[0], *dims), (Xs.shape[0], C), dtype=dt, rank_normal=R[0],
+                                             rank_spectral=R[1], n_complex_dim=R[2] - 1,
+                                             Bcp_init=[[b.clone() for b in B0[0]], [b.clone() for b in B0[1]]],
+                                             device=device, shard_group=group)
+                m.fit_Adam(Xs.to(device), ys.to(device), lambda_L2=LAMBDA, max_iter=K, tol=0.0, patience=10 ** 9,
+                           Adam_kwargs=ADAM)
+            elif kind == 'std':
                 m = STR.CP_linear_regression((Xs.shape[0], *dims), dtype=dt, rank=R, Bcp_init=[b.clone() for b in B0],
                                              device=device, shard_group=group)
                 if fused >= 0:
