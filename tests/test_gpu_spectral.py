@@ -233,3 +233,62 @@ def test_spectral_convergence_rule_and_nan_stop(capsys):
     conv = m2.fit_Adam(Xn.to(DEV), y.to(DEV), max_iter=50, Adam_kwargs={'lr': 1e-3})
     assert conv is False and len(m2.loss_running) == 1
     assert 'Loss is NaN. Stopping.' in capsys.readouterr().out
+
+
+@pytest.mark.parametrize('shape', [
+    (1, 1, 1, 1, 1, 0, 1, torch.float64),          # one sample, one element, normal part only
+    (3, 5, 7, 40, 2, 1, 2, torch.float32),         # more outputs than lanes in a warp; fewer samples than warps
+    (9, 3, 300, 2, 0, 2, 3, torch.float32),        # spectral part only, D spans three warp tiles (separate-kernel path)
+    (17, 65, 4, 3, 2, 2, 2, torch.float64),        # window longer than the batch of rows, tiny D
+], ids=lambda s: 'x'.join(str(v) for v in s[:7]))
+def test_spectral_edge_geometries(shape):
+    from tensor_regression_b200 import spectral_tensor_regression as SPR
+    T, W, D, NO, rn, rs, cc, dtype = shape
+    g = torch.Generator().manual_seed(3)
+    X = torch.randn((T, W, D), generator=g, dtype=dtype)
+    y = torch.randn((T, NO), generator=g, dtype=dtype)
+    Bn, Bc = OS.init(W, D, NO, rn, rs, cc, dtype=dtype, seed=17)
+    nn = [False, True, False]
+    w = np.linspace(0.8, 1.2, rn + rs)
+    bias = torch.linspace(-0.2, 0.2, NO, dtype=dtype)
+    both = rn > 0 and rs > 0
+    if NO == 1 and both:
+        pytest.skip('the reference expression broadcasts (T,) + (T,1) to (T,T) for one output')
+    r = OS.loss_grad(X.double(), y.double(), [b.double() for b in Bn], [b.double() for b in Bc], bias.double(),
+                     torch.tensor(w, dtype=torch.float64), nn, 0.01)
+    m = SPR.CP_linear_regression(X.shape, y.shape, dtype=dtype, rank_normal=rn, rank_spectral=rs, non_negative=nn,
+                                 weights=w, Bcp_init=[Bn, Bc], n_complex_dim=cc - 1, device=DEV)
+    m.bias.copy_(bias.to(DEV))
+    eng = m._engine()
+    beta, thr = m._sp()
+    yhat = torch.empty((T, NO), dtype=dtype, device=DEV)
+    gs = eng.fwd_grad(X.to(DEV), y.to(DEV), m.theta, m.weights, m._mask(), beta, thr, yhat=yhat)
+    grad, loss = eng.finish(gs, 2.0 / y.numel(), 1.0 / y.numel(), m.theta, 0.01, m._mask(), beta, thr)
+    tol = 1e-10 if dtype == torch.float64 else 1e-5
+    assert rel(yhat.reshape(-1), r['y_hat'].reshape(-1)) < tol
+    assert abs(loss[1].item() - r['loss']) < tol * abs(r['loss'])
+    want = torch.cat([t.reshape(-1) for t in r['grad_n'] + r['grad_c']] + [r['dbias'].reshape(-1)])
+    assert rel(grad, want) < tol
+
+
+def test_spectral_empty_batch_and_limits():
+    import ctypes
+    from tensor_regression_b200 import _lib, engine
+    eng = engine.SpectralEngine(6, 8, 2, 1, 1, 2, torch.float32, DEV)
+    th = torch.zeros(eng.P, device=DEV)
+    w = torch.ones(2, device=DEV)
+    gs = torch.full((eng.n_gradsum,), 7.0, dtype=torch.float64, device=DEV)
+    X = torch.empty((0, 6, 8), device=DEV)
+    y = torch.empty((0, 2), device=DEV)
+    rc = _lib.lib.tr_spec_fwd_grad(eng._h, None, None, 0, th.data_ptr(), w.data_ptr(), 0, 50.0, 1.0, gs.data_ptr(), None, None)
+    assert rc == 0 and float(gs.abs().sum()) == 0.0          # N = 0: the sums are zero
+    h = ctypes.c_void_p()
+    assert _lib.lib.tr_spec_create(ctypes.byref(h), 0, 6, 8, 2, 9, 8, 1, 0) != 0        # 17 components
+    assert b'rank' in _lib.lib.tr_last_error(None)
+    assert _lib.lib.tr_spec_create(ctypes.byref(h), 0, 6, 8, 2, 0, 0, 1, 0) != 0        # no component at all
+    assert _lib.lib.tr_spec_create(ctypes.byref(h), 0, 6, 8, 200, 1, 1, 1, 0) != 0      # too many outputs
+    # tr_spec_* refuses a standard / multinomial handle
+    e2 = engine.Engine((6, 8), 2, 0, torch.float32, DEV)
+    rc = _lib.lib.tr_spec_fwd_grad(e2._h, X.data_ptr(), y.data_ptr(), 0, th.data_ptr(), w.data_ptr(), 0, 50.0, 1.0,
+                                   gs.data_ptr(), None, None)
+    assert rc != 0 and b'tr_spec_create' in _lib.lib.tr_last_error(e2._h)
