@@ -503,11 +503,12 @@ def roofline_of(res, wk, x_bytes, ratios):
         # reading X from HBM once -> "achieved" exceeds the HBM peak by design; frac_physical and traffic show the
         # bytes that really cross the HBM interface
         path = res['launch_info']['path']
-        dom = 'k_flow' if path.startswith('single-launch dataflow') else ('k_fused_mn' if wk.kind == 'mn' else 'k_fused_std')
+        dom = 'k_flow' if path.startswith('single-launch dataflow') else (
+            'k_fused_mn' if wk.kind == 'mn' else ('k_spec_single' if wk.kind == 'spec' else 'k_fused_std'))
         dom_ms, alg, phys = fused_ms, 2 * x_bytes, x_bytes
         extra = {'k_single_ms': fused_ms,
                  'note': 'single-pass kernel: X is read from HBM once, the second (gradient) pass is served from '
-                         'cluster shared memory; frac counts the 2-pass algorithmic bytes (the contract of SURVEY 8d), '
+                         'cluster shared memory (spectral variant: from the SM\'s own shared memory); frac counts the 2-pass algorithmic bytes (the contract of SURVEY 8d), '
                          'frac_physical the bytes that cross the HBM interface',
                  'share_of_step': {dom: fused_ms / ms_per_step}}
     else:

@@ -15,6 +15,7 @@
 #include "tr_dispatch.h"
 #include "tr_small.cuh"
 #include "tr_spectral.cuh"
+#include "tr_spectral_single.h"
 #include "tr_fused.cuh"
 #include "tr_fused_mn.h"
 
@@ -114,6 +115,9 @@ struct tr_handle {
     int kind = 0;
     SpecGeo sg;
     Buf spA, spDA, spMc, spU, spDS, spRes, spPart, spDf1;
+    int spec_single = -1;               // single-pass spectral kernel (tr_spectral_single.cuh): -1 auto, 0 never, 1 always (error when not eligible)
+    int spec_single_ns = 0;             // testing knob (option "spec_single_ns"): cap on its shared-memory stages
+    int smem_optin = 0;                 // cudaDevAttrMaxSharedMemoryPerBlockOptin (queried at first use)
 };
 
 // trainable scalars after the factor entries: the scalar bias of the standard model, the (n_out) bias of the spectral one
@@ -1177,6 +1181,72 @@ int spec_fused_pass1(tr_handle* h, const T* X, const T* y, long long N, const T*
     return TR_OK;
 }
 
+// ---- single-pass spectral kernel (tr_spectral_single.cuh): plan + launch ----
+struct SpecSinglePlan { bool ok; int NS; size_t smem; unsigned stage_bytes; const void* kern; };
+
+template <typename T>
+int spec_single_plan(tr_handle* h, const void* X, SpecSinglePlan* sp) {
+    const SpecGeo& sg = h->sg;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    sp->ok = false; sp->NS = 0; sp->smem = 0; sp->kern = nullptr;
+    if (!vec_ok(X, sg.D, sizeof(T)) || sg.Q > TRS_MAXQ || sg.D > 32 * VEC || sg.W > TRSS_NG * TRS_WT) return TR_OK;
+    const size_t stage = (size_t)sg.W * sg.D * sizeof(T);
+    if (stage % 16 != 0 || stage > (1u << 20)) return TR_OK;
+    if (h->smem_optin == 0) TR_CUDA(h, cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    int NS = TRSS_MAX_NS;
+    if (h->spec_single_ns > 0) NS = std::min(NS, h->spec_single_ns);
+    while (NS >= 2 && spec_single_layout<T>(sg, sg.Q, VEC, NS, stage).total > (size_t)h->smem_optin) --NS;
+    if (NS < 2) return TR_OK;
+    sp->kern = sizeof(T) == 4 ? trss_kernel_f32(sg.Q) : trss_kernel_f64(sg.Q);
+    if (!sp->kern) return TR_OK;
+    sp->ok = true; sp->NS = NS; sp->stage_bytes = (unsigned)stage;
+    sp->smem = spec_single_layout<T>(sg, sg.Q, VEC, NS, stage).total;
+    return TR_OK;
+}
+
+// forward + epilogue + both factor gradients of the spectral model with X read once; fills res, U, gradsum[F*0 | F*1], loss parts
+template <typename T>
+int spec_single_pass(tr_handle* h, const SpecSinglePlan& sp, const T* X, const T* y, long long N, const T* theta, const T* w,
+                     double nb, double* gradsum, T* yhat, int* nloss, cudaStream_t st) {
+    const SpecGeo& sg = h->sg;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int QT = sg.Q, TILE = 32 * VEC;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(N, (long long)h->sms));
+    const int WTN = (sg.W + TRS_WT - 1) / TRS_WT;
+    const size_t nslots = (size_t)grid * TRSS_NF;
+    int rc;
+    if ((rc = ensure(h, h->spDf1, nslots * QT * TILE * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->spPart, (size_t)grid * WTN * TRS_WT * QT * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->epi_part, (size_t)grid * sizeof(double)))) return rc;
+    SpecSingleArgs<T> fa;
+    fa.X = X; fa.y = y; fa.N = N; fa.FtT = (const T*)h->FtT.p; fa.theta = theta; fa.w = w; fa.g = sg; fa.nb = nb;
+    fa.res = (T*)h->spRes.p; fa.U = (T*)h->spU.p; fa.yhat = yhat;
+    fa.df1part = (double*)h->spDf1.p; fa.dgpart = (double*)h->spPart.p; fa.losspart = (double*)h->epi_part.p;
+    const long long per = (N + grid - 1) / grid;
+    fa.spc = sizeof(T) == 4 ? std::max<long long>(1, std::min<long long>(per, 2048)) : std::max<long long>(1, per);
+    fa.NS = sp.NS; fa.stage_bytes = sp.stage_bytes;
+    fa.piece = (unsigned)std::max(16, h->fused_piece / 16 * 16);
+    fa.trace = nullptr;
+#ifdef TRSS_TRACE
+    if ((rc = ensure(h, h->trace, (size_t)TRSS_TRACE_N * TRSS_TRACE_EV * sizeof(long long)))) return rc;
+    TR_CUDA(h, cudaMemsetAsync(h->trace.p, 0, (size_t)TRSS_TRACE_N * TRSS_TRACE_EV * sizeof(long long), st));
+    fa.trace = (long long*)h->trace.p;
+#endif
+    if ((rc = raise_smem_limit(h, sp.kern, sp.smem))) return rc;
+    if (h->prof) { rc = prof_fold(h, false); if (rc) return rc; TR_CUDA(h, cudaEventRecord(h->ev[4], st)); }
+    void* kargs[] = {(void*)&fa};
+    TR_CUDA(h, cudaLaunchKernel(sp.kern, dim3(grid), dim3(TRSS_NT), kargs, sp.smem, st));
+    TR_LAUNCH_CHECK(h);
+    if (h->prof) { TR_CUDA(h, cudaEventRecord(h->ev[5], st)); h->ev_set[2] = true; }
+    k_spec_df1_fold<<<sg.RT * sg.D, 128, 0, st>>>((const double*)h->spDf1.p, (int)nslots, QT, TILE, sg, gradsum);
+    TR_LAUNCH_CHECK(h);
+    k_spec_dg_fold<<<sg.W * QT, 128, 0, st>>>((const double*)h->spPart.p, WTN, grid, QT, 0, sg, gradsum);
+    TR_LAUNCH_CHECK(h);
+    *nloss = grid;
+    h->info[1] = grid; h->info[2] = grid; h->info[3] = 1; h->info[5] = sp.NS; h->info[6] = QT; h->info[7] = VEC;
+    return TR_OK;
+}
+
 // forward (+ gradient when y and gradsum are given) of the spectral model
 template <typename T>
 int run_spec(tr_handle* h, const T* X, const T* y, long long N, const T* theta, const T* w, uint32_t nn_mask, double beta,
@@ -1193,7 +1263,6 @@ int run_spec(tr_handle* h, const T* X, const T* y, long long N, const T* theta, 
     const int CR = sg.NO * (sg.RT + 1);
     const int slabs = (int)std::max<long long>(1, std::min<long long>(N / 32 + 1, std::max<long long>(1, (long long)h->sms * 4 / ((sg.D + TR_TPB - 1) / TR_TPB))));
     if (grad) {
-        if ((rc = ensure(h, h->spDA, (size_t)N * sg.Q * sg.D * sizeof(T)))) return rc;
         if ((rc = ensure(h, h->spU, (size_t)N * (sg.RT + 1) * sizeof(T) + (size_t)(sg.RT + 1) * sizeof(T)))) return rc;
         if ((rc = ensure(h, h->spRes, (size_t)N * sg.NO * sizeof(T)))) return rc;
         if ((rc = ensure(h, h->epi_part, (size_t)egrid * sizeof(double)))) return rc;
@@ -1208,7 +1277,15 @@ int run_spec(tr_handle* h, const T* X, const T* y, long long N, const T* theta, 
     const bool can_fuse = grad && sg.Q <= TRS_MAXQ && sg.D <= 32 * (vec ? VEC : 1);
     if (h->fused_mode == 1 && grad && !can_fuse)
         return fail(h, TR_ERR_UNSUPPORTED, "option fused=1: the fused spectral pass needs Q <= %d channels and D <= %d features", TRS_MAXQ, 32 * (vec ? VEC : 1));
-    const bool fuse = can_fuse && h->fused_mode != 0;
+    // ... and when a ring of whole samples fits the shared memory of an SM, the first-mode gradient as well: X is read once
+    SpecSinglePlan sp;
+    sp.ok = false;
+    if (grad && can_fuse && h->spec_single != 0) { if ((rc = spec_single_plan<T>(h, X, &sp))) return rc; }
+    if (h->spec_single == 1 && grad && !sp.ok)
+        return fail(h, TR_ERR_UNSUPPORTED, "option spec_single=1: the single-pass spectral kernel needs 16-byte rows, Q <= %d channels, D <= %d features, "
+                    "W <= %d window rows and two whole samples in shared memory", TRS_MAXQ, 32 * VEC, TRSS_NG * TRS_WT);
+    const bool single = sp.ok && (h->spec_single == 1 || (h->fused_mode != 0 && N >= 16LL * h->sms));
+    const bool fuse = single || (can_fuse && h->fused_mode != 0);
     if (!fuse) {
         if ((rc = ensure(h, h->spA, (size_t)N * sg.Q * sg.D * sizeof(T)))) return rc;
         if (grad) {
@@ -1217,8 +1294,13 @@ int run_spec(tr_handle* h, const T* X, const T* y, long long N, const T* theta, 
             if ((rc = ensure(h, h->spDf1, (size_t)slabs * sg.RT * sg.D * sizeof(double)))) return rc;
         }
     }
+    if (grad && !single) {
+        if ((rc = ensure(h, h->spDA, (size_t)N * sg.Q * sg.D * sizeof(T)))) return rc;
+    }
     int nloss = egrid;
-    if (fuse) {
+    if (single) {
+        if ((rc = spec_single_pass<T>(h, sp, X, y, N, theta, w, nbias_mult, gradsum, yhat, &nloss, st))) return rc;
+    } else if (fuse) {
         if ((rc = vec ? spec_fused_pass1<T, VEC>(h, X, y, N, theta, w, nbias_mult, gradsum, yhat, &nloss, st)
                       : spec_fused_pass1<T, 1>(h, X, y, N, theta, w, nbias_mult, gradsum, yhat, &nloss, st))) return rc;
     } else {
@@ -1269,9 +1351,11 @@ int run_spec(tr_handle* h, const T* X, const T* y, long long N, const T* theta, 
             TR_LAUNCH_CHECK(h);
         }
         // first-mode factors: the second pass over X
-        if ((rc = vec ? spec_pass2<T, VEC>(h, X, N, gradsum, st) : spec_pass2<T, 1>(h, X, N, gradsum, st))) return rc;
+        if (!single) {
+            if ((rc = vec ? spec_pass2<T, VEC>(h, X, N, gradsum, st) : spec_pass2<T, 1>(h, X, N, gradsum, st))) return rc;
+        }
     }
-    h->info[0] = h->launches; h->info[4] = fuse ? 0 : slabs;
+    h->info[0] = h->launches; h->info[4] = single ? -1 : (fuse ? 0 : slabs);
     return TR_OK;
 }
 
@@ -1335,6 +1419,7 @@ int tr_create(tr_handle** out, int dtype, int k, const int64_t* dims, int R, int
     h->l2_bytes = (size_t)prop.l2CacheSize;
     if (const char* ev = getenv("TR_B200_FUSED")) h->fused_mode = atoi(ev) < 0 ? -1 : (atoi(ev) > 0 ? 1 : 0);
     if (const char* ev = getenv("TR_B200_FUSED_NS")) h->fused_ns = atoi(ev);
+    if (const char* ev = getenv("TR_B200_SPEC_SINGLE")) h->spec_single = atoi(ev) < 0 ? -1 : (atoi(ev) > 0 ? 1 : 0);
     if (const char* ev = getenv("TR_B200_FUSED_PACE")) h->fused_pace = atoi(ev);
     if (const char* ev = getenv("TR_B200_FUSED_PIECE")) { const int v = atoi(ev); if (v >= 16 && v % 16 == 0) h->fused_piece = v; }
     *out = h;
@@ -1754,6 +1839,12 @@ int tr_set_option(tr_handle* h, const char* name, int64_t value) {
         h->flow_window_mb = value;
         return TR_OK;
     }
+    if (strcmp(name, "spec_single") == 0) {
+        if (value < -1 || value > 1) return fail(h, TR_ERR_INVALID, "option spec_single: -1 (auto), 0 (never), 1 (always the single-pass spectral kernel)");
+        h->spec_single = (int)value;
+        return TR_OK;
+    }
+    if (strcmp(name, "spec_single_ns") == 0) { h->spec_single_ns = (int)value; return TR_OK; }
     if (strcmp(name, "fused_pace") == 0) { h->fused_pace = (int)value; return TR_OK; }
     if (strcmp(name, "fused_ns") == 0) { h->fused_ns = (int)value; h->occ_clusters.clear(); return TR_OK; }
     if (strcmp(name, "fused_cl") == 0) {
@@ -1814,6 +1905,16 @@ int tr_lbfgs_gtd(tr_handle* h, const void* g, const void* d, double* scal2, void
     return TR_OK;
 }
 
+#if defined(TRSS_TRACE) && !defined(TRM_TRACE)
+// debug builds only (not part of include/tr_b200.h): the timeline of the last k_spec_single launch
+int tr_debug_trace(tr_handle* h, long long* out, int n) {
+    if (!h || !out || !h->trace.p) return TR_ERR_INVALID;
+    DeviceGuard dg(h->device);
+    TR_CUDA(h, cudaDeviceSynchronize());
+    TR_CUDA(h, cudaMemcpy(out, h->trace.p, (size_t)std::min(n, TRSS_TRACE_N * TRSS_TRACE_EV) * sizeof(long long), cudaMemcpyDeviceToHost));
+    return TR_OK;
+}
+#endif
 #ifdef TRM_TRACE
 // debug builds only (not part of include/tr_b200.h): the timeline of the last k_fused_mn launch, TRM_TRACE_N x TRM_TRACE_EV stamps
 int tr_debug_trace(tr_handle* h, long long* out, int n) {

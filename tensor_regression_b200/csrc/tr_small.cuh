@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(TR_TPB) k_dfc(const T* __restrict__ dZ, const 
 }
 
 // out[j] = sum_b part[b, j] for a (rows, cols) double matrix; one block per column (deterministic)
+#ifndef TR_TEMPLATES_ONLY
 __global__ void __launch_bounds__(128) k_colsum(const double* __restrict__ part, int rows, int cols,
                                                  double* __restrict__ out) {
     __shared__ double sbuf[32];
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(128) k_colsum(const double* __restrict__ part,
     s = block_sum(s, sbuf);
     if (threadIdx.x == 0) out[j] = s;
 }
+#endif
 
 // part[b] = { sum res, sum res^2 } over block b's grid-stride share of a residual vector (fp64)
 template <typename T>
@@ -123,6 +125,7 @@ struct MtArgs {
     double* gradsum;
 };
 
+#ifndef TR_TEMPLATES_ONLY
 __global__ void __launch_bounds__(TR_TPB) k_mttkrp(const MtArgs a) {
     __shared__ double sbuf[32];
     const int k = a.geo.k, R = a.geo.R;
@@ -177,6 +180,7 @@ __global__ void __launch_bounds__(TR_TPB) k_mttkrp(const MtArgs a) {
         }
     }
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Finish: normalisation, softplus chain rule, penalty gradient and value (single block).

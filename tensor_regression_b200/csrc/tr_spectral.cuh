@@ -425,6 +425,7 @@ __global__ void __launch_bounds__(TR_TPB) k_spec_grad(const SpecGradArgs<T> a) {
 
 // third-mode factors and bias from the (NO, RT + 1) matrix  M[n, c] = wcat_c sum_t res[t,n] U[t,c]  (k_dfc + k_colsum):
 // c < Rn -> dFn2[n,c], c < RT -> dFc2[n, c - Rn], c = RT -> nb * sum_t res[t,n] (bias), and the loss sum
+#ifndef TR_TEMPLATES_ONLY
 __global__ void k_spec_scatter(const double* __restrict__ M, const double* __restrict__ losspart, int nloss, SpecGeo g,
                                double nb, double* __restrict__ gradsum) {
     const int total = g.NO * (g.RT + 1);
@@ -441,6 +442,7 @@ __global__ void k_spec_scatter(const double* __restrict__ M, const double* __res
         gradsum[g.off[6] + g.NO] = s;
     }
 }
+#endif
 
 // wcat = [ rank weights of the normal components | 1 for the spectral components and the bias column ]
 template <typename T>
@@ -753,6 +755,7 @@ __global__ void __launch_bounds__(TR_TPB, 2) k_spec_fused(const SpecFusedArgs<T>
 }
 
 // gradsum[Fn1 | Fc1] = sum over the warps' slots of df1part (warps, QT, TILE); one block per (r, d)
+#ifndef TR_TEMPLATES_ONLY
 __global__ void __launch_bounds__(128) k_spec_df1_fold(const double* __restrict__ part, int nslots, int QT, int TILE, SpecGeo g,
                                                        double* __restrict__ gradsum) {
     __shared__ double sbuf[32];
@@ -765,8 +768,10 @@ __global__ void __launch_bounds__(128) k_spec_df1_fold(const double* __restrict_
         else gradsum[g.off[4] + d * g.Rs + (r - g.Rn)] = s;
     }
 }
+#endif
 
 // gradsum[Fn0 | Fc0] from the gradient pass's slots (WTN * Gn, TRS_WT, QT): one block per (w, q)
+#ifndef TR_TEMPLATES_ONLY
 __global__ void __launch_bounds__(128) k_spec_dg_fold(const double* __restrict__ part, int WTN, int Gn, int QT, int q0, SpecGeo g,
                                                       double* __restrict__ gradsum) {
     __shared__ double sbuf[32];
@@ -781,3 +786,4 @@ __global__ void __launch_bounds__(128) k_spec_dg_fold(const double* __restrict__
         else gradsum[g.off[3] + w * (g.Rs * g.CC) + (q - g.Rn)] = s;
     }
 }
+#endif

@@ -346,8 +346,12 @@ class SpectralEngine(Engine):
         keys = ['launches', 'grid_fwd', 'grid_grad', 'tiles_per_sample', 'df1_slabs', 'groups_grad', 'channels_per_pass',
                 'vector_width']
         d = dict(zip(keys, [int(v) for v in info]))
-        d['path'] = ('two-pass, epilogue fused into the first (window contraction + norm epilogue + second-mode gradient in one kernel)'
-                     if d['df1_slabs'] == 0 else 'two-pass (window contraction, epilogue and second-mode gradient as separate kernels)')
+        if d['df1_slabs'] < 0:
+            d['stages'] = d.pop('groups_grad')
+            d['path'] = 'single-pass (ring of whole samples in shared memory: window contraction, norm epilogue and both factor gradients in one kernel)'
+        else:
+            d['path'] = ('two-pass, epilogue fused into the first (window contraction + norm epilogue + second-mode gradient in one kernel)'
+                         if d['df1_slabs'] == 0 else 'two-pass (window contraction, epilogue and second-mode gradient as separate kernels)')
         return d
 
 

@@ -292,3 +292,102 @@ def test_spectral_empty_batch_and_limits():
     rc = _lib.lib.tr_spec_fwd_grad(e2._h, X.data_ptr(), y.data_ptr(), 0, th.data_ptr(), w.data_ptr(), 0, 50.0, 1.0,
                                    gs.data_ptr(), None, None)
     assert rc != 0 and b'tr_spec_create' in _lib.lib.tr_last_error(e2._h)
+
+
+# ---------------------------------------------------------------------------------------------
+# single-pass kernel (tr_spectral_single.cuh): ring of whole samples in shared memory, X read once
+# ---------------------------------------------------------------------------------------------
+def _spectral_model(shape, seed=4242):
+    from tensor_regression_b200 import spectral_tensor_regression as SPR
+    T, W, D, NO, rn, rs, cc, dtype = shape
+    X, y = OS.synth(T, W, D, NO, rn, rs, cc, seed, dtype=dtype)
+    Bn, Bc = OS.init(W, D, NO, rn, rs, cc, dtype=dtype, seed=99)
+    nn = [True, False, False]
+    w = np.linspace(0.5, 1.5, rn + rs)
+    bias = 0.1 * torch.arange(1, NO + 1, dtype=dtype)
+    m = SPR.CP_linear_regression(X.shape, y.shape, dtype=dtype, rank_normal=rn, rank_spectral=rs, non_negative=nn,
+                                 weights=w, Bcp_init=[Bn, Bc], n_complex_dim=cc - 1, device=DEV)
+    m.bias.copy_(bias.to(DEV))
+    return m, X, y, Bn, Bc, bias, w, nn
+
+
+@pytest.mark.parametrize('shape', [
+    # T, W, D, n_out, rank_normal, rank_spectral, complex, dtype
+    (700, 64, 128, 4, 2, 2, 2, torch.float32),     # the bench workload's sample shape: 8 full row tiles, full warp tile
+    (301, 50, 100, 3, 2, 2, 2, torch.float32),     # 25 active lanes, last row tile holds 2 rows, batch remainder of 2 rows
+    (257, 13, 32, 5, 1, 1, 3, torch.float32),      # short window (one batch + remainder), 8 active lanes
+    (3, 64, 128, 2, 2, 2, 2, torch.float32),       # fewer samples than forward warps
+    (1, 9, 16, 2, 1, 1, 2, torch.float32),         # one sample
+    (200, 33, 36, 2, 3, 1, 2, torch.float64),      # fp64: 2 elements per lane, 18 active lanes
+    (150, 24, 64, 100, 2, 1, 2, torch.float64),    # more outputs than lanes
+    (90, 40, 60, 3, 0, 2, 4, torch.float64),       # spectral part only, four complex columns (8 channels)
+    (120, 16, 128, 3, 8, 0, 1, torch.float32),     # normal part only, 8 channels
+], ids=lambda s: 'x'.join(str(v) for v in s[:7]) + ('_f64' if s[7] == torch.float64 else '_f32'))
+@pytest.mark.parametrize('stages', [0, 2, 3])
+def test_spectral_single_pass_vs_oracle_and_two_pass(shape, stages):
+    T, W, D, NO, rn, rs, cc, dtype = shape
+    m, X, y, Bn, Bc, bias, w, nn = _spectral_model(shape)
+    lam = 0.01
+    r = OS.loss_grad(X.double(), y.double(), [b.double() for b in Bn], [b.double() for b in Bc], bias.double(),
+                     torch.tensor(w, dtype=torch.float64), nn, lam)
+    eng = m._engine()
+    beta, thr = m._sp()
+    Xd, yd = X.to(DEV), y.to(DEV)
+    eng.set_option('spec_single', 1)
+    eng.set_option('spec_single_ns', stages)
+    yhat = torch.full_like(yd, float('nan'))
+    gs = eng.fwd_grad(Xd, yd, m.theta, m.weights, m._mask(), beta, thr, yhat=yhat).clone()
+    info = eng.launch_info()
+    assert info['path'].startswith('single-pass') and info['stages'] >= 2
+    if stages:
+        assert info['stages'] <= stages
+    grad, loss = eng.finish(gs, 2.0 / y.numel(), 1.0 / y.numel(), m.theta, lam, m._mask(), beta, thr)
+    tol = 1e-10 if dtype == torch.float64 else 1e-5
+    assert rel(yhat.reshape(-1), r['y_hat'].reshape(-1)) < tol
+    assert abs(loss[1].item() - r['loss']) < tol * abs(r['loss'])
+    want = torch.cat([g.reshape(-1) for g in r['grad_n'] + r['grad_c']] + [r['dbias'].reshape(-1)])
+    assert rel(grad, want) < tol
+    off = 0
+    for blk in r['grad_n'] + r['grad_c'] + [r['dbias']]:
+        if blk.numel():
+            assert rel(grad[off:off + blk.numel()], blk.reshape(-1)) < 10 * tol
+        off += blk.numel()
+    # relaunch: bit-identical
+    gs2 = eng.fwd_grad(Xd, yd, m.theta, m.weights, m._mask(), beta, thr)
+    assert torch.equal(gs, gs2)
+    # the two-pass path on the same inputs
+    eng.set_option('spec_single', 0)
+    gs0 = eng.fwd_grad(Xd, yd, m.theta, m.weights, m._mask(), beta, thr)
+    assert not eng.launch_info()['path'].startswith('single-pass')
+    assert rel(gs, gs0) < (1e-12 if dtype == torch.float64 else 2e-6)
+
+
+@pytest.mark.parametrize('path', SPEC, ids=[os.path.basename(p)[:-4] for p in SPEC])
+def test_spectral_single_pass_fit_adam_vs_reference_golden(path):
+    """20 Adam iterations of the reference's fit_Adam on the single-pass kernel against the unmodified reference's outputs."""
+    z, X, y, Bn, Bc, w, nn, lam = case(path)
+    f64 = X.dtype == torch.float64
+    q = int(z['rank_normal']) + int(z['rank_spectral']) * (int(z['n_complex_dim']) + 1)
+    vec = 2 if f64 else 4
+    if q > 8 or X.shape[2] > 32 * vec or X.shape[2] % vec or X.shape[1] > 64:
+        pytest.skip('geometry outside the single-pass kernel (runs on the two-pass path)')
+    m = model_of(z, X, y, Bn, Bc, w, nn)
+    m._engine().set_option('spec_single', 1)
+    m.fit_Adam(X.to(DEV), y.to(DEV), lambda_L2=lam, max_iter=20, tol=1e-50, patience=100, verbose=False, Adam_kwargs=ADAM)
+    assert m._engine().launch_info()['path'].startswith('single-pass')
+    assert rel(m.loss_running, z['adam_loss_running']) < (1e-9 if f64 else 1e-5)
+    ftol = 1e-9 if f64 else 1e-4
+    for i in range(3):
+        assert rel(m.Bcp_n[i], z[f'adam_Bn_{i}']) < ftol
+        assert rel(m.Bcp_c[i], z[f'adam_Bc_{i}']) < ftol
+    assert rel(m.bias, z['adam_bias']) < ftol
+
+
+def test_spectral_single_pass_refuses_geometry_loudly():
+    from tensor_regression_b200._lib import TRError
+    m, X, y, *_ = _spectral_model((20, 70, 64, 2, 1, 1, 2, torch.float32))        # 70 window rows > 64
+    eng = m._engine()
+    eng.set_option('spec_single', 1)
+    beta, thr = m._sp()
+    with pytest.raises(TRError, match='spec_single'):
+        eng.fwd_grad(X.to(DEV), y.to(DEV), m.theta, m.weights, m._mask(), beta, thr)
