@@ -1182,6 +1182,16 @@ int spec_fused_pass1(tr_handle* h, const T* X, const T* y, long long N, const T*
 }
 
 // ---- single-pass spectral kernel (tr_spectral_single.cuh): plan + launch ----
+// first-mode table G[w][q] in the layout the kernel keeps in shared memory: rows of `stride` values (TrssG)
+template <typename T>
+__global__ void k_spec_pack_g(const T* __restrict__ FtT, SpecGeo g, int QT, int stride, T* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.W * stride; i += gridDim.x * blockDim.x) {
+        const int w = i / stride, e = i % stride;
+        const int q = trss_g_twice<T>() ? e / 2 : e;
+        out[i] = (q < QT && q < g.Q) ? spec_G(FtT, g, w, q) : (T)0;
+    }
+}
+
 struct SpecSinglePlan { bool ok; int NS; size_t smem; unsigned stage_bytes; const void* kern; };
 
 template <typename T>
@@ -1195,7 +1205,7 @@ int spec_single_plan(tr_handle* h, const void* X, SpecSinglePlan* sp) {
     if (h->smem_optin == 0) TR_CUDA(h, cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     int NS = TRSS_MAX_NS;
     if (h->spec_single_ns > 0) NS = std::min(NS, h->spec_single_ns);
-    while (NS >= 2 && spec_single_layout<T>(sg, sg.Q, VEC, NS, stage).total > (size_t)h->smem_optin) --NS;
+    while (NS >= 2 && spec_single_layout<T>(sg, sg.Q, VEC, NS, stage).total + 1024 > (size_t)h->smem_optin) --NS;
     if (NS < 2) return TR_OK;
     sp->kern = sizeof(T) == 4 ? trss_kernel_f32(sg.Q) : trss_kernel_f64(sg.Q);
     if (!sp->kern) return TR_OK;
@@ -1233,11 +1243,19 @@ int spec_single_pass(tr_handle* h, const SpecSinglePlan& sp, const T* X, const T
     fa.trace = (long long*)h->trace.p;
 #endif
     if ((rc = raise_smem_limit(h, sp.kern, sp.smem))) return rc;
-    if (h->prof) { rc = prof_fold(h, false); if (rc) return rc; TR_CUDA(h, cudaEventRecord(h->ev[4], st)); }
-    void* kargs[] = {(void*)&fa};
-    TR_CUDA(h, cudaLaunchKernel(sp.kern, dim3(grid), dim3(TRSS_NT), kargs, sp.smem, st));
-    TR_LAUNCH_CHECK(h);
-    if (h->prof) { TR_CUDA(h, cudaEventRecord(h->ev[5], st)); h->ev_set[2] = true; }
+    {
+        // first-mode table in the kernel's layout (every block copies it into its shared memory)
+        const int stride = trss_g_stride<T>(QT);
+        if ((rc = ensure(h, h->f3_stage, (size_t)sg.W * stride * sizeof(T)))) return rc;
+        k_spec_pack_g<T><<<4, 256, 0, st>>>((const T*)h->FtT.p, sg, QT, stride, (T*)h->f3_stage.p);
+        TR_LAUNCH_CHECK(h);
+        fa.gtab = (const T*)h->f3_stage.p;
+        if (h->prof) { rc = prof_fold(h, false); if (rc) return rc; TR_CUDA(h, cudaEventRecord(h->ev[4], st)); }
+        void* kargs[] = {(void*)&fa};
+        TR_CUDA(h, cudaLaunchKernel(sp.kern, dim3(grid), dim3(TRSS_NT), kargs, sp.smem, st));
+        TR_LAUNCH_CHECK(h);
+        if (h->prof) { TR_CUDA(h, cudaEventRecord(h->ev[5], st)); h->ev_set[2] = true; }
+    }
     k_spec_df1_fold<<<sg.RT * sg.D, 128, 0, st>>>((const double*)h->spDf1.p, (int)nslots, QT, TILE, sg, gradsum);
     TR_LAUNCH_CHECK(h);
     k_spec_dg_fold<<<sg.W * QT, 128, 0, st>>>((const double*)h->spPart.p, WTN, grid, QT, 0, sg, gradsum);
@@ -1284,7 +1302,7 @@ int run_spec(tr_handle* h, const T* X, const T* y, long long N, const T* theta, 
     if (h->spec_single == 1 && grad && !sp.ok)
         return fail(h, TR_ERR_UNSUPPORTED, "option spec_single=1: the single-pass spectral kernel needs 16-byte rows, Q <= %d channels, D <= %d features, "
                     "W <= %d window rows and two whole samples in shared memory", TRS_MAXQ, 32 * VEC, TRSS_NG * TRS_WT);
-    const bool single = sp.ok && (h->spec_single == 1 || (h->fused_mode != 0 && N >= 16LL * h->sms));
+    const bool single = sp.ok && (h->spec_single == 1 || (h->fused_mode != 0 && N >= 4LL * h->sms));
     const bool fuse = single || (can_fuse && h->fused_mode != 0);
     if (!fuse) {
         if ((rc = ensure(h, h->spA, (size_t)N * sg.Q * sg.D * sizeof(T)))) return rc;

@@ -18,12 +18,23 @@
 // No block-wide barrier in the sample loop; every hand-off is an mbarrier.  da, a and m never touch global memory; the
 // kernel writes res[t], [s | 1] (third-mode factors / bias, k_dfc) and its partial sums.  Deterministic: fixed orders,
 // one owner per slot, no atomics.  Eligible when the sample fits one warp tile (D <= 32 * VEC, 16-byte rows),
-// Q <= TRS_MAXQ, W <= 8 * NG and at least three stages fit (tr_api.cu: spec_single_plan).
+// Q <= TRS_MAXQ, W <= 8 * NG and at least two stages fit (tr_api.cu: spec_single_plan).
+//
+// Each role is a separate (not inlined) device function: the register allocation of one role does not see the other
+// roles' live ranges (as one function body the kernel spilled loop-carried values of every role, and with ~220 KB of
+// the SM's memory configured as shared memory the remaining L1 does not hold the spill slots of 13+ warps).
 #pragma once
 #include "tr_spectral.cuh"
 #include "tr_fused.cuh"
 
-#define TRSS_NF 4                                      // forward warps
+#ifndef TRSS_NF
+#define TRSS_NF 6                                      // forward warps
+#endif
+#ifndef TRSS_FFMA2
+#define TRSS_FFMA2 0                                   // float window loop: 1 = FFMA2 over element pairs (G values stored twice), 0 = scalar FMAs
+#endif
+// every wait carries a suspend-time hint: a warp that waits for microseconds is parked by the hardware instead of polling
+#define TRSS_WAIT(bar, parity) trf::mbar_wait_hint(bar, parity)
 #define TRSS_NG 8                                      // gradient warps (TRS_WT window rows each)
 #define TRSS_NT ((TRSS_NF + TRSS_NG + 1) * 32)         // + the producer warp
 #define TRSS_MAX_NS 8
@@ -43,6 +54,7 @@ struct SpecSingleArgs {
     unsigned stage_bytes;  // W * D * sizeof(T), multiple of 16
     unsigned piece;        // bytes per bulk-copy instruction
     long long* trace;      // debug timeline of block 0 (builds with -DTRSS_TRACE only), else null
+    const T* gtab;         // first-mode table in the kernel's layout (W rows of TrssG::STRIDE values), packed by k_spec_pack_g
 };
 
 // debug timeline: clock64 stamp of event e of the block's sample j (block 0, TRSS_TRACE_N samples from TRSS_TRACE_J0)
@@ -53,22 +65,80 @@ struct SpecSingleArgs {
 #define TRSS_STAMP(j, e)                                                                                     \
     do {                                                                                                     \
         if (blockIdx.x == 0 && lane == 0 && (j) >= TRSS_TRACE_J0 && (j) < TRSS_TRACE_J0 + TRSS_TRACE_N)        \
-            a.trace[((j) - TRSS_TRACE_J0) * TRSS_TRACE_EV + (e)] = clock64();                                \
+            trace[((j) - TRSS_TRACE_J0) * TRSS_TRACE_EV + (e)] = clock64();                                  \
     } while (0)
 #else
 #define TRSS_STAMP(j, e) do {} while (0)
 #endif
+
+// ---------------------------------------------------------------------------------------------
+// rows of the first-mode table G in shared memory (packed by k_spec_pack_g, copied in by the kernel's prologue) and the
+// row update acc[q][v] += x[v] * G[w][q].  Build option -DTRSS_FFMA2=1 (float): every value stored twice, (g, g), so that
+// one FFMA2 (fma.rn.f32x2) updates the element pair (v, v+1) of a 16-byte load with no register shuffling — same bits,
+// half the FMA issue slots, but three 16-byte row loads instead of two: measured 5 % slower on spec1, not the default.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int QT> struct TrssG {
+    static constexpr int CH = 16 / (int)sizeof(T);
+    static constexpr int STRIDE = (QT + CH - 1) / CH * CH;
+    template <int VEC>
+    static __device__ __forceinline__ void fma_row(T (&acc)[QT][VEC], const T (&x)[VEC], const T* row) {
+        T gq[STRIDE];
+        VECG<T>::template ld<STRIDE>(row, gq);
+#pragma unroll
+        for (int q = 0; q < QT; ++q)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[q][v] = tr_fma<T>(x[v], gq[q], acc[q][v]);
+    }
+};
+#if TRSS_FFMA2
+template <int QT> struct TrssG<float, QT> {
+    static constexpr int STRIDE = (2 * QT + 3) / 4 * 4;
+    template <int VEC>
+    static __device__ __forceinline__ void fma_row(float (&acc)[QT][VEC], const float (&x)[VEC], const float* row) {
+        static_assert(VEC == 4, "float rows are 16-byte chunks");
+        float gq[STRIDE];
+        VECG<float>::template ld<STRIDE>(row, gq);
+#pragma unroll
+        for (int q = 0; q < QT; ++q) {
+            tr_ffma2(acc[q][0], acc[q][1], x[0], x[1], gq[2 * q], gq[2 * q + 1]);
+            tr_ffma2(acc[q][2], acc[q][3], x[2], x[3], gq[2 * q], gq[2 * q + 1]);
+        }
+    }
+};
+#endif
+// row stride of the table for a run-time channel count (host side and the packing kernel); float values stored twice
+template <typename T> __host__ __device__ inline bool trss_g_twice() { return sizeof(T) == 4 && TRSS_FFMA2; }
+template <typename T> __host__ __device__ inline int trss_g_stride(int QT) {
+    const int ch = 16 / (int)sizeof(T);
+    return trss_g_twice<T>() ? (2 * QT + 3) / 4 * 4 : (QT + ch - 1) / ch * ch;
+}
+
+// shared-memory loads that keep their program order (the compiler otherwise sinks the batch of row loads of the window
+// loop next to their first use, which exposes the full shared-memory latency once per row)
+template <typename T, int VEC> struct TrssLd;
+template <> struct TrssLd<float, 4> {
+    static __device__ __forceinline__ void ld(uint32_t addr, float (&x)[4]) {
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]) : "r"(addr));
+    }
+};
+template <> struct TrssLd<double, 2> {
+    static __device__ __forceinline__ void ld(uint32_t addr, double (&x)[2]) {
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x[0]), "=d"(x[1]) : "r"(addr));
+    }
+};
+
+// 1 / m for m > 0: correctly rounded reciprocal for float, an exact division for double
+__device__ __forceinline__ float spec_recip(float m) { const float r = __frcp_rn(m); return r; }
+__device__ __forceinline__ double spec_recip(double m) { return 1.0 / m; }
 
 struct SpecSingleLayout { size_t tab, sF1, sDA, stage, total; };
 
 // shared-memory carve-up, the same on host (size) and device (pointers)
 template <typename T>
 __host__ __device__ inline SpecSingleLayout spec_single_layout(const SpecGeo& g, int QT, int VEC, int NS, size_t stage_bytes) {
-    const int CH = 16 / (int)sizeof(T);
-    const int QP = (QT + CH - 1) / CH * CH;
     SpecSingleLayout L;
     L.tab = TRSS_HDR;
-    const size_t tabB = ((size_t)g.W * QP + (size_t)g.NO * QT + g.NO) * sizeof(T);
+    const size_t tabB = ((size_t)g.W * trss_g_stride<T>(QT) + (size_t)g.NO * QT + g.NO) * sizeof(T);
     L.sF1 = L.tab + (tabB + 15) / 16 * 16;                                   // (QT, 32 * VEC): second-mode factor rows
     L.sDA = L.sF1 + (size_t)QT * 32 * VEC * sizeof(T);
     L.stage = (L.sDA + (size_t)NS * QT * 32 * VEC * sizeof(T) + 127) / 128 * 128;
@@ -76,350 +146,413 @@ __host__ __device__ inline SpecSingleLayout spec_single_layout(const SpecGeo& g,
     return L;
 }
 
+// what every role needs: views into the block's dynamic shared memory, derived from the launch arguments in every role
+// function itself (pointers handed over through memory would lose their address space: generic loads instead of LDS)
+template <typename T>
+struct TrssCtx {
+    uint64_t* full; uint64_t* ready; uint64_t* empty; double* sloss;
+    T* sG; T* sF2; T* sB; T* sF1; T* sDA; unsigned char* stages;
+    long long nj;          // samples of this block: t = blockIdx.x + j * gridDim.x
+};
+
+extern __shared__ __align__(128) unsigned char trss_smem[];
+
 template <typename T, int QT, int VEC>
-__global__ void __launch_bounds__(TRSS_NT, 1) k_spec_single(const SpecSingleArgs<T> a) {
-    extern __shared__ __align__(128) unsigned char trss_smem[];
-    unsigned char* const tr_smem = trss_smem;
-    const SpecGeo& g = a.g;
-    constexpr int QP = (QT + VECG<T>::v - 1) / VECG<T>::v * VECG<T>::v;
-    constexpr int TILE = 32 * VEC;
-    const int NS = a.NS;
-    const SpecSingleLayout L = spec_single_layout<T>(g, QT, VEC, NS, a.stage_bytes);
+__device__ __forceinline__ TrssCtx<T> trss_ctx(const SpecGeo& g, int NS, unsigned stage_bytes, long long N) {
+    const SpecSingleLayout L = spec_single_layout<T>(g, QT, VEC, NS, stage_bytes);
+    TrssCtx<T> c;
     // full[(round & 1) * MAX_NS + s]: the bytes of the stage's sample of that round landed.  Two barriers per stage: a forward
     // warp may start waiting for sample j while sample j - NS (same stage, previous round) is still on its way; with one
     // barrier its parity wait would alias to the round before that.  With two, the barrier's previous use is sample
     // j - 2 NS, whose landing precedes the issue of the load the warp's previous sample came with.
-    uint64_t* full = reinterpret_cast<uint64_t*>(tr_smem);
-    uint64_t* ready = full + 2 * TRSS_MAX_NS;                                  // [NS] da of the sample is in shared memory
-    uint64_t* empty = ready + TRSS_MAX_NS;                                   // [NS] gradient warps are done with the stage
-    double* sloss = reinterpret_cast<double*>(empty + TRSS_MAX_NS);          // [NF]
-    T* sG = reinterpret_cast<T*>(tr_smem + L.tab);                           // (W, QP)
-    T* sF2 = sG + (size_t)g.W * QP;                                          // (NO, QT): w_r Fn2[n,r] | Fc2[n,r]
-    T* sB = sF2 + (size_t)g.NO * QT;                                         // (NO): nb * bias
-    T* sF1 = reinterpret_cast<T*>(tr_smem + L.sF1);                          // (QT, TILE): F1[d, r] of component r (0 beyond D / RT)
-    T* sDA = reinterpret_cast<T*>(tr_smem + L.sDA);                          // (NS, QT, TILE): a, then da of the stage's sample
-    unsigned char* stages = tr_smem + L.stage;
+    c.full = reinterpret_cast<uint64_t*>(trss_smem);
+    c.ready = c.full + 2 * TRSS_MAX_NS;                                      // [NS] da of the sample is in shared memory
+    c.empty = c.ready + TRSS_MAX_NS;                                         // [NS] gradient warps are done with the stage
+    c.sloss = reinterpret_cast<double*>(c.empty + TRSS_MAX_NS);              // [NF]
+    c.sG = reinterpret_cast<T*>(trss_smem + L.tab);                          // (W, TrssG::STRIDE)
+    c.sF2 = c.sG + (size_t)g.W * TrssG<T, QT>::STRIDE;   // (NO, QT): w_r Fn2[n,r] | Fc2[n,r]
+    c.sB = c.sF2 + (size_t)g.NO * QT;                                        // (NO): nb * bias
+    c.sF1 = reinterpret_cast<T*>(trss_smem + L.sF1);                         // (QT, TILE): F1[d, r] of component r (0 beyond D / RT)
+    c.sDA = reinterpret_cast<T*>(trss_smem + L.sDA);                         // (NS, QT, TILE): a, then da of the stage's sample
+    c.stages = trss_smem + L.stage;
+    const long long grid = gridDim.x;
+    // the block's samples: t = blockIdx.x + j * grid, j < nj (strided: all SMs sweep one moving window of X)
+    c.nj = (long long)blockIdx.x < N ? (N - blockIdx.x + grid - 1) / grid : 0;
+    return c;
+}
 
+// ---------------- producer (one lane) ----------------
+template <typename T, int QT, int VEC>
+__device__ __noinline__ void trss_producer(const SpecSingleArgs<T>* __restrict__ ap) {
+    const int NS = ap->NS;
+    const unsigned stage_bytes = ap->stage_bytes, piece = ap->piece;
+    const TrssCtx<T> c = trss_ctx<T, QT, VEC>(ap->g, NS, stage_bytes, ap->N);
+    const size_t WD = (size_t)ap->g.W * ap->g.D;
+    const T* X = ap->X;
+    const long long grid = gridDim.x;
+#ifdef TRSS_TRACE
+    long long* trace = ap->trace;
+    const int lane = 0;
+#endif
+    int s = 0; unsigned round = 0;
+    for (long long j = 0; j < c.nj; ++j) {
+        if (round > 0) TRSS_WAIT(&c.empty[s], (round - 1) & 1);
+        TRSS_STAMP(j, 0);
+        uint64_t* fb = &c.full[(round & 1) * TRSS_MAX_NS + s];
+        trf::mbar_arrive_expect_tx(fb, stage_bytes);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(X + (size_t)(blockIdx.x + j * grid) * WD);
+        unsigned char* dst = c.stages + (size_t)s * stage_bytes;
+        for (unsigned off = 0; off < stage_bytes; off += piece) {
+            const unsigned nb = stage_bytes - off < piece ? stage_bytes - off : piece;
+            trf::bulk_g2s(dst + off, src + off, nb, fb);
+        }
+        if (++s == NS) { s = 0; ++round; }
+    }
+}
+
+// ---------------- forward + per-sample epilogue (one warp per sample) ----------------
+template <typename T, int QT, int VEC>
+__device__ __noinline__ void trss_forward(const SpecSingleArgs<T>* __restrict__ ap) {
+    using GR = TrssG<T, QT>;
+    constexpr int TILE = 32 * VEC;
+    const SpecGeo g = ap->g;
+    const int NS = ap->NS;
+    const unsigned stage_bytes = ap->stage_bytes;
+    const TrssCtx<T> c = trss_ctx<T, QT, VEC>(g, NS, stage_bytes, ap->N);
+    const T* __restrict__ yp = ap->y;
+    T* __restrict__ resp = ap->res; T* __restrict__ Up = ap->U; T* __restrict__ yhatp = ap->yhat;
+    const long long grid = gridDim.x;
+#ifdef TRSS_TRACE
+    long long* trace = ap->trace;
+#endif
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int d0 = lane * VEC;
+    const bool act = d0 < g.D;
+    // a warp waits for the landing of sample j + nfa while the barrier of that stage may still be one phase behind
+    // only if the stage's previous sample is not younger than j: at most NS forward warps take part
+    const int nfa = NS < TRSS_NF ? NS : TRSS_NF;
+    const T* f1p = c.sF1 + d0;                                               // F1[d0.., r] at f1p + r * TILE
+    T accF[QT][VEC];                                                         // sum_t ds[t,r] m[t,r,d] since the last fold
+#pragma unroll
+    for (int r = 0; r < QT; ++r)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) accF[r][v] = (T)0;
+    double* slot = ap->df1part + ((size_t)blockIdx.x * TRSS_NF + wid) * QT * TILE + d0;
+#pragma unroll
+    for (int r = 0; r < QT; ++r)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) slot[(size_t)r * TILE + v] = 0.0;
+    double loss = 0.0;
+    const int spc = (int)(ap->spc < (1LL << 30) ? ap->spc : (1LL << 30));
+    int left = spc;
+    int s = wid; unsigned round = 0;
+    for (long long j = wid < nfa ? wid : c.nj; j < c.nj; j += nfa) {
+        const long long t = blockIdx.x + j * grid;
+        T yv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) yv[k] = (lane + 32 * k < g.NO) ? __ldg(yp + t * g.NO + lane + 32 * k) : (T)0;
+        T acc[QT][VEC];
+#pragma unroll
+        for (int q = 0; q < QT; ++q)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[q][v] = (T)0;
+        TRSS_STAMP(j, 1);
+        TRSS_WAIT(&c.full[(round & 1) * TRSS_MAX_NS + s], (round >> 1) & 1);
+        TRSS_STAMP(j, 2);
+        uint32_t xa = trf::smem_u32(c.stages + (size_t)s * stage_bytes) + (uint32_t)((act ? d0 : 0) * sizeof(T));
+        const uint32_t rowb = (uint32_t)(g.D * sizeof(T));
+        const T* gr = c.sG;
+        constexpr int UW = 8;
+        int w = 0;
+        for (; w + UW <= g.W; w += UW) {
+            T x[UW][VEC];
+#pragma unroll
+            for (int u = 0; u < UW; ++u) TrssLd<T, VEC>::ld(xa + u * rowb, x[u]);
+#pragma unroll
+            for (int u = 0; u < UW; ++u) GR::template fma_row<VEC>(acc, x[u], gr + u * GR::STRIDE);
+            xa += UW * rowb;
+            gr += UW * GR::STRIDE;
+        }
+        for (; w < g.W; ++w) {
+            T x[VEC];
+            TrssLd<T, VEC>::ld(xa, x);
+            GR::template fma_row<VEC>(acc, x, gr);
+            xa += rowb;
+            gr += GR::STRIDE;
+        }
+        if (!act) {
+#pragma unroll
+            for (int q = 0; q < QT; ++q)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[q][v] = (T)0;
+        }
+        TRSS_STAMP(j, 3);
+        // window sums -> the stage's da slot (free until this warp releases it; a lane reads back only what it wrote), so
+        // that the channels of a component can be addressed at run time; da overwrites them in place below
+        T* das = c.sDA + (size_t)s * QT * TILE + d0;
+#pragma unroll
+        for (int q = 0; q < QT; ++q) SpecSm<T, VEC>::st(das + (size_t)q * TILE, acc[q]);
+        // m[r][v]: a itself (normal component) or the norm over the component's complex channels
+        T m[QT][VEC];
+#pragma unroll
+        for (int r = 0; r < QT; ++r) {
+            if (r < g.Rn) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) m[r][v] = acc[r][v];
+            } else if (r < g.RT) {
+                T ss[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) ss[v] = (T)0;
+                const T* apq = das + (size_t)(g.Rn + (r - g.Rn) * g.CC) * TILE;
+                for (int cc = 0; cc < g.CC; ++cc) {
+                    T av[VEC];
+                    SpecSm<T, VEC>::ld(apq + (size_t)cc * TILE, av);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) ss[v] = tr_fma<T>(av[v], av[v], ss[v]);
+                }
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { T ri; spec_norm(ss[v], m[r][v], ri); }
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) m[r][v] = (T)0;
+            }
+        }
+        TRSS_STAMP(j, 9);
+        // second contraction: s[r] = sum_d m[d,r] F1[d,r]  (lane partial, then an all-reduce over the warp)
+        T sr[QT];
+#pragma unroll
+        for (int r = 0; r < QT; ++r) {
+            T p = (T)0, f1[VEC];
+            SpecSm<T, VEC>::ld(f1p + (size_t)r * TILE, f1);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) p = tr_fma<T>(m[r][v], f1[v], p);
+            sr[r] = p;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+            for (int r = 0; r < QT; ++r) sr[r] += __shfl_xor_sync(TR_FULL, sr[r], off);
+        TRSS_STAMP(j, 10);
+        if (lane <= g.RT) {
+            T uv = (T)1;
+#pragma unroll
+            for (int r = 0; r < QT; ++r) if (r == lane && r < g.RT) uv = sr[r];
+            Up[t * (g.RT + 1) + lane] = uv;
+        }
+        // outputs and residuals: lanes along n; ds[r] = sum_n res[n] F2[n,r]
+        T ds[QT];
+#pragma unroll
+        for (int r = 0; r < QT; ++r) ds[r] = (T)0;
+        T l2 = (T)0;                                                         // sum of this lane's squared residuals (at most 4)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int n = lane + 32 * k;
+            if (n < g.NO) {
+                const T* f2 = c.sF2 + (size_t)n * QT;
+                T yh = c.sB[n];
+#pragma unroll
+                for (int r = 0; r < QT; ++r) yh = tr_fma<T>(sr[r], f2[r], yh);
+                const T rr = yh - yv[k];
+                if (yhatp) yhatp[t * g.NO + n] = yh;
+                resp[t * g.NO + n] = rr;
+                l2 = tr_fma<T>(rr, rr, l2);
+#pragma unroll
+                for (int r = 0; r < QT; ++r) ds[r] = tr_fma<T>(rr, f2[r], ds[r]);
+            }
+        }
+        loss += (double)l2;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+            for (int r = 0; r < QT; ++r) ds[r] += __shfl_xor_sync(TR_FULL, ds[r], off);
+        TRSS_STAMP(j, 11);
+        // second-mode gradient (registers) and da -> shared memory next to the stage
+#pragma unroll
+        for (int r = 0; r < QT; ++r) {
+            // da of a normal channel r = ds[r] F1[d,r]; of the channels (r, c) of a spectral component = ds[r] F1[d,r] / m[d,r] * a
+            // (0 where the norm is 0: torch.norm's subgradient)
+            T kf[VEC], f1[VEC];
+            SpecSm<T, VEC>::ld(f1p + (size_t)r * TILE, f1);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                accF[r][v] = tr_fma<T>(ds[r], m[r][v], accF[r][v]);
+                kf[v] = ds[r] * f1[v];
+            }
+            if (r < g.Rn) {
+                SpecSm<T, VEC>::st(das + (size_t)r * TILE, kf);
+            } else if (r < g.RT) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) kf[v] = m[r][v] > (T)0 ? kf[v] * spec_recip(m[r][v]) : (T)0;
+                T* dq = das + (size_t)(g.Rn + (r - g.Rn) * g.CC) * TILE;
+                for (int cc = 0; cc < g.CC; ++cc) {
+                    T av[VEC];
+                    SpecSm<T, VEC>::ld(dq + (size_t)cc * TILE, av);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) av[v] *= kf[v];
+                    SpecSm<T, VEC>::st(dq + (size_t)cc * TILE, av);
+                }
+            }
+        }
+        __syncwarp();                                                        // the lanes' stores, then one release for the warp
+        if (lane == 0) trf::mbar_arrive(&c.ready[s]);
+        TRSS_STAMP(j, 4);
+        if (--left == 0) {
+#pragma unroll
+            for (int r = 0; r < QT; ++r)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    slot[(size_t)r * TILE + v] += (double)accF[r][v];
+                    accF[r][v] = (T)0;
+                }
+            left = spc;
+        }
+        s += nfa;
+        if (s >= NS) { s -= NS; ++round; }
+    }
+#pragma unroll
+    for (int r = 0; r < QT; ++r)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) slot[(size_t)r * TILE + v] += (double)accF[r][v];
+    loss = warp_sum(loss);
+    if (lane == 0) c.sloss[wid] = loss;
+}
+
+// ---------------- first-mode gradient (warp = 8 window rows of every sample) ----------------
+template <typename T, int QT, int VEC>
+__device__ __noinline__ void trss_gradient(const SpecSingleArgs<T>* __restrict__ ap) {
+    constexpr int TILE = 32 * VEC;
+    const int W = ap->g.W, D = ap->g.D;
+    const int NS = ap->NS;
+    const unsigned stage_bytes = ap->stage_bytes;
+    const TrssCtx<T> c = trss_ctx<T, QT, VEC>(ap->g, NS, stage_bytes, ap->N);
+#ifdef TRSS_TRACE
+    long long* trace = ap->trace;
+#endif
+    const int lane = threadIdx.x & 31;
+    const int wt = (threadIdx.x >> 5) - TRSS_NF;
+    const int d0 = lane * VEC;
+    const int w0 = wt * TRS_WT;
+    const bool rows = w0 < W;
+    // rows of X this lane works on: the warp's tile clipped to the window; none for lanes beyond D
+    const int nrow = d0 >= D ? 0 : (W - w0 < TRS_WT ? W - w0 : TRS_WT);
+    T acc[TRS_WT][QT];
+#pragma unroll
+    for (int i = 0; i < TRS_WT; ++i)
+#pragma unroll
+        for (int q = 0; q < QT; ++q) acc[i][q] = (T)0;
+    const int WTN = (W + TRS_WT - 1) / TRS_WT;
+    double* slot = ap->dgpart + ((size_t)blockIdx.x * WTN + wt) * TRS_WT * QT;
+    if (rows) {
+        if (lane < TRS_WT * QT) slot[lane] = 0.0;
+        if (lane + 32 < TRS_WT * QT) slot[lane + 32] = 0.0;
+    }
+    const unsigned xoff = (unsigned)(((size_t)w0 * D + d0) * sizeof(T));         // the lane's first element within a stage
+    const int nji = (int)c.nj;
+    const int spc = (int)(ap->spc < (long long)nji ? ap->spc : (long long)(nji > 0 ? nji : 1));
+    int s = 0; unsigned round = 0;
+    for (int j0 = 0; j0 < nji; j0 += spc) {
+        const int j1 = j0 + spc < nji ? j0 + spc : nji;
+        for (int j = j0; j < j1; ++j) {
+            if (wt == 0) TRSS_STAMP(j, 5);
+            TRSS_WAIT(&c.ready[s], round & 1);
+            if (wt == 0) TRSS_STAMP(j, 6);
+            const T* xs = reinterpret_cast<const T*>(c.stages + (size_t)s * stage_bytes + xoff);
+            const T* das = c.sDA + (size_t)s * QT * TILE + d0;
+            if (sizeof(T) == 4 && nrow == TRS_WT) {
+                // full tile (float: the registers allow it): all loads first, their latencies overlap, then 8 * QT * VEC FMAs
+                T da[QT][VEC], x[TRS_WT][VEC];
+#pragma unroll
+                for (int q = 0; q < QT; ++q) SpecSm<T, VEC>::ld(das + (size_t)q * TILE, da[q]);
+#pragma unroll
+                for (int i = 0; i < TRS_WT; ++i) SpecSm<T, VEC>::ld(xs + (size_t)i * D, x[i]);
+#pragma unroll
+                for (int i = 0; i < TRS_WT; ++i)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                        for (int q = 0; q < QT; ++q) acc[i][q] = tr_fma<T>(x[i][v], da[q][v], acc[i][q]);
+            } else if (nrow > 0) {
+                T da[QT][VEC];
+#pragma unroll
+                for (int q = 0; q < QT; ++q) SpecSm<T, VEC>::ld(das + (size_t)q * TILE, da[q]);
+#pragma unroll
+                for (int i = 0; i < TRS_WT; ++i) {
+                    if (i < nrow) {
+                        T x[VEC];
+                        SpecSm<T, VEC>::ld(xs + (size_t)i * D, x);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                            for (int q = 0; q < QT; ++q) acc[i][q] = tr_fma<T>(x[v], da[q][v], acc[i][q]);
+                    }
+                }
+            }
+            __syncwarp();                                                    // every lane has read the stage
+            if (lane == 0) trf::mbar_arrive(&c.empty[s]);
+            if (wt == 0) TRSS_STAMP(j, 7);
+            if (wt == TRSS_NG - 1) TRSS_STAMP(j, 8);
+            if (++s == NS) { s = 0; ++round; }
+        }
+        if (rows) {
+            // fold across lanes and add to the warp's slot (double); bounds every fp32 running sum
+#pragma unroll
+            for (int i = 0; i < TRS_WT; ++i)
+#pragma unroll
+                for (int q = 0; q < QT; ++q) {
+                    double sv = (double)acc[i][q];
+                    sv = warp_sum(sv);
+                    if (lane == 0) slot[i * QT + q] += sv;
+                    acc[i][q] = (T)0;
+                }
+        }
+    }
+}
+
+template <typename T, int QT, int VEC>
+__global__ void __launch_bounds__(TRSS_NT, 1) k_spec_single(const __grid_constant__ SpecSingleArgs<T> a) {
+    const SpecGeo& g = a.g;
+    constexpr int TILE = 32 * VEC;
+    const int NS = a.NS;
+    const TrssCtx<T> c = trss_ctx<T, QT, VEC>(g, NS, a.stage_bytes, a.N);
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) {
-            trf::mbar_init(&full[s], 1);
-            trf::mbar_init(&full[TRSS_MAX_NS + s], 1);
-            trf::mbar_init(&ready[s], 1);
-            trf::mbar_init(&empty[s], TRSS_NG);
+            trf::mbar_init(&c.full[s], 1);
+            trf::mbar_init(&c.full[TRSS_MAX_NS + s], 1);
+            trf::mbar_init(&c.ready[s], 1);
+            trf::mbar_init(&c.empty[s], TRSS_NG);
         }
         trf::fence_mbar_init();
     }
-    for (int i = threadIdx.x; i < g.W * QP; i += TRSS_NT) {
-        const int w = i / QP, q = i % QP;
-        sG[i] = q < g.Q ? spec_G(a.FtT, g, w, q) : (T)0;
-    }
+    for (int i = threadIdx.x; i < g.W * TrssG<T, QT>::STRIDE; i += TRSS_NT) c.sG[i] = a.gtab[i];
     for (int i = threadIdx.x; i < g.NO * QT; i += TRSS_NT) {
         const int n = i / QT, r = i % QT;
         T v = (T)0;
         if (r < g.Rn) v = a.w[r] * a.FtT[g.off[2] + n * g.Rn + r];
         else if (r < g.RT) v = a.FtT[g.off[5] + n * g.Rs + (r - g.Rn)];
-        sF2[i] = v;
+        c.sF2[i] = v;
     }
-    for (int i = threadIdx.x; i < g.NO; i += TRSS_NT) sB[i] = (T)(a.nb * (double)a.theta[g.off[6] + i]);
+    for (int i = threadIdx.x; i < g.NO; i += TRSS_NT) c.sB[i] = (T)(a.nb * (double)a.theta[g.off[6] + i]);
     for (int i = threadIdx.x; i < QT * TILE; i += TRSS_NT) {
         const int r = i / TILE, d = i % TILE;
         T val = (T)0;
         if (d < g.D && r < g.Rn) val = a.FtT[g.off[1] + d * g.Rn + r];
         else if (d < g.D && r < g.RT) val = a.FtT[g.off[4] + d * g.Rs + (r - g.Rn)];
-        sF1[i] = val;
+        c.sF1[i] = val;
     }
     __syncthreads();
 
     const int wid = threadIdx.x >> 5;
-    // every role derives its lane-dependent values from an opaque copy of the lane index, so that nothing is computed
-    // (and kept alive, i.e. spilled) across the other roles' code
-#define TRSS_ROLE_LOCALS()                                        \
-    int lane = threadIdx.x & 31;                                  \
-    asm volatile("" : "+r"(lane));                                \
-    const int d0 = lane * VEC;                                    \
-    const bool act = d0 < g.D;
-    const size_t WD = (size_t)g.W * g.D;
-    const long long grid = gridDim.x;
-    // the block's samples: t = blockIdx.x + j * grid, j < nj (strided: all SMs sweep one moving window of X)
-    const long long nj = (long long)blockIdx.x < a.N ? (a.N - blockIdx.x + grid - 1) / grid : 0;
-
     if (wid == TRSS_NF + TRSS_NG) {
-        // ---------------- producer ----------------
-        int lane = threadIdx.x & 31;
-        if (lane == 0) {
-            int s = 0; unsigned round = 0;
-            for (long long j = 0; j < nj; ++j) {
-                if (round > 0) trf::mbar_wait(&empty[s], (round - 1) & 1);
-                TRSS_STAMP(j, 0);
-                uint64_t* fb = &full[(round & 1) * TRSS_MAX_NS + s];
-                trf::mbar_arrive_expect_tx(fb, a.stage_bytes);
-                const unsigned char* src = reinterpret_cast<const unsigned char*>(a.X + (size_t)(blockIdx.x + j * grid) * WD);
-                unsigned char* dst = stages + (size_t)s * a.stage_bytes;
-                for (unsigned off = 0; off < a.stage_bytes; off += a.piece) {
-                    const unsigned nb = a.stage_bytes - off < a.piece ? a.stage_bytes - off : a.piece;
-                    trf::bulk_g2s(dst + off, src + off, nb, fb);
-                }
-                if (++s == NS) { s = 0; ++round; }
-            }
-        }
+        if ((threadIdx.x & 31) == 0) trss_producer<T, QT, VEC>(&a);
     } else if (wid < TRSS_NF) {
-        // ---------------- forward + per-sample epilogue ----------------
-        TRSS_ROLE_LOCALS()
-        // a warp waits for the landing of sample j + nfa while the barrier of that stage may still be one phase behind
-        // only if the stage's previous sample is not younger than j: at most NS forward warps take part
-        const int nfa = NS < TRSS_NF ? NS : TRSS_NF;
-        const T* f1p = sF1 + d0;                                             // F1[d0.., r] at f1p + r * TILE
-        T accF[VEC][QT];                                                     // sum_t ds[t,r] m[t,r,d] since the last fold
-#pragma unroll
-        for (int v = 0; v < VEC; ++v)
-#pragma unroll
-            for (int r = 0; r < QT; ++r) accF[v][r] = (T)0;
-        double* slot = a.df1part + ((size_t)blockIdx.x * TRSS_NF + wid) * QT * TILE;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v)
-#pragma unroll
-            for (int r = 0; r < QT; ++r) slot[(size_t)r * TILE + d0 + v] = 0.0;
-        double loss = 0.0;
-        long long left = a.spc;
-        int s = wid; unsigned round = 0;
-        for (long long j = wid < nfa ? wid : nj; j < nj; j += nfa) {
-            const long long t = blockIdx.x + j * grid;
-            T yv[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) yv[k] = (lane + 32 * k < g.NO) ? __ldg(a.y + t * g.NO + lane + 32 * k) : (T)0;
-            T acc[VEC][QT];
-#pragma unroll
-            for (int v = 0; v < VEC; ++v)
-#pragma unroll
-                for (int q = 0; q < QT; ++q) acc[v][q] = (T)0;
-            TRSS_STAMP(j, 1);
-            trf::mbar_wait(&full[(round & 1) * TRSS_MAX_NS + s], (round >> 1) & 1);
-            TRSS_STAMP(j, 2);
-            const T* xs = reinterpret_cast<const T*>(stages + (size_t)s * a.stage_bytes) + (act ? d0 : 0);
-            constexpr int UW = 8;
-            int w = 0;
-            for (; w + UW <= g.W; w += UW) {
-                T x[UW][VEC];
-#pragma unroll
-                for (int u = 0; u < UW; ++u) SpecSm<T, VEC>::ld(xs + (size_t)(w + u) * g.D, x[u]);
-#pragma unroll
-                for (int u = 0; u < UW; ++u) {
-                    T gq[QP];
-                    VECG<T>::template ld<QP>(sG + (size_t)(w + u) * QP, gq);
-#pragma unroll
-                    for (int q = 0; q < QT; ++q)
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) acc[v][q] = tr_fma<T>(x[u][v], gq[q], acc[v][q]);
-                }
-            }
-            for (; w < g.W; ++w) {
-                T x[VEC], gq[QP];
-                SpecSm<T, VEC>::ld(xs + (size_t)w * g.D, x);
-                VECG<T>::template ld<QP>(sG + (size_t)w * QP, gq);
-#pragma unroll
-                for (int q = 0; q < QT; ++q)
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) acc[v][q] = tr_fma<T>(x[v], gq[q], acc[v][q]);
-            }
-            if (!act) {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v)
-#pragma unroll
-                    for (int q = 0; q < QT; ++q) acc[v][q] = (T)0;
-            }
-            TRSS_STAMP(j, 3);
-            // window sums -> the stage's da slot (free until this warp releases it; a lane reads back only what it wrote), so
-            // that the channels of a component can be addressed at run time; da overwrites them in place below
-            T* das = sDA + (size_t)s * QT * TILE + d0;
-#pragma unroll
-            for (int q = 0; q < QT; ++q) {
-                T out[VEC];
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) out[v] = acc[v][q];
-                SpecSm<T, VEC>::st(das + (size_t)q * TILE, out);
-            }
-            T m[VEC][QT], rinv[VEC][QT];
-#pragma unroll
-            for (int r = 0; r < QT; ++r) {
-                if (r < g.Rn) {
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) { m[v][r] = acc[v][r]; rinv[v][r] = (T)1; }
-                } else if (r < g.RT) {
-                    T ss[VEC];
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) ss[v] = (T)0;
-                    const T* ap = das + (size_t)(g.Rn + (r - g.Rn) * g.CC) * TILE;
-                    for (int c = 0; c < g.CC; ++c) {
-                        T av[VEC];
-                        SpecSm<T, VEC>::ld(ap + (size_t)c * TILE, av);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) ss[v] = tr_fma<T>(av[v], av[v], ss[v]);
-                    }
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) spec_norm(ss[v], m[v][r], rinv[v][r]);
-                } else {
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) { m[v][r] = (T)0; rinv[v][r] = (T)0; }
-                }
-            }
-            T sr[QT];
-#pragma unroll
-            for (int r = 0; r < QT; ++r) {
-                T p = (T)0, f1[VEC];
-                SpecSm<T, VEC>::ld(f1p + (size_t)r * TILE, f1);
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) p = tr_fma<T>(m[v][r], f1[v], p);
-                sr[r] = p;
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1)
-#pragma unroll
-                for (int r = 0; r < QT; ++r) sr[r] += __shfl_xor_sync(TR_FULL, sr[r], off);
-            if (lane <= g.RT) {
-                T uv = (T)1;
-#pragma unroll
-                for (int r = 0; r < QT; ++r) if (r == lane && r < g.RT) uv = sr[r];
-                a.U[t * (g.RT + 1) + lane] = uv;
-            }
-            T ds[QT];
-#pragma unroll
-            for (int r = 0; r < QT; ++r) ds[r] = (T)0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int n = lane + 32 * k;
-                if (n < g.NO) {
-                    const T* f2 = sF2 + (size_t)n * QT;
-                    T yh = sB[n];
-#pragma unroll
-                    for (int r = 0; r < QT; ++r) yh = tr_fma<T>(sr[r], f2[r], yh);
-                    const T rr = yh - yv[k];
-                    if (a.yhat) a.yhat[t * g.NO + n] = yh;
-                    a.res[t * g.NO + n] = rr;
-                    loss += (double)rr * (double)rr;
-#pragma unroll
-                    for (int r = 0; r < QT; ++r) ds[r] = tr_fma<T>(rr, f2[r], ds[r]);
-                }
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1)
-#pragma unroll
-                for (int r = 0; r < QT; ++r) ds[r] += __shfl_xor_sync(TR_FULL, ds[r], off);
-            // second-mode gradient (registers) and da -> shared memory next to the stage
-#pragma unroll
-            for (int r = 0; r < QT; ++r) {
-                T kf[VEC], f1[VEC];
-                SpecSm<T, VEC>::ld(f1p + (size_t)r * TILE, f1);
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    accF[v][r] = tr_fma<T>(ds[r], m[v][r], accF[v][r]);
-                    kf[v] = ds[r] * f1[v] * rinv[v][r];
-                }
-                if (r < g.Rn) {
-                    SpecSm<T, VEC>::st(das + (size_t)r * TILE, kf);
-                } else if (r < g.RT) {
-                    const int qb = g.Rn + (r - g.Rn) * g.CC;
-                    for (int c = 0; c < g.CC; ++c) {
-                        T av[VEC];
-                        SpecSm<T, VEC>::ld(das + (size_t)(qb + c) * TILE, av);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) av[v] *= kf[v];
-                        SpecSm<T, VEC>::st(das + (size_t)(qb + c) * TILE, av);
-                    }
-                }
-            }
-            __syncwarp();                                                    // the lanes' stores, then one release for the warp
-            if (lane == 0) trf::mbar_arrive(&ready[s]);
-            TRSS_STAMP(j, 4);
-            if (--left == 0) {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v)
-#pragma unroll
-                    for (int r = 0; r < QT; ++r) {
-                        slot[(size_t)r * TILE + d0 + v] += (double)accF[v][r];
-                        accF[v][r] = (T)0;
-                    }
-                left = a.spc;
-            }
-            s += nfa;
-            if (s >= NS) { s -= NS; ++round; }
-        }
-#pragma unroll
-        for (int v = 0; v < VEC; ++v)
-#pragma unroll
-            for (int r = 0; r < QT; ++r) slot[(size_t)r * TILE + d0 + v] += (double)accF[v][r];
-        loss = warp_sum(loss);
-        if (lane == 0) sloss[wid] = loss;
+        trss_forward<T, QT, VEC>(&a);
     } else {
-        // ---------------- first-mode gradient ----------------
-        TRSS_ROLE_LOCALS()
-        const int wt = wid - TRSS_NF;
-        const int w0 = wt * TRS_WT;
-        const bool rows = w0 < g.W;
-        // rows of X this lane works on: the warp's tile clipped to the window; none for lanes beyond D
-        const int nrow = !act ? 0 : (g.W - w0 < TRS_WT ? g.W - w0 : TRS_WT);
-        T acc[TRS_WT][QT];
-#pragma unroll
-        for (int i = 0; i < TRS_WT; ++i)
-#pragma unroll
-            for (int q = 0; q < QT; ++q) acc[i][q] = (T)0;
-        const int WTN = (g.W + TRS_WT - 1) / TRS_WT;
-        double* slot = a.dgpart + ((size_t)blockIdx.x * WTN + wt) * TRS_WT * QT;
-        if (rows) {
-            if (lane < TRS_WT * QT) slot[lane] = 0.0;
-            if (lane + 32 < TRS_WT * QT) slot[lane + 32] = 0.0;
-        }
-        const unsigned xoff = (unsigned)(((size_t)w0 * g.D + d0) * sizeof(T));   // the lane's first element within a stage
-        const int nji = (int)nj;
-        const int spc = (int)(a.spc < (long long)nji ? a.spc : (long long)(nji > 0 ? nji : 1));
-        int s = 0; unsigned round = 0;
-        for (int j0 = 0; j0 < nji; j0 += spc) {
-            const int j1 = j0 + spc < nji ? j0 + spc : nji;
-            for (int j = j0; j < j1; ++j) {
-                if (wt == 0) TRSS_STAMP(j, 5);
-                trf::mbar_wait(&ready[s], round & 1);
-                if (wt == 0) TRSS_STAMP(j, 6);
-                if (nrow > 0) {
-                    const T* xs = reinterpret_cast<const T*>(stages + (size_t)s * a.stage_bytes + xoff);
-                    const T* das = sDA + (size_t)s * QT * TILE + d0;
-                    T da[QT][VEC];
-#pragma unroll
-                    for (int q = 0; q < QT; ++q) SpecSm<T, VEC>::ld(das + (size_t)q * TILE, da[q]);
-#pragma unroll
-                    for (int i = 0; i < TRS_WT; ++i) {
-                        if (i < nrow) {
-                            T x[VEC];
-                            SpecSm<T, VEC>::ld(xs + (size_t)i * g.D, x);
-#pragma unroll
-                            for (int q = 0; q < QT; ++q)
-#pragma unroll
-                                for (int v = 0; v < VEC; ++v) acc[i][q] = tr_fma<T>(x[v], da[q][v], acc[i][q]);
-                        }
-                    }
-                }
-                __syncwarp();                                                // every lane has read the stage
-                if (lane == 0) trf::mbar_arrive(&empty[s]);
-                if (wt == 0) TRSS_STAMP(j, 7);
-                if (wt == TRSS_NG - 1) TRSS_STAMP(j, 8);
-                if (++s == NS) { s = 0; ++round; }
-            }
-            if (rows) {
-                // fold across lanes and add to the warp's slot (double); bounds every fp32 running sum
-#pragma unroll
-                for (int i = 0; i < TRS_WT; ++i)
-#pragma unroll
-                    for (int q = 0; q < QT; ++q) {
-                        double sv = (double)acc[i][q];
-                        sv = warp_sum(sv);
-                        if (lane == 0) slot[i * QT + q] += sv;
-                        acc[i][q] = (T)0;
-                    }
-            }
-        }
+        trss_gradient<T, QT, VEC>(&a);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         double tot = 0.0;
-        for (int i = 0; i < TRSS_NF; ++i) tot += sloss[i];
+        for (int i = 0; i < TRSS_NF; ++i) tot += c.sloss[i];
         a.losspart[blockIdx.x] = tot;
     }
 }

@@ -6,7 +6,7 @@
 
 Events per sample j of the block (cycles relative to the first traced TMA issue):
   0 TMA issued | 1 forward warp starts waiting | 2 bytes landed (forward start) | 3 window loop done |
-  4 epilogue done, da released | 5 gradient warp 0 starts waiting | 6 gradient start | 7 gradient warp 0 done | 8 gradient warp 7 done
+  4 epilogue done, da released (9 norms done, 10 s reduced, 11 ds reduced) | 5 gradient warp 0 starts waiting | 6 gradient start | 7 gradient warp 0 done | 8 gradient warp 7 done
 """
 import ctypes
 import sys
@@ -37,11 +37,12 @@ rc = _lib.lib.tr_debug_trace(eng._h, out, NSM * EV)
 assert rc == 0, rc
 t = np.array(out, dtype=np.int64).reshape(NSM, EV)
 t0 = t[0, 0]
-names = ['tma', 'fwait', 'fwd0', 'loop1', 'ready', 'gwait', 'g0', 'g1', 'g1w7']
+names = ['tma', 'fwait', 'fwd0', 'loop1', 'ready', 'gwait', 'g0', 'g1', 'g1w7', 'norm', 'sred', 'dsred']
 print('sample ' + ' '.join(f'{n:>8s}' for n in names))
 for i in range(NSM):
     print(f'{i:6d} ' + ' '.join(f'{(t[i, e] - t0) if t[i, e] else 0:8d}' for e in range(len(names))))
 d = lambda a, b: np.median((t[:, b] - t[:, a])[(t[:, a] > 0) & (t[:, b] > 0)])  # noqa: E731
 print('median cycles: tma->landed(fwd0) %d | fwd wait %d | window loop %d | epilogue %d | ready->g0 %d | gradient w0 %d | tma->g1 (stage residency) %d'
       % (d(0, 2), d(1, 2), d(2, 3), d(3, 4), d(4, 6), d(6, 7), d(0, 8)))
+print('epilogue: store a + norms %d | second contraction + reduce %d | outputs + ds reduce %d | da + release %d' % (d(3, 9), d(9, 10), d(10, 11), d(11, 4)))
 print('period (cycles per sample): %.0f' % np.median(np.diff(t[:, 0])))
