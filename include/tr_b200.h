@@ -225,7 +225,12 @@ int tr_profile_read(tr_handle* h, double* out6);
  * "flow": 0 = never (default), 1 = run tr_fwd_grad_std / tr_fwd_grad_mn as ONE cooperative
  * dataflow kernel whose gradient warps re-read X from L2 a bounded window behind the forward warps
  * (experimental: correct, but measured slower than the two-pass kernels; error if the
- * geometry / alignment is not eligible); "flow_window_mb": size of that window in MiB (default 32). */
+ * geometry / alignment is not eligible); "flow_window_mb": size of that window in MiB (default 32).
+ * "spec_single" (spectral handles): -1 = auto (default; env TR_B200_SPEC_SINGLE overrides: the single-pass
+ * kernel from 4 x SMs samples when the geometry fits), 0 = never, 1 = always the single-pass kernel of
+ * tr_spec_fwd_grad that keeps a ring of whole samples in shared memory and reads X once (error unless
+ * 16-byte rows, D <= 32 lanes x 16 bytes, Q <= 8 channels, W <= 64 window rows and two samples fit);
+ * "spec_single_ns": cap on its shared-memory stages (testing knob). */
 int tr_set_option(tr_handle* h, const char* name, int64_t value);
 
 /* How the last tr_fwd_grad_* / tr_forward_* call was executed (host ints):

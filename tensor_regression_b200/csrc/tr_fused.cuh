@@ -75,11 +75,20 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_addr) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
     unsigned ok;
+#ifdef TRF_WAIT_NS
+    // build option: suspend-time hint on every wait of the cluster kernels (see mbar_try_wait_hint below)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"((unsigned)TRF_WAIT_NS) : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
     return ok != 0;
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, unsigned parity) {
