@@ -33,12 +33,15 @@
 #ifndef TRSS_FFMA2
 #define TRSS_FFMA2 0                                   // float window loop: 1 = FFMA2 over element pairs (G values stored twice), 0 = scalar FMAs
 #endif
+#ifndef TRSS_EPI
+#define TRSS_EPI 2                                     // per-sample epilogue: 2 = static (r, q) pairs, loads batched outside uniform branches; 0 = run-time loops over a component's channels through shared memory
+#endif
 // every wait carries a suspend-time hint: a warp that waits for microseconds is parked by the hardware instead of polling
 #define TRSS_WAIT(bar, parity) trf::mbar_wait_hint(bar, parity)
 #define TRSS_NG 8                                      // gradient warps (TRS_WT window rows each)
 #define TRSS_NT ((TRSS_NF + TRSS_NG + 1) * 32)         // + the producer warp
-#define TRSS_MAX_NS 8
-#define TRSS_HDR 384                                   // barriers + loss scratch
+#define TRSS_MAX_NS 12
+#define TRSS_HDR 512                                   // barriers (4 per stage) + loss scratch
 
 template <typename T>
 struct SpecSingleArgs {
@@ -127,8 +130,23 @@ template <> struct TrssLd<double, 2> {
     }
 };
 
-// 1 / m for m > 0: correctly rounded reciprocal for float, an exact division for double
-__device__ __forceinline__ float spec_recip(float m) { const float r = __frcp_rn(m); return r; }
+// sqrt(ss) for ss >= 0 (0 at 0): one flush-to-zero reciprocal square root plus a Newton step on the product for float
+// (2 ulp -> fp32 rounding; an order of magnitude fewer instructions than sqrtf), the exact square root for double
+__device__ __forceinline__ float trss_norm(float ss) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(ss));
+    r = ss > 0.0f ? r : 0.0f;
+    r = r * fmaf(-0.5f * ss * r, r, 1.5f);
+    return ss * r;
+}
+__device__ __forceinline__ double trss_norm(double ss) { return sqrt(ss); }
+// 1 / m for m > 0: the hardware reciprocal (1 ulp) plus one Newton step for float — an IEEE-rounded reciprocal
+// (__frcp_rn) is a ~30-instruction sequence and was a quarter of the epilogue's stall samples —, an exact division for double
+__device__ __forceinline__ float spec_recip(float m) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(m));
+    return fmaf(r, fmaf(-m, r, 1.0f), r);
+}
 __device__ __forceinline__ double spec_recip(double m) { return 1.0 / m; }
 
 struct SpecSingleLayout { size_t tab, sF1, sDA, stage, total; };
@@ -243,11 +261,13 @@ __device__ __noinline__ void trss_forward(const SpecSingleArgs<T>* __restrict__ 
 #pragma unroll
         for (int v = 0; v < VEC; ++v) slot[(size_t)r * TILE + v] = 0.0;
     double loss = 0.0;
+    T lossp = (T)0;                                                          // squared residuals of up to 16 samples of this lane
     const int spc = (int)(ap->spc < (1LL << 30) ? ap->spc : (1LL << 30));
     int left = spc;
     int s = wid; unsigned round = 0;
-    for (long long j = wid < nfa ? wid : c.nj; j < c.nj; j += nfa) {
-        const long long t = blockIdx.x + j * grid;
+    long long t = blockIdx.x + (long long)wid * grid;
+    const long long tstep = (long long)nfa * grid;
+    for (long long j = wid < nfa ? wid : c.nj; j < c.nj; j += nfa, t += tstep) {
         T yv[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) yv[k] = (lane + 32 * k < g.NO) ? __ldg(yp + t * g.NO + lane + 32 * k) : (T)0;
@@ -287,6 +307,127 @@ __device__ __noinline__ void trss_forward(const SpecSingleArgs<T>* __restrict__ 
                 for (int v = 0; v < VEC; ++v) acc[q][v] = (T)0;
         }
         TRSS_STAMP(j, 3);
+#if TRSS_EPI == 2
+        // Channel q belongs to component r when  r < Rn: q == r  (normal)  |  Rn <= r < RT: qb(r) <= q < qb(r) + CC, qb(r) = Rn + (r - Rn) CC
+        // — all warp-uniform.  The epilogue runs over STATIC (r, q) pairs guarded by uniform branches that contain arithmetic
+        // (and stores) only: every shared-memory load is issued in a batch outside the branches, so no ~100-cycle load latency
+        // is serialised per component in the warp that is the critical path of its sample.
+        // m[r] = a itself (normal component) or the norm over the component's complex channels is parked in row r of the stage's
+        // da slot (free until this warp releases it; a lane reads back only what it wrote) and re-read in batches: next to
+        // the window sums and the second-mode gradient sums it would not fit the registers
+        T* das = c.sDA + (size_t)s * QT * TILE + d0;
+#pragma unroll
+        for (int r = 0; r < QT; ++r) {
+            T m[VEC];
+            if (r < g.Rn) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) m[v] = acc[r][v];
+            } else if (r < g.RT) {
+                const int qb = g.Rn + (r - g.Rn) * g.CC;
+                T ss[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) ss[v] = (T)0;
+#pragma unroll
+                for (int q = r; q < QT; ++q) {                               // qb(r) >= r
+                    if (q >= qb && q < qb + g.CC) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) ss[v] = tr_fma<T>(acc[q][v], acc[q][v], ss[v]);
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) m[v] = trss_norm(ss[v]);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) m[v] = (T)0;
+            }
+            SpecSm<T, VEC>::st(das + (size_t)r * TILE, m);
+        }
+        TRSS_STAMP(j, 9);
+        // second contraction: s[r] = sum_d m[d,r] F1[d,r]  (lane partial, then an all-reduce over the warp)
+        T sr[QT];
+#pragma unroll
+        for (int r = 0; r < QT; ++r) {
+            T p = (T)0, f1[VEC], m[VEC];
+            SpecSm<T, VEC>::ld(f1p + (size_t)r * TILE, f1);
+            SpecSm<T, VEC>::ld(das + (size_t)r * TILE, m);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) p = tr_fma<T>(m[v], f1[v], p);
+            sr[r] = p;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+            for (int r = 0; r < QT; ++r) sr[r] += __shfl_xor_sync(TR_FULL, sr[r], off);
+        TRSS_STAMP(j, 10);
+        if (lane <= g.RT) {
+            T uv = (T)1;
+#pragma unroll
+            for (int r = 0; r < QT; ++r) if (r == lane && r < g.RT) uv = sr[r];
+            Up[t * (g.RT + 1) + lane] = uv;
+        }
+        // outputs and residuals: lanes along n; ds[r] = sum_n res[n] F2[n,r]
+        T ds[QT];
+#pragma unroll
+        for (int r = 0; r < QT; ++r) ds[r] = (T)0;
+        T l2 = (T)0;                                                         // sum of this lane's squared residuals (at most 4)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int n = lane + 32 * k;
+            if (n < g.NO) {
+                const T* f2 = c.sF2 + (size_t)n * QT;
+                T yh = c.sB[n];
+#pragma unroll
+                for (int r = 0; r < QT; ++r) yh = tr_fma<T>(sr[r], f2[r], yh);
+                const T rr = yh - yv[k];
+                if (yhatp) yhatp[t * g.NO + n] = yh;
+                resp[t * g.NO + n] = rr;
+                l2 = tr_fma<T>(rr, rr, l2);
+#pragma unroll
+                for (int r = 0; r < QT; ++r) ds[r] = tr_fma<T>(rr, f2[r], ds[r]);
+            }
+        }
+        lossp += l2;
+        if ((left & 15) == 0) { loss += (double)lossp; lossp = (T)0; }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+            for (int r = 0; r < QT; ++r) ds[r] += __shfl_xor_sync(TR_FULL, ds[r], off);
+        TRSS_STAMP(j, 11);
+        // second-mode gradient (registers) and da -> shared memory next to the stage.
+        // da of a normal channel r = ds[r] F1[d,r]; of the channels (r, c) of a spectral component = ds[r] F1[d,r] / m[d,r] * a
+        // (0 where the norm is 0: torch.norm's subgradient)
+        {
+            T m[QT][VEC];                                                    // all rows first: da overwrites them below
+#pragma unroll
+            for (int r = 0; r < QT; ++r) SpecSm<T, VEC>::ld(das + (size_t)r * TILE, m[r]);
+#pragma unroll
+            for (int r = 0; r < QT; ++r) {
+                T kf[VEC], f1[VEC];
+                SpecSm<T, VEC>::ld(f1p + (size_t)r * TILE, f1);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    accF[r][v] = tr_fma<T>(ds[r], m[r][v], accF[r][v]);
+                    kf[v] = ds[r] * f1[v];
+                }
+                if (r < g.Rn) {
+                    SpecSm<T, VEC>::st(das + (size_t)r * TILE, kf);
+                } else if (r < g.RT) {
+                    const int qb = g.Rn + (r - g.Rn) * g.CC;
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) kf[v] = m[r][v] > (T)0 ? kf[v] * spec_recip(m[r][v]) : (T)0;
+#pragma unroll
+                    for (int q = r; q < QT; ++q) {
+                        if (q >= qb && q < qb + g.CC) {
+                            T out[VEC];
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) out[v] = acc[q][v] * kf[v];
+                            SpecSm<T, VEC>::st(das + (size_t)q * TILE, out);
+                        }
+                    }
+                }
+            }
+        }
+#else
         // window sums -> the stage's da slot (free until this warp releases it; a lane reads back only what it wrote), so
         // that the channels of a component can be addressed at run time; da overwrites them in place below
         T* das = c.sDA + (size_t)s * QT * TILE + d0;
@@ -311,7 +452,7 @@ __device__ __noinline__ void trss_forward(const SpecSingleArgs<T>* __restrict__ 
                     for (int v = 0; v < VEC; ++v) ss[v] = tr_fma<T>(av[v], av[v], ss[v]);
                 }
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) { T ri; spec_norm(ss[v], m[r][v], ri); }
+                for (int v = 0; v < VEC; ++v) m[r][v] = trss_norm(ss[v]);
             } else {
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) m[r][v] = (T)0;
@@ -360,7 +501,8 @@ __device__ __noinline__ void trss_forward(const SpecSingleArgs<T>* __restrict__ 
                 for (int r = 0; r < QT; ++r) ds[r] = tr_fma<T>(rr, f2[r], ds[r]);
             }
         }
-        loss += (double)l2;
+        lossp += l2;
+        if ((left & 15) == 0) { loss += (double)lossp; lossp = (T)0; }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1)
 #pragma unroll
@@ -393,6 +535,7 @@ __device__ __noinline__ void trss_forward(const SpecSingleArgs<T>* __restrict__ 
                 }
             }
         }
+#endif
         __syncwarp();                                                        // the lanes' stores, then one release for the warp
         if (lane == 0) trf::mbar_arrive(&c.ready[s]);
         TRSS_STAMP(j, 4);
@@ -413,7 +556,7 @@ __device__ __noinline__ void trss_forward(const SpecSingleArgs<T>* __restrict__ 
     for (int r = 0; r < QT; ++r)
 #pragma unroll
         for (int v = 0; v < VEC; ++v) slot[(size_t)r * TILE + v] += (double)accF[r][v];
-    loss = warp_sum(loss);
+    loss = warp_sum(loss + (double)lossp);
     if (lane == 0) c.sloss[wid] = loss;
 }
 
