@@ -550,6 +550,8 @@ def multi_gpu_check(rank, world, device, dist, E, STR, MTR):
              ('mn_f32', 'mn', (100, 50, 20), 6, 10, torch.float32, -1, 1e-6),
              # spectral variant: dims = (W, D), R = (rank_normal, rank_spectral, complex columns), C = outputs
              ('spec_f32', 'spec', (16, 128), (2, 2, 2), 3, torch.float32, -1, 1e-6),
+             # ... the same on the single-pass kernel (k_spec_single; fused = 2 forces it at this size)
+             ('spec_f32_single_pass', 'spec', (16, 128), (2, 2, 2), 3, torch.float32, 2, 1e-6),
              ('spec_f64', 'spec', (12, 40), (1, 2, 3), 2, torch.float64, -1, 1e-12)]
     for name, kind, dims, R, C, dt, fused, tol in cases:
         n_glob = 24 * world + 5                         # uneven split on purpose
@@ -574,8 +576,12 @@ def multi_gpu_check(rank, world, device, dist, E, STR, MTR):
                                              rank_spectral=R[1], n_complex_dim=R[2] - 1,
                                              Bcp_init=[[b.clone() for b in B0[0]], [b.clone() for b in B0[1]]],
                                              device=device, shard_group=group)
+                if fused == 2:
+                    m._engine().set_option('spec_single', 1)
                 m.fit_Adam(Xs.to(device), ys.to(device), lambda_L2=LAMBDA, max_iter=K, tol=0.0, patience=10 ** 9,
                            Adam_kwargs=ADAM)
+                if fused == 2:
+                    assert m._engine().launch_info()['path'].startswith('single-pass')
             elif kind == 'std':
                 m = STR.CP_linear_regression((Xs.shape[0], *dims), dtype=dt, rank=R, Bcp_init=[b.clone() for b in B0],
                                              device=device, shard_group=group)
