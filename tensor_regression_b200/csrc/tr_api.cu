@@ -101,7 +101,7 @@ struct tr_handle {
     int fused_piece = 32768;            // bytes per bulk-copy instruction (option "fused_piece")
     int last_fused = 0;
     int fused_ns = 0;                   // testing knob (option "fused_ns", env TR_B200_FUSED_NS): cap on the shared-memory stages of k_fused_mn
-    int fused_cl = 0;                   // testing knob (option "fused_cl"): force the cluster size of the single-pass multinomial kernel
+    int fused_cl = 0;                   // testing knob (option "fused_cl", env TR_B200_FUSED_CL): force the cluster size of the single-pass cluster kernels
     std::map<const void*, int> occ_clusters;
     int flow_mode = 0;                  // dataflow kernel (tr_flow.cuh), experimental: 0 never (default), 1 always (error when
                                         // not eligible); -1 is accepted and currently means 0 (it measured slower)
@@ -371,7 +371,14 @@ int plan_fused(tr_handle* h, long long N, const void* X, FusedPlan* fp) {
     if (g.C != 0 || !vec_ok(X, g.D, sizeof(T)) || N < 1) return TR_OK;
     const size_t fixed = ((((sizeof(FusedCtl) + 15) / 16) * 16 + (size_t)(g.pfeat + g.R) * sizeof(T)) + 1023) / 1024 * 1024;
     const size_t budget = 226 * 1024;
-    for (int CL = 1; CL <= TR_FUSED_MAX_CL; CL *= 2) {
+    // The kernel takes any cluster size (option "fused_cl"); how many clusters of a size are resident depends on the GPC
+    // layout (B200, one CTA per SM: 15 clusters of 8 = 120 SMs, 15 clusters of 9 = 135 SMs).  Measured on cfg 2: 9 instead
+    // of 8 changes nothing (16.1-16.3 ms either way: the kernel is bound by HBM, not by the SMs it covers), so the automatic
+    // choice stays with the powers of two — the size that covers the most SMs, ties to the smaller cluster.
+    long long best_cover = 0;
+    for (int CL = 1; CL <= TR_FUSED_MAX_CL; ++CL) {
+        if (h->fused_cl > 0 ? CL != h->fused_cl : (CL & (CL - 1)) != 0) continue;
+        if (CL > g.D / VEC) break;                                           // every CTA needs at least one 16-byte chunk
         // ragged slices: the first (D/VEC mod CL) CTAs of a cluster hold one 16-byte chunk more
         const long long chunks = (g.D / VEC + CL - 1) / CL;
         const long long Dc = chunks * VEC;
@@ -408,6 +415,8 @@ int plan_fused(tr_handle* h, long long N, const void* X, FusedPlan* fp) {
         }
         if (NC < 1) continue;
         if ((long long)NC * CL * 10 < (long long)h->sms * 6) continue;       // would leave > 40 % of the SMs idle
+        if ((long long)NC * CL <= best_cover) continue;
+        best_cover = (long long)NC * CL;
         if (NC > N) NC = (int)N;
         fp->CL = CL; fp->E = E; fp->NS = NS; fp->NC = NC; fp->stage_bytes = (unsigned)stage; fp->smem = smem; fp->Dc = (int)Dc;
         const long long cnt = (N + NC - 1) / NC;
@@ -417,7 +426,6 @@ int plan_fused(tr_handle* h, long long N, const void* X, FusedPlan* fp) {
         while (nchunk > 1 && (size_t)nchunk * NC * slot_bytes > ((size_t)1 << 30)) --nchunk;
         fp->nchunk = (int)nchunk;
         fp->spc = std::max<long long>(1, (cnt + nchunk - 1) / nchunk);
-        return TR_OK;
     }
     return TR_OK;
 }
@@ -1437,6 +1445,7 @@ int tr_create(tr_handle** out, int dtype, int k, const int64_t* dims, int R, int
     h->l2_bytes = (size_t)prop.l2CacheSize;
     if (const char* ev = getenv("TR_B200_FUSED")) h->fused_mode = atoi(ev) < 0 ? -1 : (atoi(ev) > 0 ? 1 : 0);
     if (const char* ev = getenv("TR_B200_FUSED_NS")) h->fused_ns = atoi(ev);
+    if (const char* ev = getenv("TR_B200_FUSED_CL")) { const int v = atoi(ev); if (v >= 0 && v <= 16) h->fused_cl = v; }
     if (const char* ev = getenv("TR_B200_SPEC_SINGLE")) h->spec_single = atoi(ev) < 0 ? -1 : (atoi(ev) > 0 ? 1 : 0);
     if (const char* ev = getenv("TR_B200_FUSED_PACE")) h->fused_pace = atoi(ev);
     if (const char* ev = getenv("TR_B200_FUSED_PIECE")) { const int v = atoi(ev); if (v >= 16 && v % 16 == 0) h->fused_piece = v; }
@@ -1866,9 +1875,10 @@ int tr_set_option(tr_handle* h, const char* name, int64_t value) {
     if (strcmp(name, "fused_pace") == 0) { h->fused_pace = (int)value; return TR_OK; }
     if (strcmp(name, "fused_ns") == 0) { h->fused_ns = (int)value; h->occ_clusters.clear(); return TR_OK; }
     if (strcmp(name, "fused_cl") == 0) {
-        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
-            return fail(h, TR_ERR_INVALID, "fused_cl must be 0 (auto), 1, 2, 4, 8 or 16");
+        if (value < 0 || value > 16)
+            return fail(h, TR_ERR_INVALID, "fused_cl must be 0 (auto) or a cluster size 1..16 (the multinomial kernel takes 1, 2, 4, 8, 16)");
         h->fused_cl = (int)value;
+        h->occ_clusters.clear();
         return TR_OK;
     }
     if (strcmp(name, "fused_piece") == 0) {

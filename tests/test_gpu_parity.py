@@ -467,6 +467,48 @@ def test_fused_single_pass_matches_two_pass_and_oracle(name, N, dims, R, dt):
     eng.set_option('fused', -1)
 
 
+@pytest.mark.parametrize('cl', [2, 3, 5, 6, 7, 9, 10, 11, 12, 13, 15, 16])
+@pytest.mark.parametrize('dims,R,dt', [((64, 64, 32), 4, torch.float32), ((20, 30, 41 * 4), 3, torch.float32),
+                                       ((16, 16, 16, 32), 5, torch.float64)],
+                         ids=['cfg2_shape', 'ragged_24600_chunks', 'cfg4_shape_f64'])
+def test_fused_single_pass_any_cluster_size(cl, dims, R, dt):
+    """The cluster size is not restricted to powers of two (the automatic choice takes the size that covers the most SMs,
+    e.g. 15 clusters of 9 instead of 15 clusters of 8 on cfg 2): every size, forced, against the two-pass kernels."""
+    from tensor_regression_b200 import engine
+    N = 97
+    X, y, _ = O.synth_std(N, dims, R, 4321, dtype=dt)
+    y = y.reshape(-1)
+    nn = [False] * (len(dims) + 1)
+    B0 = O.init_std(dims, R, nn, dtype=dt)
+    bias = torch.tensor([-0.03], dtype=dt)
+    w = torch.linspace(0.8, 1.2, R, dtype=dt)
+    eng = engine_for(dims, R, 0, dt)
+    theta = dev(O.pack(B0, bias))
+    Xd, yd, wd = dev(X), dev(y), dev(w)
+    eng.set_option('fused', 0)
+    yh2 = torch.empty_like(yd)
+    two = eng.fwd_grad_std(Xd, yd, theta, wd, 0, 50.0, 1.0, yhat=yh2).clone()
+    eng.set_option('fused_cl', cl)
+    eng.set_option('fused', -1)
+    try:
+        # does this size fit (three stages, resident clusters)?  fused=1 on a size that does not fails loudly
+        eng.set_option('fused', 1)
+        yh1 = torch.full_like(yd, float('nan'))
+        try:
+            one = eng.fwd_grad_std(Xd, yd, theta, wd, 0, 50.0, 1.0, yhat=yh1).clone()
+        except engine.TRError:
+            pytest.skip(f'cluster size {cl} does not fit this geometry')
+        info = eng.launch_info()
+        assert info['path'].startswith('single-pass') and info['cluster_size'] == cl, info
+        tol = TOL[dt]
+        assert rel(yh1, yh2) < tol and rel(one, two) < tol
+        again = eng.fwd_grad_std(Xd, yd, theta, wd, 0, 50.0, 1.0)
+        assert torch.equal(again, one)
+    finally:
+        eng.set_option('fused_cl', 0)
+        eng.set_option('fused', -1)
+
+
 # ------------------------------------------------------------------------------------------
 # single-launch dataflow kernel (option flow=1: forward, epilogue and gradient in one persistent
 # kernel, second read of X from L2) vs two-pass vs oracle
