@@ -391,3 +391,43 @@ def test_spectral_single_pass_refuses_geometry_loudly():
     beta, thr = m._sp()
     with pytest.raises(TRError, match='spec_single'):
         eng.fwd_grad(X.to(DEV), y.to(DEV), m.theta, m.weights, m._mask(), beta, thr)
+
+
+def test_spectral_full_size_properties_single_pass():
+    """The bench workload spec1 at full size (200 000 samples of 64 x 128 fp32, 6.55 GB): the single-pass kernel is the
+    automatic choice, agrees with the two-pass path, relaunches bit-identically, its sums over two halves of the sample
+    axis add up, and a slice of it agrees with the fp64 oracle."""
+    from tensor_regression_b200 import engine
+    T, W, D, NO, rn, rs, cc = 200000, 64, 128, 4, 2, 2, 2
+    g = torch.Generator(device=DEV).manual_seed(5)
+    X = torch.randn((T, W, D), generator=g, device=DEV)
+    y = torch.randn((T, NO), generator=g, device=DEV)
+    eng = engine.SpectralEngine(W, D, NO, rn, rs, cc, torch.float32, DEV)
+    Bn, Bc = OS.init(W, D, NO, rn, rs, cc, seed=21)
+    th = torch.cat([b.reshape(-1) for b in Bn + Bc] + [0.05 * torch.arange(1, NO + 1, dtype=torch.float32)]).to(DEV)
+    assert th.numel() == eng.P
+    w = torch.linspace(0.7, 1.3, rn + rs, device=DEV)
+    gs = eng.fwd_grad(X, y, th, w, 0, 50.0, 1.0).clone()
+    assert eng.launch_info()['path'].startswith('single-pass')
+    assert torch.equal(gs, eng.fwd_grad(X, y, th, w, 0, 50.0, 1.0))
+    eng.set_option('spec_single', 0)
+    gs2 = eng.fwd_grad(X, y, th, w, 0, 50.0, 1.0).clone()
+    assert not eng.launch_info()['path'].startswith('single-pass')
+    assert rel(gs, gs2) < 2e-6
+    eng.set_option('spec_single', -1)
+    h = 123457                                       # uneven halves
+    ga = eng.fwd_grad(X[:h], y[:h], th, w, 0, 50.0, 1.0).clone()
+    gb = eng.fwd_grad(X[h:], y[h:], th, w, 0, 50.0, 1.0)
+    assert rel(ga + gb, gs) < 1e-6
+    # a slice against the fp64 oracle (closure value and every gradient block through finish)
+    n = 4000
+    Xs, ys = X[70000:70000 + n].contiguous(), y[70000:70000 + n].contiguous()
+    gsl = eng.fwd_grad(Xs, ys, th, w, 0, 50.0, 1.0)
+    assert eng.launch_info()['path'].startswith('single-pass')
+    grad, loss = eng.finish(gsl, 2.0 / ys.numel(), 1.0 / ys.numel(), th, 0.01, 0, 50.0, 1.0)
+    bias = (0.05 * torch.arange(1, NO + 1, dtype=torch.float64))
+    r = OS.loss_grad(Xs.double().cpu(), ys.double().cpu(), [b.double() for b in Bn], [b.double() for b in Bc], bias,
+                     w.double().cpu(), [False, False, False], 0.01)
+    want = torch.cat([t.reshape(-1) for t in r['grad_n'] + r['grad_c']] + [r['dbias'].reshape(-1)])
+    assert abs(loss[1].item() - r['loss']) < 1e-5 * abs(r['loss'])
+    assert rel(grad, want) < 1e-5
