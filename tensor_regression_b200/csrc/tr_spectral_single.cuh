@@ -33,9 +33,6 @@
 #ifndef TRSS_FFMA2
 #define TRSS_FFMA2 0                                   // float window loop: 1 = FFMA2 over element pairs (G values stored twice), 0 = scalar FMAs
 #endif
-#ifndef TRSS_EPI
-#define TRSS_EPI 2                                     // per-sample epilogue: 2 = static (r, q) pairs, loads batched outside uniform branches; 0 = run-time loops over a component's channels through shared memory
-#endif
 // every wait carries a suspend-time hint: a warp that waits for microseconds is parked by the hardware instead of polling
 #define TRSS_WAIT(bar, parity) trf::mbar_wait_hint(bar, parity)
 #define TRSS_NG 8                                      // gradient warps (TRS_WT window rows each)
@@ -307,7 +304,6 @@ __device__ __noinline__ void trss_forward(const SpecSingleArgs<T>* __restrict__ 
                 for (int v = 0; v < VEC; ++v) acc[q][v] = (T)0;
         }
         TRSS_STAMP(j, 3);
-#if TRSS_EPI == 2
         // Channel q belongs to component r when  r < Rn: q == r  (normal)  |  Rn <= r < RT: qb(r) <= q < qb(r) + CC, qb(r) = Rn + (r - Rn) CC
         // — all warp-uniform.  The epilogue runs over STATIC (r, q) pairs guarded by uniform branches that contain arithmetic
         // (and stores) only: every shared-memory load is issued in a batch outside the branches, so no ~100-cycle load latency
@@ -427,115 +423,6 @@ __device__ __noinline__ void trss_forward(const SpecSingleArgs<T>* __restrict__ 
                 }
             }
         }
-#else
-        // window sums -> the stage's da slot (free until this warp releases it; a lane reads back only what it wrote), so
-        // that the channels of a component can be addressed at run time; da overwrites them in place below
-        T* das = c.sDA + (size_t)s * QT * TILE + d0;
-#pragma unroll
-        for (int q = 0; q < QT; ++q) SpecSm<T, VEC>::st(das + (size_t)q * TILE, acc[q]);
-        // m[r][v]: a itself (normal component) or the norm over the component's complex channels
-        T m[QT][VEC];
-#pragma unroll
-        for (int r = 0; r < QT; ++r) {
-            if (r < g.Rn) {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) m[r][v] = acc[r][v];
-            } else if (r < g.RT) {
-                T ss[VEC];
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) ss[v] = (T)0;
-                const T* apq = das + (size_t)(g.Rn + (r - g.Rn) * g.CC) * TILE;
-                for (int cc = 0; cc < g.CC; ++cc) {
-                    T av[VEC];
-                    SpecSm<T, VEC>::ld(apq + (size_t)cc * TILE, av);
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) ss[v] = tr_fma<T>(av[v], av[v], ss[v]);
-                }
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) m[r][v] = trss_norm(ss[v]);
-            } else {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) m[r][v] = (T)0;
-            }
-        }
-        TRSS_STAMP(j, 9);
-        // second contraction: s[r] = sum_d m[d,r] F1[d,r]  (lane partial, then an all-reduce over the warp)
-        T sr[QT];
-#pragma unroll
-        for (int r = 0; r < QT; ++r) {
-            T p = (T)0, f1[VEC];
-            SpecSm<T, VEC>::ld(f1p + (size_t)r * TILE, f1);
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) p = tr_fma<T>(m[r][v], f1[v], p);
-            sr[r] = p;
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1)
-#pragma unroll
-            for (int r = 0; r < QT; ++r) sr[r] += __shfl_xor_sync(TR_FULL, sr[r], off);
-        TRSS_STAMP(j, 10);
-        if (lane <= g.RT) {
-            T uv = (T)1;
-#pragma unroll
-            for (int r = 0; r < QT; ++r) if (r == lane && r < g.RT) uv = sr[r];
-            Up[t * (g.RT + 1) + lane] = uv;
-        }
-        // outputs and residuals: lanes along n; ds[r] = sum_n res[n] F2[n,r]
-        T ds[QT];
-#pragma unroll
-        for (int r = 0; r < QT; ++r) ds[r] = (T)0;
-        T l2 = (T)0;                                                         // sum of this lane's squared residuals (at most 4)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int n = lane + 32 * k;
-            if (n < g.NO) {
-                const T* f2 = c.sF2 + (size_t)n * QT;
-                T yh = c.sB[n];
-#pragma unroll
-                for (int r = 0; r < QT; ++r) yh = tr_fma<T>(sr[r], f2[r], yh);
-                const T rr = yh - yv[k];
-                if (yhatp) yhatp[t * g.NO + n] = yh;
-                resp[t * g.NO + n] = rr;
-                l2 = tr_fma<T>(rr, rr, l2);
-#pragma unroll
-                for (int r = 0; r < QT; ++r) ds[r] = tr_fma<T>(rr, f2[r], ds[r]);
-            }
-        }
-        lossp += l2;
-        if ((left & 15) == 0) { loss += (double)lossp; lossp = (T)0; }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1)
-#pragma unroll
-            for (int r = 0; r < QT; ++r) ds[r] += __shfl_xor_sync(TR_FULL, ds[r], off);
-        TRSS_STAMP(j, 11);
-        // second-mode gradient (registers) and da -> shared memory next to the stage
-#pragma unroll
-        for (int r = 0; r < QT; ++r) {
-            // da of a normal channel r = ds[r] F1[d,r]; of the channels (r, c) of a spectral component = ds[r] F1[d,r] / m[d,r] * a
-            // (0 where the norm is 0: torch.norm's subgradient)
-            T kf[VEC], f1[VEC];
-            SpecSm<T, VEC>::ld(f1p + (size_t)r * TILE, f1);
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                accF[r][v] = tr_fma<T>(ds[r], m[r][v], accF[r][v]);
-                kf[v] = ds[r] * f1[v];
-            }
-            if (r < g.Rn) {
-                SpecSm<T, VEC>::st(das + (size_t)r * TILE, kf);
-            } else if (r < g.RT) {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) kf[v] = m[r][v] > (T)0 ? kf[v] * spec_recip(m[r][v]) : (T)0;
-                T* dq = das + (size_t)(g.Rn + (r - g.Rn) * g.CC) * TILE;
-                for (int cc = 0; cc < g.CC; ++cc) {
-                    T av[VEC];
-                    SpecSm<T, VEC>::ld(dq + (size_t)cc * TILE, av);
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) av[v] *= kf[v];
-                    SpecSm<T, VEC>::st(dq + (size_t)cc * TILE, av);
-                }
-            }
-        }
-#endif
         __syncwarp();                                                        // the lanes' stores, then one release for the warp
         if (lane == 0) trf::mbar_arrive(&c.ready[s]);
         TRSS_STAMP(j, 4);
