@@ -981,7 +981,10 @@ int mn_t(tr_handle* h, const void* X, const long long* y, const void* class_w, l
         // auto: as for the standard model — every cluster has samples to pipeline and X is well beyond L2; rows whose
         // 16-byte chunk count is even make the row-per-thread shared-memory reads bank-conflicted: two-pass is kept
         const bool big = (size_t)N * (size_t)g.D * sizeof(T) >= 3 * h->l2_bytes;
-        if (fp.ok && (h->fused_mode == 1 || (N >= 8LL * fp.NC && big && (fp.IKC & 1)))) {
+        // row pitch in 16-byte chunks: odd = conflict-free row-per-thread reads; 6 = two-way conflicts, still 15 % ahead of the
+        // two-pass kernels (4.5 against 5.3 ms on 16 GB of 100 x 50 x 24); 2 and 4 lose to them (tools/mn_even_pitch.py)
+        const bool pitch_ok = (fp.IKC & 1) || fp.IKC == 6;
+        if (fp.ok && (h->fused_mode == 1 || (N >= 8LL * fp.NC && big && pitch_ok))) {
             h->launches = 0;
             return run_fused_mn<T>(h, (const T*)X, y, (const T*)class_w, N, (const T*)theta, (const T*)w, nn_mask, beta, thr,
                                    fp, gradsum, (T*)P, st);

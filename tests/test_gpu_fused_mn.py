@@ -246,3 +246,23 @@ def test_fused_mn_cfg3_full_size_properties():
     eng.close()
     del X
     torch.cuda.empty_cache()
+
+
+def test_fused_mn_automatic_selection_by_row_pitch():
+    """Automatic selection (X >= 3 x L2): last modes of an odd number of 16-byte chunks, or six (two-way bank conflicts, still
+    ahead of the two-pass kernels), run single-pass; 4 chunks (four-way conflicts) stay on the two-pass kernels."""
+    from tensor_regression_b200 import engine
+    for dims, single in (((100, 50, 24), True), ((100, 50, 20), True), ((100, 50, 16), False)):
+        N = 3000
+        X = torch.randn((N, *dims), device=DEV)
+        eng = engine.Engine(dims, 6, 10, torch.float32, DEV)
+        th = 0.2 * torch.rand(eng.P, device=DEV) - 0.1
+        y = torch.randint(0, 10, (N,), device=DEV)
+        args = (X, y, torch.ones(10, device=DEV), th, torch.ones(6, device=DEV), 0, 50.0, 1.0)
+        one = eng.fwd_grad_mn(*args).clone()
+        assert eng.launch_info()['path'].startswith('single-pass') == single, (dims, eng.launch_info())
+        eng.set_option('fused', 0)
+        two = eng.fwd_grad_mn(*args)
+        assert rel(one, two) < 1e-5
+        eng.close()
+        del X
