@@ -38,6 +38,17 @@
 #include "tr_fused.cuh"
 #include "tr_epi.cuh"
 
+// CTA-local mbarrier waits carry a suspend-time hint (nanoseconds; 0 = plain try_wait polling): the waiting warps are
+// parked instead of spending issue slots on the polling loop.  Measured on one box, two rounds: cfg 3 6.18 -> 6.06 ms,
+// cfg 5 unchanged (25.5 ms); the same hint on k_fused_std costs 11 % (tr_fused.cuh: TRF_WAIT_NS), so it is set here only.
+#ifndef TRM_HINT
+#define TRM_HINT 20000
+#endif
+#if TRM_HINT > 0
+#define TRM_WAIT(bar, ph) trf::mbar_wait_hint(bar, ph, TRM_HINT)
+#else
+#define TRM_WAIT(bar, ph) trf::mbar_wait(bar, ph)
+#endif
 #define TRM_NWF 4                       // forward warps 0-3 (a fifth one on warp 15 was measured: its sub-partition then hosts
                                         // two forward warps and lags, cfg 3 went from 6.8 to 7.0 ms)
 #define TRM_NFT (TRM_NWF * 32)          // forward threads: row of thread t, iteration j = t + j * TRM_NFT
@@ -549,8 +560,8 @@ __device__ __forceinline__ void trm_gradient_role(const FusedMnArgs<T>& a, Fused
     int left = (int)(a.spc < cnt ? a.spc : cnt);
     int chunk_idx = 0;
     for (int i = 0; i < cnt; ++i) {
-        trf::mbar_wait(&ctl->rready[s], ph);                       // v[n,:] of this sample arrived (all lanes wait)
-        if (WITH_S) trf::mbar_wait(&ctl->redA[s], ph);             // acquire the forward warps' t[row,:] stores
+        TRM_WAIT(&ctl->rready[s], ph);                       // v[n,:] of this sample arrived (all lanes wait)
+        if (WITH_S) TRM_WAIT(&ctl->redA[s], ph);             // acquire the forward warps' t[row,:] stores
         __syncwarp();
 #if TRM_TMEM
         if (WITH_S) trf::tmem_fence_after();
@@ -720,9 +731,9 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
         int s = 0;
         unsigned ph = 0;
         for (int i = 0; i < cnt; ++i) {
-            trf::mbar_wait(&ctl->full[s], ph);                     // every lane waits on the barrier itself (tr_fused.cuh)
+            TRM_WAIT(&ctl->full[s], ph);                     // every lane waits on the barrier itself (tr_fused.cuh)
             // slot i & 1 of the partial buffer was last used by sample i - 2: its use number is (i >> 1) - 1
-            if (i >= 2) trf::mbar_wait(&ctl->pfree[i & 1], (unsigned)(((i >> 1) - 1) & 1));
+            if (i >= 2) TRM_WAIT(&ctl->pfree[i & 1], (unsigned)(((i >> 1) - 1) & 1));
             __syncwarp();
             if (tid == 0) TRM_STAMP(1, i);
             const T* xs = reinterpret_cast<const T*>(stageX0 + (size_t)s * a.stage_x_bytes);
@@ -771,7 +782,7 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
             int s = 0;
             unsigned ph = 0;
             for (int j = 0; j < cnt; ++j) {
-                if (j >= NS) trf::mbar_wait(&ctl->empty[s], ph);
+                if (j >= NS) TRM_WAIT(&ctl->empty[s], ph);
                 TRM_STAMP(0, j);
                 trf::mbar_arrive_expect_tx(&ctl->full[s], my_bytes);
                 const unsigned char* sp = reinterpret_cast<const unsigned char*>(src);
@@ -789,7 +800,7 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
         int s = 0, owner = 0, slot = 0;
         unsigned ph = 0;
         for (int i = 0; i < cnt; ++i) {
-            trf::mbar_wait(&ctl->redA[s], ph);
+            TRM_WAIT(&ctl->redA[s], ph);
             __syncwarp();
             if (lane == 0) TRM_STAMP(3, i);
             // the previous use of rready[s] (sample i - NS) has completed: its gradient phase released the stage
@@ -840,7 +851,7 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
             const T omega = sCW[yn];
             if (lane == 0) trf::mbar_arrive_expect_tx(&ctl->cready[slot], (unsigned)(CL * RKS * sizeof(T)));
             if (lane == 0) TRM_STAMP(4, i);
-            trf::mbar_wait(&ctl->cready[slot], phc);
+            TRM_WAIT(&ctl->cready[slot], phc);
             __syncwarp();
             if (lane == 0) TRM_STAMP(5, i);
             // u[n,:] = sum of the CL CTA partials: lane c (and its twin c + 16) holds CTA c's partial, a fixed 4-step
@@ -890,7 +901,7 @@ __global__ void __launch_bounds__(TRM_NT, 1) k_fused_mn(const FusedMnArgs<T> a) 
             int s = 0;
             unsigned ph = 0;
             for (int i = 0; i < cnt; ++i) {
-                trf::mbar_wait(&ctl->full[s], ph);
+                TRM_WAIT(&ctl->full[s], ph);
                 TRM_STAMP(14, i);
                 if (++s == NS) { s = 0; ph ^= 1u; }
             }
