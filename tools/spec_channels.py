@@ -1,3 +1,7 @@
+#!/usr/bin/env python
+"""Spectral fit iteration (tr_spec_fwd_grad) over the channel count Q = rank_normal + rank_spectral * complex columns and the
+dtype: two-pass path against the single-pass kernel on 60 000 samples of 64 x 128 (fp32) / 64 x 64 (fp64) — DESIGN 4e.
+    python tools/spec_channels.py"""
 import sys, torch
 sys.path.insert(0, '.')
 from tensor_regression_b200 import engine
